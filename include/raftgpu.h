@@ -1,0 +1,383 @@
+/*
+ * raftgpu.h -- C-ABI boundary of the B200 batched multi-raft commit-index engine.
+ *
+ * raft-rs (pingcap/raft-rs, crate `raft` 0.6.0 @ 7c21f8d) has no FFI/plugin
+ * interface for this path: the boundary is the Rust method surface of
+ * ProgressTracker / Progress / quorum::{MajorityConfig,JointConfig} /
+ * RaftLog::maybe_commit / Raft::maybe_commit.  Each entry point below names the
+ * reference interface (file:line, relative to the reference checkout) it
+ * replaces; the Rust-side binding a maintainer would add is in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C: pointers and sizes only, no C++/torch types;
+ *  - every function returns an int32_t status (RAFTGPU_OK or a negative
+ *    RAFTGPU_ERR_*); nothing throws or aborts across the boundary.  The hot-path
+ *    functions of the reference are infallible (they return bool / tuples);
+ *    the codes here cover misuse and CUDA failures, plus the two places the
+ *    reference itself errors: StepPeerNotFound (raw_node.rs:402-411) and the
+ *    `fatal!` in RaftLog::commit_to (raft_log.rs:291-298);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    returns RAFTGPU_ERR_NO_DEVICE;
+ *  - `stream` parameters are a cudaStream_t passed as void* (NULL = the arena's
+ *    own compute stream);
+ *  - threading follows the reference (raw_node.rs:284 "RawNode is a
+ *    thread-unsafe Node", raft.rs:292-294 `Raft: Send`): calls that touch ONE
+ *    group may run concurrently for DIFFERENT groups; raftgpu_step* and the
+ *    arena lifecycle calls need exclusive access.
+ *
+ * Data layout in HBM (struct-of-arrays): per-peer columns are
+ * [RAFTGPU_SLOTS][cap] u64 / u8, per-group columns are [cap]; a "group" is one
+ * raft group (one ProgressTracker), a "peer slot" one Progress of that group.
+ */
+#ifndef RAFTGPU_H
+#define RAFTGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAFTGPU_ABI_VERSION 1
+#define RAFTGPU_SLOTS 8 /* peer slots per group (voters + learners, both halves of a joint config) */
+
+/* ---- status codes ------------------------------------------------------- */
+#define RAFTGPU_OK 0
+#define RAFTGPU_ERR_INVALID (-1)        /* bad argument */
+#define RAFTGPU_ERR_CUDA (-2)           /* CUDA runtime error; see raftgpu_last_error */
+#define RAFTGPU_ERR_NOMEM (-3)          /* host / device allocation failed, or arena full */
+#define RAFTGPU_ERR_NO_DEVICE (-4)      /* no CUDA device: there is no CPU fallback */
+#define RAFTGPU_ERR_RANGE (-5)          /* group / peer slot out of range or not allocated */
+#define RAFTGPU_ERR_FULL (-6)           /* staging ring full: call raftgpu_step first */
+#define RAFTGPU_ERR_PEER_NOT_FOUND (-7) /* Error::StepPeerNotFound, raw_node.rs:402-411 */
+#define RAFTGPU_ERR_COMMIT_RANGE (-8)   /* RaftLog::commit_to fatal!, raft_log.rs:291-298 */
+#define RAFTGPU_ERR_BUSY (-9)           /* a step is still in flight on this buffer */
+
+const char *raftgpu_strerror(int32_t status);
+uint32_t raftgpu_abi_version(void);
+
+/* ---- constants shared with the reference -------------------------------- */
+/* ProgressState, src/tracker/state.rs:22-29 */
+#define RAFTGPU_STATE_PROBE 0
+#define RAFTGPU_STATE_REPLICATE 1
+#define RAFTGPU_STATE_SNAPSHOT 2
+/* INVALID_INDEX, src/raft.rs:81 */
+#define RAFTGPU_INVALID_INDEX 0ull
+/* VoteResult, src/quorum.rs:12-20 (declaration order) */
+#define RAFTGPU_VOTE_PENDING 0
+#define RAFTGPU_VOTE_LOST 1
+#define RAFTGPU_VOTE_WON 2
+/* "not a leader": no index is of the current term */
+#define RAFTGPU_NO_TERM_START UINT64_MAX
+
+/* per-peer flag byte (column RAFTGPU_COL_PFLAGS) */
+#define RAFTGPU_PF_STATE_MASK 0x03u
+#define RAFTGPU_PF_PAUSED 0x04u        /* Progress::paused, progress.rs:24 */
+#define RAFTGPU_PF_RECENT_ACTIVE 0x08u /* Progress::recent_active, progress.rs:41 */
+#define RAFTGPU_PF_INS_FULL 0x10u      /* host-maintained copy of Inflights::full(), inflights.rs:54-56 */
+
+/* per-group meta word (column RAFTGPU_COL_META): the tracker::Configuration
+ * (tracker.rs:37-92) as bit masks over peer slots. */
+#define RAFTGPU_META_IN(m) ((m) & 0xffu)            /* voters.incoming, joint.rs:13 */
+#define RAFTGPU_META_OUT(m) (((m) >> 8) & 0xffu)    /* voters.outgoing, joint.rs:14 */
+#define RAFTGPU_META_LEARN(m) (((m) >> 16) & 0xffu) /* learners | learners_next */
+#define RAFTGPU_META_SELF(m) (((m) >> 24) & 0x7u)   /* slot of Raft::id */
+#define RAFTGPU_META_HAS_SELF 0x08000000u
+#define RAFTGPU_META_GROUP_COMMIT 0x10000000u       /* ProgressTracker::group_commit, tracker.rs:207 */
+
+/* ---- plain data types --------------------------------------------------- */
+typedef struct raftgpu_arena raftgpu_arena; /* opaque; owns all device + pinned memory */
+
+/* One Progress (src/tracker/progress.rs:8-56) minus `ins` (Inflights stays host-side). */
+typedef struct {
+    uint64_t matched;                  /* progress.rs:10 */
+    uint64_t next_idx;                 /* progress.rs:12 */
+    uint64_t pending_snapshot;         /* progress.rs:31 */
+    uint64_t pending_request_snapshot; /* progress.rs:35 */
+    uint64_t commit_group_id;          /* progress.rs:52 */
+    uint64_t committed_index;          /* progress.rs:55 */
+    uint8_t state;                     /* progress.rs:22 */
+    uint8_t paused;                    /* progress.rs:25 */
+    uint8_t recent_active;             /* progress.rs:41 */
+    uint8_t ins_full;                  /* Inflights::full() as last reported by the host */
+    uint8_t present;                   /* 1 when the slot holds a Progress */
+    uint8_t reserved[3];
+} raftgpu_progress;
+
+/* Per-group log / commit bookkeeping: the part of RaftLog (raft_log.rs:33-59)
+ * RaftLog::maybe_commit needs, in range form (DESIGN.md "term test"). */
+typedef struct {
+    uint32_t meta;
+    uint32_t reserved;
+    uint64_t committed;  /* RaftLog::committed, raft_log.rs:45 */
+    uint64_t term_start; /* first index whose entry carries the leader's current term */
+    uint64_t last_index; /* RaftLog::last_index() */
+} raftgpu_group_state;
+
+/* One MsgAppendResponse as handle_append_response consumes it (raft.rs:1559-1775,
+ * eraftpb.proto:71-92): 24 bytes.  A REJECT record is followed by ONE EXT record
+ * with the same group/peer_slot whose `index` is next_probe_index (m.reject_hint,
+ * or find_conflict_by_term(..).0 when m.log_term > 0 -- that lookup needs the
+ * leader's log and is done by the caller, raft.rs:1560-1661) and whose `commit`
+ * is m.request_snapshot. */
+typedef struct {
+    uint32_t group;     /* group slot */
+    uint8_t peer_slot;  /* slot of m.from */
+    uint8_t flags;      /* RAFTGPU_REC_* */
+    uint16_t reserved;
+    uint64_t index;     /* m.index */
+    uint64_t commit;    /* m.commit */
+} raftgpu_append_resp;
+#define RAFTGPU_REC_REJECT 0x01u /* m.reject */
+/* Leader-local record (not a message): `commit`, when non-zero, is the new
+ * last_index after Raft::append_entry (raft.rs:974-991); `index` is the newly
+ * persisted index of Raft::on_persist_entries (raft.rs:994-1016), which runs
+ * prs[self].maybe_update(index); peer_slot is the leader's own slot. */
+#define RAFTGPU_REC_LOCAL 0x02u
+#define RAFTGPU_REC_EXT 0x80u    /* extension record of the preceding REJECT */
+
+/* per-record result byte */
+#define RAFTGPU_RES_OK 0x01u          /* maybe_update / maybe_decr_to returned true */
+#define RAFTGPU_RES_OLD_PAUSED 0x02u  /* pr.is_paused() before maybe_update, raft.rs:1724 */
+#define RAFTGPU_RES_NO_PROGRESS 0x04u /* prs.get_mut(m.from) == None, raft.rs:1663-1673 */
+#define RAFTGPU_RES_SEND 0x08u        /* reject path reached self.send_append(m.from), raft.rs:1719 */
+
+/* column ids for bulk IO */
+enum {
+    RAFTGPU_COL_MATCHED = 0,              /* u64 [SLOTS][cap] */
+    RAFTGPU_COL_NEXT_IDX = 1,             /* u64 [SLOTS][cap] */
+    RAFTGPU_COL_PEER_COMMITTED = 2,       /* u64 [SLOTS][cap]  Progress::committed_index */
+    RAFTGPU_COL_PENDING_SNAPSHOT = 3,     /* u64 [SLOTS][cap] */
+    RAFTGPU_COL_PENDING_REQ_SNAPSHOT = 4, /* u64 [SLOTS][cap] */
+    RAFTGPU_COL_COMMIT_GROUP_ID = 5,      /* u64 [SLOTS][cap] */
+    RAFTGPU_COL_PFLAGS = 6,               /* u8  [SLOTS][cap] */
+    RAFTGPU_COL_VOTES = 7,                /* u8  [SLOTS][cap]  0 missing, 1 no, 2 yes */
+    RAFTGPU_COL_META = 8,                 /* u32 [cap] */
+    RAFTGPU_COL_COMMITTED = 9,            /* u64 [cap] */
+    RAFTGPU_COL_TERM_START = 10,          /* u64 [cap] */
+    RAFTGPU_COL_LAST_INDEX = 11,          /* u64 [cap] */
+    RAFTGPU_COL__COUNT = 12
+};
+
+typedef struct {
+    uint32_t abi_version;
+    int32_t device;
+    uint32_t cap;          /* max groups */
+    uint32_t slots;        /* RAFTGPU_SLOTS */
+    uint32_t n_alloc;      /* groups currently allocated */
+    uint32_t hi;           /* allocated groups live in [0, hi) */
+    uint32_t sm_count;
+    uint32_t reserved;
+    uint64_t l2_bytes;
+    uint64_t device_bytes; /* HBM held by this arena */
+    uint64_t pinned_bytes;
+} raftgpu_info;
+
+/* monotonically increasing device-side counters (what the multi-GPU run gathers) */
+typedef struct {
+    uint64_t recomputes;      /* per-group Raft::maybe_commit evaluations */
+    uint64_t advanced;        /* of which advanced `committed` */
+    uint64_t records;         /* AppendResponse records applied */
+    uint64_t updates;         /* maybe_update returned true */
+    uint64_t rejects;         /* reject records seen */
+    uint64_t decrements;      /* maybe_decr_to returned true */
+    uint64_t no_progress;     /* records for an unknown responder */
+    uint64_t votes_tallied;   /* per-group vote_result evaluations */
+} raftgpu_counters;
+
+typedef struct {
+    uint64_t n_records;  /* records submitted in this step (EXT records included) */
+    uint32_t n_waves;    /* kernel waves the records were split into (see raftgpu_enqueue_append_resp) */
+    uint32_t n_groups;   /* groups recomputed */
+    uint64_t n_advanced; /* groups whose committed index advanced */
+} raftgpu_step_result;
+
+/* ---- arena lifecycle ---------------------------------------------------- */
+
+/* ProgressTracker::with_capacity (tracker.rs:217-236) for `max_groups` trackers
+ * at once: allocates every column in HBM plus the pinned staging buffers.
+ * slots_per_group must be RAFTGPU_SLOTS.  ring_records = capacity of each of
+ * the `n_rings` host staging rings (0 = default). */
+int32_t raftgpu_arena_create(int32_t device, uint32_t max_groups, uint32_t slots_per_group,
+                             uint32_t n_rings, uint32_t ring_records, raftgpu_arena **out);
+int32_t raftgpu_arena_destroy(raftgpu_arena *arena);
+int32_t raftgpu_arena_info(const raftgpu_arena *arena, raftgpu_info *out);
+/* Last CUDA / argument error text for this arena (never NULL). */
+const char *raftgpu_last_error(const raftgpu_arena *arena);
+
+/* ---- group lifecycle (control plane; synchronous, small copies) --------- */
+
+/* Raft::new (raft.rs:318-400) / drop: one slot per ProgressTracker. */
+int32_t raftgpu_group_alloc(raftgpu_arena *arena, uint32_t *out_group);
+int32_t raftgpu_group_alloc_range(raftgpu_arena *arena, uint32_t n, uint32_t *out_first);
+int32_t raftgpu_group_free(raftgpu_arena *arena, uint32_t group);
+
+/* ProgressTracker::apply_conf (tracker.rs:380-397) / confchange::restore
+ * (confchange/restore.rs:91-107): replace the Configuration.  Slots that become
+ * present get Progress::new(next_idx, ..) with recent_active = true
+ * (tracker.rs:385-390); slots that disappear are removed (tracker.rs:392-394). */
+int32_t raftgpu_group_set_conf(raftgpu_arena *arena, uint32_t group, uint32_t incoming_mask,
+                               uint32_t outgoing_mask, uint32_t learner_mask, int32_t self_slot,
+                               uint64_t next_idx);
+
+/* Raft::reset (raft.rs:942-971) followed by become_leader's bookkeeping
+ * (raft.rs:1162-1203): every Progress is reset(last_index + 1); the self slot
+ * gets matched = persisted, committed_index = committed (raft.rs:964-970).
+ * term_start = RAFTGPU_NO_TERM_START for a non-leader. */
+int32_t raftgpu_group_reset(raftgpu_arena *arena, uint32_t group, uint64_t term_start,
+                            uint64_t last_index, uint64_t committed, uint64_t persisted);
+
+/* The tracker side of Raft::become_leader (raft.rs:1162-1203), after
+ * raftgpu_group_reset: prs[self].become_replicate() (raft.rs:1180), then the
+ * empty entry of the new term is appended (raft.rs:1192), so last_index += 1 and
+ * term_start = that index. */
+int32_t raftgpu_group_become_leader(raftgpu_arena *arena, uint32_t group);
+
+/* Raft::append_entry (raft.rs:974-991): the log grew; entries of the current
+ * term are [term_start, last_index]. */
+int32_t raftgpu_group_set_log_bounds(raftgpu_arena *arena, uint32_t group, uint64_t term_start,
+                                     uint64_t last_index);
+/* RaftLog::commit_to (raft_log.rs:286-300): never decreases; RAFTGPU_ERR_COMMIT_RANGE
+ * where the reference `fatal!`s (to_commit > last_index). */
+int32_t raftgpu_group_commit_to(raftgpu_arena *arena, uint32_t group, uint64_t to_commit);
+int32_t raftgpu_group_get(raftgpu_arena *arena, uint32_t group, raftgpu_group_state *out);
+
+/* ProgressTracker::get / get_mut (tracker.rs:267-275): Progress has pub fields,
+ * so the Rust shim reads a copy and writes it back. */
+int32_t raftgpu_progress_get(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot,
+                             raftgpu_progress *out);
+int32_t raftgpu_progress_set(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot,
+                             const raftgpu_progress *in);
+
+/* ProgressTracker::enable_group_commit (tracker.rs:238-241) and
+ * Raft::assign_commit_groups / clear_commit_group (raft.rs:531-552). */
+int32_t raftgpu_set_group_commit(raftgpu_arena *arena, uint32_t group, int32_t enable);
+int32_t raftgpu_assign_commit_group(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot,
+                                    uint64_t commit_group_id);
+
+/* Bulk column IO for [first_group, first_group + n) of one column (peer_slot is
+ * ignored for per-group columns): restoring / inspecting many groups at once. */
+int32_t raftgpu_column_write(raftgpu_arena *arena, int32_t column, uint32_t peer_slot,
+                             uint32_t first_group, uint32_t n, const void *host_src);
+int32_t raftgpu_column_read(raftgpu_arena *arena, int32_t column, uint32_t peer_slot,
+                            uint32_t first_group, uint32_t n, void *host_dst);
+
+/* ---- the hot path ------------------------------------------------------- */
+
+/* ProgressTracker::maximal_committed_index (tracker.rs:294-298) for one group:
+ * JointConfig::committed_index (joint.rs:47-51) over MajorityConfig::committed_index
+ * (majority.rs:70-124).  Runs the batched kernel on a 1-group range. */
+int32_t raftgpu_maximal_committed_index(raftgpu_arena *arena, uint32_t group, uint64_t *out_index,
+                                        int32_t *out_use_group_commit);
+
+/* Raft::maybe_commit (raft.rs:893-904) for one group: maximal_committed_index ->
+ * RaftLog::maybe_commit (raft_log.rs:487-499) -> prs[self].update_committed. */
+int32_t raftgpu_maybe_commit(raftgpu_arena *arena, uint32_t group, int32_t *out_advanced,
+                             uint64_t *out_committed);
+
+/* Batched Raft::maybe_commit over groups [first, first + n): ONE kernel pass.
+ * Asynchronous on `stream`.  d_adv_bitmap (device, u32 words indexed by
+ * group >> 5 from group 0; may be NULL) gets bit g set iff group g advanced;
+ * d_commit_out (device u64 [cap], may be NULL) gets the new committed index of
+ * advanced groups; d_mci_out / d_gc_out (may be NULL) get maximal_committed_index
+ * for every group. */
+int32_t raftgpu_recompute(raftgpu_arena *arena, void *stream, uint32_t first, uint32_t n,
+                          uint32_t *d_adv_bitmap, uint64_t *d_commit_out, uint64_t *d_mci_out,
+                          uint8_t *d_gc_out);
+
+/* Batched handle_append_response prefix (raft.rs:1663-1743: recent_active,
+ * update_committed, maybe_decr_to | maybe_update + state transition) over `n`
+ * records ALREADY IN HBM.  Precondition: at most one non-EXT record per
+ * (group, peer_slot) in the range -- one "wave"; raftgpu_enqueue_append_resp
+ * builds waves for arbitrary streams.  d_results (device, n bytes) may be NULL.
+ * Asynchronous on `stream`. */
+int32_t raftgpu_apply_device(raftgpu_arena *arena, void *stream,
+                             const raftgpu_append_resp *d_records, uint64_t n, uint8_t *d_results);
+
+/* Stage host records for the next step (RawNode::step -> Raft::step ->
+ * handle_append_response, raw_node.rs:402-411 / raft.rs:1559).  Records for one
+ * (group, peer) keep their arrival order: a second record for a cell that
+ * already has one in the pending step is placed in a later wave.  `ring`
+ * selects one of the arena's staging rings; different threads use different
+ * rings (and, as in the reference, different groups). */
+int32_t raftgpu_enqueue_append_resp(raftgpu_arena *arena, uint32_t ring,
+                                    const raftgpu_append_resp *records, uint64_t n);
+
+/* One batched step over everything enqueued: H2D of the staged records, the
+ * apply kernel per wave, ONE recompute pass over all allocated groups, D2H of
+ * the results.  raftgpu_step = raftgpu_step_begin + raftgpu_step_wait.  Between
+ * begin and wait the caller may already enqueue the NEXT step's records (double
+ * buffered). */
+#define RAFTGPU_STEP_READ_COMMITTED 0x1u /* also copy back the new committed index of advanced groups */
+#define RAFTGPU_STEP_READ_RESULTS 0x2u   /* also copy back the per-record result bytes */
+int32_t raftgpu_step_begin(raftgpu_arena *arena, uint32_t flags);
+int32_t raftgpu_step_wait(raftgpu_arena *arena, raftgpu_step_result *out);
+int32_t raftgpu_step(raftgpu_arena *arena, uint32_t flags, raftgpu_step_result *out);
+
+/* Results of the last completed step, in arena-owned pinned memory, valid until
+ * the next raftgpu_step_wait: adv_bitmap has bit g set iff group g advanced
+ * (LightReady.commit_index, raw_node.rs:643-650); committed[g] is meaningful
+ * for advanced groups when RAFTGPU_STEP_READ_COMMITTED was set; record_results
+ * holds one byte per record in submission order (wave 0 rings in ring order,
+ * then later waves) when RAFTGPU_STEP_READ_RESULTS was set. */
+int32_t raftgpu_step_results(raftgpu_arena *arena, const uint32_t **adv_bitmap,
+                             const uint64_t **committed, const uint8_t **record_results);
+
+/* ---- votes ----------------------------------------- */
+
+/* ProgressTracker::reset_votes / record_vote (tracker.rs:301-310). */
+int32_t raftgpu_reset_votes(raftgpu_arena *arena, uint32_t group);
+int32_t raftgpu_record_vote(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot, int32_t vote);
+/* Batched ProgressTracker::tally_votes (tracker.rs:313-340) over [first, first+n):
+ * d_out[g] = VoteResult | granted << 8 | rejected << 16.  Asynchronous. */
+int32_t raftgpu_tally_votes(raftgpu_arena *arena, void *stream, uint32_t first, uint32_t n,
+                            uint32_t *d_out);
+/* Single-group form (synchronous). */
+int32_t raftgpu_vote_result(raftgpu_arena *arena, uint32_t group, int32_t *out_result,
+                            uint32_t *out_granted, uint32_t *out_rejected);
+
+/* ---- plumbing ------------------------------------------------------------ */
+int32_t raftgpu_counters_read(raftgpu_arena *arena, raftgpu_counters *out);
+int32_t raftgpu_synchronize(raftgpu_arena *arena);
+/* Device scratch owned by the arena (for callers that keep record batches in
+ * HBM, e.g. the bench's device-resident leg). */
+int32_t raftgpu_device_alloc(raftgpu_arena *arena, uint64_t bytes, void **out_device_ptr);
+int32_t raftgpu_device_free(raftgpu_arena *arena, void *device_ptr);
+int32_t raftgpu_memcpy_h2d(raftgpu_arena *arena, void *device_dst, const void *host_src,
+                           uint64_t bytes);
+int32_t raftgpu_memcpy_d2h(raftgpu_arena *arena, void *host_dst, const void *device_src,
+                           uint64_t bytes);
+
+/* ---- synthetic workload; deterministic, splitmix64 -------- */
+/* Fills host columns for groups [0, n) of a K-peer configuration (`joint` != 0:
+ * 7 slots, incoming = {0..4}, outgoing = {0,1,2,5,6}).  Arrays are [SLOTS][cap]
+ * / [cap] like the arena's columns. */
+typedef struct {
+    uint32_t cap;
+    uint32_t n_groups;
+    /* initial arena columns: written by raftgpu_synth_init only */
+    uint64_t *matched, *next_idx, *peer_committed;
+    uint8_t *pflags;
+    uint32_t *meta;
+    uint64_t *committed, *term_start, *last_index, *term;
+    /* follower simulation, advanced by raftgpu_synth_round */
+    uint64_t *sim_acked; /* [SLOTS][cap] last index each peer acknowledged */
+    uint64_t *sim_last;  /* [cap] the leader's last_index */
+    uint8_t *sim_flags;  /* [SLOTS][cap] bit 0: the peer's previous response was a reject */
+} raftgpu_synth_columns;
+int32_t raftgpu_synth_init(const raftgpu_synth_columns *cols, uint64_t seed, uint32_t k_peers,
+                           int32_t joint);
+/* Generates ONE round for all groups from the follower simulation: 1 + r mod (K-1)
+ * distinct followers answer (88 % accept, 10 % stale accept, 2 % reject = REJECT +
+ * EXT), then one RAFTGPU_REC_LOCAL record advances the leader's log / persisted
+ * index.  At most one record per (group, peer): a round is one wave.  Records are
+ * in group order.  Returns the count in *out_n, or RAFTGPU_ERR_FULL. */
+int32_t raftgpu_synth_round(const raftgpu_synth_columns *cols, uint64_t seed, uint32_t round,
+                            uint32_t k_peers, raftgpu_append_resp *out, uint64_t max_records,
+                            uint64_t *out_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAFTGPU_H */

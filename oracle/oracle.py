@@ -25,7 +25,7 @@ STATE_PROBE, STATE_REPLICATE, STATE_SNAPSHOT = 0, 1, 2
 
 PF_STATE_MASK, PF_PAUSED, PF_RECENT_ACTIVE, PF_INS_FULL = 0x03, 0x04, 0x08, 0x10
 META_HAS_SELF, META_GROUP_COMMIT = 0x08000000, 0x10000000
-REC_REJECT, REC_EXT = 0x01, 0x80
+REC_REJECT, REC_LOCAL, REC_EXT = 0x01, 0x02, 0x80
 RES_OK, RES_OLD_PAUSED, RES_NO_PROGRESS, RES_SEND = 0x01, 0x02, 0x04, 0x08
 
 APPEND_RESP_DTYPE = np.dtype(

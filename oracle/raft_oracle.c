@@ -463,6 +463,25 @@ uint8_t ro_arena_handle_append_response(ro_arena_view *a, const ro_append_resp *
     ro_progress pr;
     load_progress(a, slot, g, &pr);
     uint8_t res = 0;
+
+    if (rec->flags & RO_REC_LOCAL) {
+        /* raft.rs:974-991 append_entry: the leader's log grew to `commit` */
+        if (rec->commit != 0) a->last_index[g] = rec->commit;
+        /* raft.rs:1010-1014 on_persist_entries on a leader:
+         * pr.maybe_update(index) && self.maybe_commit() */
+        if (ro_progress_maybe_update(&pr, rec->index)) {
+            res |= RO_RES_OK;
+            store_progress(a, slot, g, &pr);
+            if (per_message_commit) {
+                int adv = ro_arena_maybe_commit(a, g);
+                if (advanced) *advanced = adv;
+            }
+        } else {
+            store_progress(a, slot, g, &pr);
+        }
+        return res;
+    }
+
     pr.recent_active = 1;                           /* :1674 */
     ro_progress_update_committed(&pr, rec->commit); /* :1677 */
 

@@ -188,6 +188,11 @@ typedef struct {
     uint64_t commit;
 } ro_append_resp;
 #define RO_REC_REJECT 0x01u
+/* leader-local record: `commit` (when non-zero) is the new last_index after
+ * Raft::append_entry (raft.rs:974-991), `index` the newly persisted index fed to
+ * on_persist_entries (raft.rs:994-1016: prs[self].maybe_update(index) &&
+ * maybe_commit()); peer_slot is the leader's own slot. */
+#define RO_REC_LOCAL 0x02u
 #define RO_REC_EXT 0x80u
 
 /* per-record result byte */

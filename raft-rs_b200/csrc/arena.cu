@@ -1,0 +1,934 @@
+// arena.cu -- host side of the engine: the HBM arena, staging rings, streams and
+// the extern "C" surface declared in include/raftgpu.h.
+//
+// The arena owns every byte of device and pinned memory.  There is no CPU
+// compute path: without a CUDA device arena creation fails with
+// RAFTGPU_ERR_NO_DEVICE and nothing else can be called.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace raftgpu;
+
+namespace {
+
+constexpr int kNumSets = 2;  // double-buffered staging
+
+struct StagingSet {
+    // host (pinned)
+    raftgpu_append_resp *h_recs = nullptr;  // [n_rings][ring_records] wave-0 records
+    raftgpu_append_resp *h_overflow = nullptr;  // later waves, packed at submit time
+    uint32_t *h_adv_bitmap = nullptr;
+    uint64_t *h_committed = nullptr;
+    uint8_t *h_results = nullptr;
+    uint32_t *h_step_adv = nullptr;
+    // host (pageable)
+    std::vector<uint64_t> ring_count;
+    uint8_t *touched = nullptr;  // [cap] one bit per peer slot: cell has a record in wave 0
+    std::mutex overflow_mu;
+    std::unordered_map<uint64_t, uint32_t> overflow_depth;       // cell -> waves used beyond 0
+    std::vector<std::vector<raftgpu_append_resp>> overflow_waves;  // wave w+1 records
+    // device
+    raftgpu_append_resp *d_recs = nullptr;
+    uint32_t *d_adv_bitmap = nullptr;
+    uint64_t *d_commit_out = nullptr;
+    uint8_t *d_results = nullptr;
+    uint32_t *d_step_adv = nullptr;
+    // sync
+    cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
+    bool in_flight = false;
+    bool dirty = false;  // touched[] has bits set
+    uint32_t flags = 0;
+    raftgpu_step_result result{};
+};
+
+}  // namespace
+
+struct raftgpu_arena {
+    int device = 0;
+    uint32_t cap = 0;
+    uint32_t n_rings = 0;
+    uint32_t ring_records = 0;
+    uint64_t overflow_records = 0;
+    Columns cols{};
+    unsigned long long *d_counters = nullptr;
+    void *d_scratch = nullptr;  // 256 B for single-group queries
+    void *h_scratch = nullptr;  // pinned mirror
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    StagingSet sets[kNumSets];
+    int fill = 0;        // set currently being filled by enqueue
+    int last_done = -1;  // set whose results raftgpu_step_results exposes
+    int pending = -1;    // set submitted by step_begin and not yet waited for
+    // group allocation
+    std::mutex alloc_mu;
+    std::vector<uint32_t> free_list;
+    std::vector<uint8_t> allocated;
+    std::vector<uint32_t> h_meta;  // host mirror of the meta column
+    uint32_t hi = 0, n_alloc = 0;
+    // info
+    int sm_count = 0;
+    uint64_t l2_bytes = 0, device_bytes = 0, pinned_bytes = 0;
+    std::string last_error;
+    std::vector<void *> user_allocs;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int32_t fail(raftgpu_arena *a, int32_t code, const std::string &msg) {
+    if (a) a->last_error = msg;
+    return code;
+}
+
+#define CK(a, call)                                                                          \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            return fail((a), RAFTGPU_ERR_CUDA,                                               \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+        }                                                                                    \
+    } while (0)
+
+#define CKL(a)                                                                               \
+    do {                                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                 \
+        if (e_ != cudaSuccess)                                                               \
+            return fail((a), RAFTGPU_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int32_t dev_alloc(raftgpu_arena *a, T **p, size_t count, bool zero = true) {
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), bytes ? bytes : 1);
+    if (e != cudaSuccess)
+        return fail(a, e == cudaErrorMemoryAllocation ? RAFTGPU_ERR_NOMEM : RAFTGPU_ERR_CUDA,
+                    std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    a->device_bytes += bytes;
+    if (zero) CK(a, cudaMemset(*p, 0, bytes ? bytes : 1));
+    return RAFTGPU_OK;
+}
+
+template <typename T>
+int32_t pin_alloc(raftgpu_arena *a, T **p, size_t count) {
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(p), bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess)
+        return fail(a, RAFTGPU_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    a->pinned_bytes += bytes;
+    memset(*p, 0, bytes);
+    return RAFTGPU_OK;
+}
+
+inline bool group_ok(const raftgpu_arena *a, uint32_t g) {
+    return g < a->cap && a->allocated[g];
+}
+
+inline uint32_t present_mask(uint32_t meta) {
+    return RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
+}
+
+inline cudaStream_t pick_stream(raftgpu_arena *a, void *stream) {
+    return stream ? static_cast<cudaStream_t>(stream) : a->s_compute;
+}
+
+inline uint32_t div_up(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
+
+int32_t launch_recompute(raftgpu_arena *a, cudaStream_t st, uint32_t first, uint32_t n,
+                         uint32_t *d_adv, uint64_t *d_commit, uint64_t *d_mci, uint8_t *d_gc,
+                         uint32_t *d_step_adv) {
+    if (n == 0) return RAFTGPU_OK;
+    const uint32_t base = first & ~31u;
+    const uint64_t threads = static_cast<uint64_t>(first - base) + n;
+    recompute_kernel<<<div_up(threads, 256), 256, 0, st>>>(a->cols, first, n, d_adv, d_commit, d_mci,
+                                                          d_gc, d_step_adv, a->d_counters);
+    CKL(a);
+    return RAFTGPU_OK;
+}
+
+int32_t launch_apply(raftgpu_arena *a, cudaStream_t st, const raftgpu_append_resp *d_recs,
+                     uint64_t n, uint8_t *d_results) {
+    if (n == 0) return RAFTGPU_OK;
+    apply_kernel<<<div_up(n, 256), 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
+    CKL(a);
+    return RAFTGPU_OK;
+}
+
+void free_set(StagingSet &s) {
+    cudaFreeHost(s.h_recs);
+    cudaFreeHost(s.h_overflow);
+    cudaFreeHost(s.h_adv_bitmap);
+    cudaFreeHost(s.h_committed);
+    cudaFreeHost(s.h_results);
+    cudaFreeHost(s.h_step_adv);
+    free(s.touched);
+    cudaFree(s.d_recs);
+    cudaFree(s.d_adv_bitmap);
+    cudaFree(s.d_commit_out);
+    cudaFree(s.d_results);
+    cudaFree(s.d_step_adv);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_compute) cudaEventDestroy(s.ev_compute);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+}
+
+void destroy(raftgpu_arena *a) {
+    if (!a) return;
+    cudaSetDevice(a->device);
+    cudaDeviceSynchronize();
+    Columns &c = a->cols;
+    cudaFree(c.matched);
+    cudaFree(c.next_idx);
+    cudaFree(c.peer_committed);
+    cudaFree(c.pending_snapshot);
+    cudaFree(c.pending_req_snapshot);
+    cudaFree(c.commit_group_id);
+    cudaFree(c.pflags);
+    cudaFree(c.votes);
+    cudaFree(c.meta);
+    cudaFree(c.committed);
+    cudaFree(c.term_start);
+    cudaFree(c.last_index);
+    cudaFree(a->d_counters);
+    cudaFree(a->d_scratch);
+    cudaFreeHost(a->h_scratch);
+    for (void *p : a->user_allocs) cudaFree(p);
+    for (auto &s : a->sets) free_set(s);
+    if (a->s_compute) cudaStreamDestroy(a->s_compute);
+    if (a->s_h2d) cudaStreamDestroy(a->s_h2d);
+    if (a->s_d2h) cudaStreamDestroy(a->s_d2h);
+    delete a;
+}
+
+int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_rings,
+               uint32_t ring_records, raftgpu_arena **out) {
+    if (!out || max_groups == 0 || slots != RAFTGPU_SLOTS) return RAFTGPU_ERR_INVALID;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return RAFTGPU_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n_dev) return RAFTGPU_ERR_INVALID;
+    raftgpu_arena *a = new (std::nothrow) raftgpu_arena();
+    if (!a) return RAFTGPU_ERR_NOMEM;
+    a->device = device;
+    // pad the column stride so every column (and every slot row of it) is 128-byte aligned
+    a->cap = (max_groups + 127u) & ~127u;
+    a->n_rings = n_rings ? n_rings : 16;
+    a->ring_records =
+        ring_records ? ring_records
+                     : static_cast<uint32_t>(std::max<uint64_t>(4096, (5ull * a->cap) / a->n_rings));
+    a->overflow_records = std::max<uint64_t>(4096, a->cap / 4);
+    int32_t rc = RAFTGPU_OK;
+    auto bail = [&](int32_t code) {
+        g_create_error = a->last_error;
+        destroy(a);
+        return code;
+    };
+#define TRY(x)                       \
+    do {                             \
+        rc = (x);                    \
+        if (rc != RAFTGPU_OK) return bail(rc); \
+    } while (0)
+#define TRYC(call)                                                                   \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            a->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+            return bail(RAFTGPU_ERR_CUDA);                                           \
+        }                                                                            \
+    } while (0)
+    TRYC(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    TRYC(cudaGetDeviceProperties(&prop, device));
+    a->sm_count = prop.multiProcessorCount;
+    a->l2_bytes = static_cast<uint64_t>(prop.l2CacheSize);
+    TRYC(cudaStreamCreateWithFlags(&a->s_compute, cudaStreamNonBlocking));
+    TRYC(cudaStreamCreateWithFlags(&a->s_h2d, cudaStreamNonBlocking));
+    TRYC(cudaStreamCreateWithFlags(&a->s_d2h, cudaStreamNonBlocking));
+
+    const size_t cells = static_cast<size_t>(kSlots) * a->cap;
+    Columns &c = a->cols;
+    c.cap = a->cap;
+    TRY(dev_alloc(a, &c.matched, cells));
+    TRY(dev_alloc(a, &c.next_idx, cells));
+    TRY(dev_alloc(a, &c.peer_committed, cells));
+    TRY(dev_alloc(a, &c.pending_snapshot, cells));
+    TRY(dev_alloc(a, &c.pending_req_snapshot, cells));
+    TRY(dev_alloc(a, &c.commit_group_id, cells));
+    TRY(dev_alloc(a, &c.pflags, cells));
+    TRY(dev_alloc(a, &c.votes, cells));
+    TRY(dev_alloc(a, &c.meta, a->cap));
+    TRY(dev_alloc(a, &c.committed, a->cap));
+    TRY(dev_alloc(a, &c.term_start, a->cap));
+    TRY(dev_alloc(a, &c.last_index, a->cap));
+    TRYC(cudaMemset(c.term_start, 0xff, sizeof(uint64_t) * a->cap));  // RAFTGPU_NO_TERM_START
+    TRY(dev_alloc(a, &a->d_counters, kCntCount));
+    TRY(dev_alloc(a, reinterpret_cast<uint8_t **>(&a->d_scratch), 256));
+    TRY(pin_alloc(a, reinterpret_cast<uint8_t **>(&a->h_scratch), 256));
+
+    const uint64_t ring_total = static_cast<uint64_t>(a->n_rings) * a->ring_records;
+    const uint64_t rec_total = ring_total + a->overflow_records;
+    for (auto &s : a->sets) {
+        TRY(pin_alloc(a, &s.h_recs, ring_total));
+        TRY(pin_alloc(a, &s.h_overflow, a->overflow_records));
+        TRY(pin_alloc(a, &s.h_adv_bitmap, a->cap / 32));
+        TRY(pin_alloc(a, &s.h_committed, a->cap));
+        TRY(pin_alloc(a, &s.h_results, rec_total));
+        TRY(pin_alloc(a, &s.h_step_adv, 4));
+        s.ring_count.assign(a->n_rings, 0);
+        s.touched = static_cast<uint8_t *>(calloc(a->cap, 1));
+        if (!s.touched) return bail(RAFTGPU_ERR_NOMEM);
+        TRY(dev_alloc(a, &s.d_recs, rec_total, false));
+        TRY(dev_alloc(a, &s.d_adv_bitmap, a->cap / 32));
+        TRY(dev_alloc(a, &s.d_commit_out, a->cap));
+        TRY(dev_alloc(a, &s.d_results, rec_total));
+        TRY(dev_alloc(a, &s.d_step_adv, 4));
+        TRYC(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        TRYC(cudaEventCreateWithFlags(&s.ev_compute, cudaEventDisableTiming));
+        TRYC(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    a->allocated.assign(a->cap, 0);
+    a->h_meta.assign(a->cap, 0);
+    TRYC(cudaDeviceSynchronize());
+#undef TRY
+#undef TRYC
+    // groups beyond max_groups exist only as padding of the column stride
+    a->cap = a->cap;  // stride
+    a->allocated.resize(a->cap);
+    *out = a;
+    (void)max_groups;
+    return RAFTGPU_OK;
+}
+
+// Single-thread control-plane kernel + sync on the compute stream.
+template <typename F>
+int32_t sync_op(raftgpu_arena *a, F &&launch) {
+    CK(a, cudaSetDevice(a->device));
+    launch(a->s_compute);
+    CKL(a);
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    return RAFTGPU_OK;
+}
+
+struct ColumnDesc {
+    void *base;
+    size_t elem;
+    bool per_peer;
+};
+
+bool column_desc(raftgpu_arena *a, int32_t col, ColumnDesc *d) {
+    Columns &c = a->cols;
+    switch (col) {
+    case RAFTGPU_COL_MATCHED: *d = {c.matched, 8, true}; return true;
+    case RAFTGPU_COL_NEXT_IDX: *d = {c.next_idx, 8, true}; return true;
+    case RAFTGPU_COL_PEER_COMMITTED: *d = {c.peer_committed, 8, true}; return true;
+    case RAFTGPU_COL_PENDING_SNAPSHOT: *d = {c.pending_snapshot, 8, true}; return true;
+    case RAFTGPU_COL_PENDING_REQ_SNAPSHOT: *d = {c.pending_req_snapshot, 8, true}; return true;
+    case RAFTGPU_COL_COMMIT_GROUP_ID: *d = {c.commit_group_id, 8, true}; return true;
+    case RAFTGPU_COL_PFLAGS: *d = {c.pflags, 1, true}; return true;
+    case RAFTGPU_COL_VOTES: *d = {c.votes, 1, true}; return true;
+    case RAFTGPU_COL_META: *d = {c.meta, 4, false}; return true;
+    case RAFTGPU_COL_COMMITTED: *d = {c.committed, 8, false}; return true;
+    case RAFTGPU_COL_TERM_START: *d = {c.term_start, 8, false}; return true;
+    case RAFTGPU_COL_LAST_INDEX: *d = {c.last_index, 8, false}; return true;
+    default: return false;
+    }
+}
+
+// Move a duplicate-cell record (and the EXT record of a reject) to a later wave.
+void push_overflow(StagingSet &s, uint64_t cell, const raftgpu_append_resp *r, int n_recs) {
+    std::lock_guard<std::mutex> lk(s.overflow_mu);
+    const uint32_t depth = s.overflow_depth[cell]++;  // 0 -> wave 1
+    if (s.overflow_waves.size() <= depth) s.overflow_waves.resize(depth + 1);
+    for (int k = 0; k < n_recs; k++) s.overflow_waves[depth].push_back(r[k]);
+}
+
+int32_t reclaim_set(raftgpu_arena *a, StagingSet &s) {
+    // make a finished set reusable for filling
+    if (s.in_flight) return RAFTGPU_ERR_BUSY;
+    if (s.dirty) {
+        memset(s.touched, 0, a->cap);
+        s.dirty = false;
+    }
+    std::fill(s.ring_count.begin(), s.ring_count.end(), 0);
+    s.overflow_depth.clear();
+    s.overflow_waves.clear();
+    return RAFTGPU_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+const char *raftgpu_strerror(int32_t status) {
+    switch (status) {
+    case RAFTGPU_OK: return "ok";
+    case RAFTGPU_ERR_INVALID: return "invalid argument";
+    case RAFTGPU_ERR_CUDA: return "CUDA error";
+    case RAFTGPU_ERR_NOMEM: return "out of memory / arena full";
+    case RAFTGPU_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case RAFTGPU_ERR_RANGE: return "group or peer slot out of range";
+    case RAFTGPU_ERR_FULL: return "staging ring full";
+    case RAFTGPU_ERR_PEER_NOT_FOUND: return "peer not found (StepPeerNotFound)";
+    case RAFTGPU_ERR_COMMIT_RANGE: return "to_commit is out of range [last_index]";
+    case RAFTGPU_ERR_BUSY: return "step in flight";
+    default: return "unknown status";
+    }
+}
+
+uint32_t raftgpu_abi_version(void) { return RAFTGPU_ABI_VERSION; }
+
+int32_t raftgpu_arena_create(int32_t device, uint32_t max_groups, uint32_t slots_per_group,
+                             uint32_t n_rings, uint32_t ring_records, raftgpu_arena **out) {
+    return create(device, max_groups, slots_per_group, n_rings, ring_records, out);
+}
+
+int32_t raftgpu_arena_destroy(raftgpu_arena *arena) {
+    if (!arena) return RAFTGPU_ERR_INVALID;
+    destroy(arena);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_arena_info(const raftgpu_arena *a, raftgpu_info *out) {
+    if (!a || !out) return RAFTGPU_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->abi_version = RAFTGPU_ABI_VERSION;
+    out->device = a->device;
+    out->cap = a->cap;
+    out->slots = RAFTGPU_SLOTS;
+    out->n_alloc = a->n_alloc;
+    out->hi = a->hi;
+    out->sm_count = static_cast<uint32_t>(a->sm_count);
+    out->l2_bytes = a->l2_bytes;
+    out->device_bytes = a->device_bytes;
+    out->pinned_bytes = a->pinned_bytes;
+    return RAFTGPU_OK;
+}
+
+const char *raftgpu_last_error(const raftgpu_arena *a) {
+    return a ? a->last_error.c_str() : g_create_error.c_str();
+}
+
+// ---- group lifecycle -------------------------------------------------------
+
+int32_t raftgpu_group_alloc(raftgpu_arena *a, uint32_t *out_group) {
+    if (!a || !out_group) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(a->alloc_mu);
+    uint32_t g;
+    if (!a->free_list.empty()) {
+        g = a->free_list.back();
+        a->free_list.pop_back();
+    } else if (a->hi < a->cap) {
+        g = a->hi;
+    } else {
+        return fail(a, RAFTGPU_ERR_NOMEM, "arena full");
+    }
+    a->allocated[g] = 1;
+    a->n_alloc++;
+    if (g >= a->hi) a->hi = g + 1;
+    *out_group = g;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_group_alloc_range(raftgpu_arena *a, uint32_t n, uint32_t *out_first) {
+    if (!a || !out_first || n == 0) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(a->alloc_mu);
+    if (static_cast<uint64_t>(a->hi) + n > a->cap) return fail(a, RAFTGPU_ERR_NOMEM, "arena full");
+    const uint32_t first = a->hi;
+    memset(&a->allocated[first], 1, n);
+    a->hi += n;
+    a->n_alloc += n;
+    *out_first = first;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_group_free(raftgpu_arena *a, uint32_t g) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    // an empty configuration with no term range is inert in every kernel
+    int32_t rc = sync_op(a, [&](cudaStream_t st) {
+        conf_kernel<<<1, 1, 0, st>>>(a->cols, g, 0u, 0u, present_mask(a->h_meta[g]), 0);
+        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 0, RAFTGPU_NO_TERM_START, 0, nullptr);
+    });
+    if (rc != RAFTGPU_OK) return rc;
+    CK(a, cudaMemsetAsync(a->cols.committed + g, 0, 8, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    std::lock_guard<std::mutex> lk(a->alloc_mu);
+    a->h_meta[g] = 0;
+    a->allocated[g] = 0;
+    a->n_alloc--;
+    a->free_list.push_back(g);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_group_set_conf(raftgpu_arena *a, uint32_t g, uint32_t incoming_mask,
+                               uint32_t outgoing_mask, uint32_t learner_mask, int32_t self_slot,
+                               uint64_t next_idx) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    if ((incoming_mask | outgoing_mask | learner_mask) > 0xffu || self_slot >= RAFTGPU_SLOTS)
+        return RAFTGPU_ERR_INVALID;
+    const uint32_t old_meta = a->h_meta[g];
+    uint32_t meta = incoming_mask | (outgoing_mask << 8) | (learner_mask << 16) |
+                    (old_meta & RAFTGPU_META_GROUP_COMMIT);
+    if (self_slot >= 0) meta |= (static_cast<uint32_t>(self_slot) << 24) | RAFTGPU_META_HAS_SELF;
+    const uint32_t was = present_mask(old_meta), now = present_mask(meta);
+    int32_t rc = sync_op(a, [&](cudaStream_t st) {
+        conf_kernel<<<1, 1, 0, st>>>(a->cols, g, meta, now & ~was, was & ~now, next_idx);
+    });
+    if (rc == RAFTGPU_OK) a->h_meta[g] = meta;
+    return rc;
+}
+
+int32_t raftgpu_group_reset(raftgpu_arena *a, uint32_t g, uint64_t term_start, uint64_t last_index,
+                            uint64_t committed, uint64_t persisted) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    return sync_op(a, [&](cudaStream_t st) {
+        reset_kernel<<<1, 1, 0, st>>>(a->cols, g, term_start, last_index, committed, persisted);
+    });
+}
+
+int32_t raftgpu_group_become_leader(raftgpu_arena *a, uint32_t g) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    return sync_op(a, [&](cudaStream_t st) { become_leader_kernel<<<1, 1, 0, st>>>(a->cols, g); });
+}
+
+int32_t raftgpu_group_set_log_bounds(raftgpu_arena *a, uint32_t g, uint64_t term_start,
+                                     uint64_t last_index) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    return sync_op(a, [&](cudaStream_t st) {
+        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 0, term_start, last_index, nullptr);
+    });
+}
+
+int32_t raftgpu_group_commit_to(raftgpu_arena *a, uint32_t g, uint64_t to_commit) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    uint32_t *d = static_cast<uint32_t *>(a->d_scratch);
+    uint32_t *h = static_cast<uint32_t *>(a->h_scratch);
+    CK(a, cudaSetDevice(a->device));
+    group_op_kernel<<<1, 1, 0, a->s_compute>>>(a->cols, g, 1, to_commit, 0, d);
+    CKL(a);
+    CK(a, cudaMemcpyAsync(h, d, 4, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    if (*h) return fail(a, RAFTGPU_ERR_COMMIT_RANGE, "to_commit is out of range [last_index]");
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_group_get(raftgpu_arena *a, uint32_t g, raftgpu_group_state *out) {
+    if (!a || !out) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    auto *d = static_cast<raftgpu_group_state *>(a->d_scratch);
+    CK(a, cudaSetDevice(a->device));
+    group_get_kernel<<<1, 1, 0, a->s_compute>>>(a->cols, g, d);
+    CKL(a);
+    CK(a, cudaMemcpyAsync(a->h_scratch, d, sizeof(*out), cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    memcpy(out, a->h_scratch, sizeof(*out));
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_progress_get(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, raftgpu_progress *out) {
+    if (!a || !out) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
+    auto *d = static_cast<raftgpu_progress *>(a->d_scratch);
+    CK(a, cudaSetDevice(a->device));
+    progress_get_kernel<<<1, 1, 0, a->s_compute>>>(a->cols, g, peer_slot, d);
+    CKL(a);
+    CK(a, cudaMemcpyAsync(a->h_scratch, d, sizeof(*out), cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    memcpy(out, a->h_scratch, sizeof(*out));
+    return out->present ? RAFTGPU_OK : RAFTGPU_ERR_PEER_NOT_FOUND;
+}
+
+int32_t raftgpu_progress_set(raftgpu_arena *a, uint32_t g, uint32_t peer_slot,
+                             const raftgpu_progress *in) {
+    if (!a || !in) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
+    if (!((present_mask(a->h_meta[g]) >> peer_slot) & 1u)) return RAFTGPU_ERR_PEER_NOT_FOUND;
+    if (in->state > RAFTGPU_STATE_SNAPSHOT) return RAFTGPU_ERR_INVALID;
+    raftgpu_progress p = *in;
+    return sync_op(a, [&](cudaStream_t st) {
+        progress_set_kernel<<<1, 1, 0, st>>>(a->cols, g, peer_slot, p);
+    });
+}
+
+int32_t raftgpu_set_group_commit(raftgpu_arena *a, uint32_t g, int32_t enable) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    int32_t rc = sync_op(a, [&](cudaStream_t st) {
+        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 2, RAFTGPU_META_GROUP_COMMIT, enable ? 1 : 0,
+                                        nullptr);
+    });
+    if (rc == RAFTGPU_OK) {
+        if (enable)
+            a->h_meta[g] |= RAFTGPU_META_GROUP_COMMIT;
+        else
+            a->h_meta[g] &= ~RAFTGPU_META_GROUP_COMMIT;
+    }
+    return rc;
+}
+
+int32_t raftgpu_assign_commit_group(raftgpu_arena *a, uint32_t g, uint32_t peer_slot,
+                                    uint64_t commit_group_id) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
+    // raft.rs:534-540: unknown peers are skipped silently
+    if (!((present_mask(a->h_meta[g]) >> peer_slot) & 1u)) return RAFTGPU_OK;
+    return sync_op(a, [&](cudaStream_t st) {
+        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 3, peer_slot, commit_group_id, nullptr);
+    });
+}
+
+int32_t raftgpu_column_write(raftgpu_arena *a, int32_t column, uint32_t peer_slot,
+                             uint32_t first_group, uint32_t n, const void *host_src) {
+    ColumnDesc d;
+    if (!a || !host_src || !column_desc(a, column, &d)) return RAFTGPU_ERR_INVALID;
+    if (static_cast<uint64_t>(first_group) + n > a->cap || (d.per_peer && peer_slot >= RAFTGPU_SLOTS))
+        return RAFTGPU_ERR_RANGE;
+    CK(a, cudaSetDevice(a->device));
+    const size_t off = ((d.per_peer ? static_cast<size_t>(peer_slot) * a->cap : 0) + first_group) * d.elem;
+    CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(d.base) + off, host_src, n * d.elem,
+                          cudaMemcpyHostToDevice, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    if (column == RAFTGPU_COL_META) memcpy(&a->h_meta[first_group], host_src, n * 4ull);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_column_read(raftgpu_arena *a, int32_t column, uint32_t peer_slot,
+                            uint32_t first_group, uint32_t n, void *host_dst) {
+    ColumnDesc d;
+    if (!a || !host_dst || !column_desc(a, column, &d)) return RAFTGPU_ERR_INVALID;
+    if (static_cast<uint64_t>(first_group) + n > a->cap || (d.per_peer && peer_slot >= RAFTGPU_SLOTS))
+        return RAFTGPU_ERR_RANGE;
+    CK(a, cudaSetDevice(a->device));
+    const size_t off = ((d.per_peer ? static_cast<size_t>(peer_slot) * a->cap : 0) + first_group) * d.elem;
+    CK(a, cudaMemcpyAsync(host_dst, static_cast<uint8_t *>(d.base) + off, n * d.elem,
+                          cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    return RAFTGPU_OK;
+}
+
+// ---- hot path ---------------------------------------------------------------
+
+int32_t raftgpu_maximal_committed_index(raftgpu_arena *a, uint32_t g, uint64_t *out_index,
+                                        int32_t *out_use_group_commit) {
+    if (!a || !out_index) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    CK(a, cudaSetDevice(a->device));
+    // The query must not commit: run the pass on a scratch copy of `committed`
+    // semantics by reading mci only.  The kernel's commit step is idempotent with
+    // Raft::maybe_commit, but maximal_committed_index alone (tracker.rs:294-298)
+    // has no side effect, so mask the commit by using the mci-only launch below.
+    uint64_t *d_mci = static_cast<uint64_t *>(a->d_scratch);
+    uint8_t *d_gc = static_cast<uint8_t *>(a->d_scratch) + 8;
+    mci_kernel<<<1, 32, 0, a->s_compute>>>(a->cols, g, d_mci, d_gc);
+    CKL(a);
+    CK(a, cudaMemcpyAsync(a->h_scratch, a->d_scratch, 16, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    *out_index = *static_cast<uint64_t *>(a->h_scratch);
+    if (out_use_group_commit) *out_use_group_commit = static_cast<uint8_t *>(a->h_scratch)[8];
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_maybe_commit(raftgpu_arena *a, uint32_t g, int32_t *out_advanced,
+                             uint64_t *out_committed) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    CK(a, cudaSetDevice(a->device));
+    uint32_t *d_word = static_cast<uint32_t *>(a->d_scratch) + 8;  // offset 32
+    CK(a, cudaMemsetAsync(d_word, 0, 4, a->s_compute));
+    // bitmap pointer is indexed by g >> 5 from group 0: bias it so word (g >> 5) lands on d_word
+    int32_t rc = launch_recompute(a, a->s_compute, g, 1, d_word - (g >> 5), nullptr, nullptr, nullptr,
+                                  nullptr);
+    if (rc != RAFTGPU_OK) return rc;
+    CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(a->h_scratch) + 32, d_word, 4, cudaMemcpyDeviceToHost,
+                          a->s_compute));
+    CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(a->h_scratch) + 40, a->cols.committed + g, 8,
+                          cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    const uint32_t word = *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(a->h_scratch) + 32);
+    if (out_advanced) *out_advanced = (word >> (g & 31)) & 1u;
+    if (out_committed) *out_committed = *reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(a->h_scratch) + 40);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_recompute(raftgpu_arena *a, void *stream, uint32_t first, uint32_t n,
+                          uint32_t *d_adv_bitmap, uint64_t *d_commit_out, uint64_t *d_mci_out,
+                          uint8_t *d_gc_out) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (static_cast<uint64_t>(first) + n > a->cap) return RAFTGPU_ERR_RANGE;
+    CK(a, cudaSetDevice(a->device));
+    return launch_recompute(a, pick_stream(a, stream), first, n, d_adv_bitmap, d_commit_out, d_mci_out,
+                            d_gc_out, nullptr);
+}
+
+int32_t raftgpu_apply_device(raftgpu_arena *a, void *stream, const raftgpu_append_resp *d_records,
+                             uint64_t n, uint8_t *d_results) {
+    if (!a || (!d_records && n)) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    return launch_apply(a, pick_stream(a, stream), d_records, n, d_results);
+}
+
+int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftgpu_append_resp *recs,
+                                    uint64_t n) {
+    if (!a || (!recs && n)) return RAFTGPU_ERR_INVALID;
+    if (ring >= a->n_rings) return RAFTGPU_ERR_RANGE;
+    StagingSet &s = a->sets[a->fill];
+    if (s.in_flight) return RAFTGPU_ERR_BUSY;
+    raftgpu_append_resp *dst = s.h_recs + static_cast<size_t>(ring) * a->ring_records;
+    uint64_t cnt = s.ring_count[ring];
+    s.dirty = true;
+    for (uint64_t i = 0; i < n; i++) {
+        const raftgpu_append_resp &r = recs[i];
+        if (r.flags & RAFTGPU_REC_EXT) continue;  // copied together with its REJECT
+        const int n_recs = ((r.flags & RAFTGPU_REC_REJECT) && i + 1 < n &&
+                            (recs[i + 1].flags & RAFTGPU_REC_EXT)) ? 2 : 1;
+        bool dup = false;
+        if (r.group < a->cap && r.peer_slot < RAFTGPU_SLOTS) {
+            const uint8_t bit = static_cast<uint8_t>(1u << r.peer_slot);
+            uint8_t &t = s.touched[r.group];
+            dup = (t & bit) != 0;
+            t |= bit;
+        }
+        if (dup) {
+            push_overflow(s, (static_cast<uint64_t>(r.group) << 3) | r.peer_slot, &r, n_recs);
+            continue;
+        }
+        if (cnt + n_recs > a->ring_records) {
+            s.ring_count[ring] = cnt;
+            return fail(a, RAFTGPU_ERR_FULL, "staging ring full");
+        }
+        dst[cnt++] = r;
+        if (n_recs == 2) dst[cnt++] = recs[i + 1];
+    }
+    s.ring_count[ring] = cnt;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (a->pending >= 0) return fail(a, RAFTGPU_ERR_BUSY, "previous step not waited for");
+    CK(a, cudaSetDevice(a->device));
+    StagingSet &s = a->sets[a->fill];
+    // H2D: wave 0 = the rings back to back, then the later waves
+    uint64_t off = 0;
+    for (uint32_t r = 0; r < a->n_rings; r++) {
+        const uint64_t cnt = s.ring_count[r];
+        if (!cnt) continue;
+        CK(a, cudaMemcpyAsync(s.d_recs + off, s.h_recs + static_cast<size_t>(r) * a->ring_records,
+                              cnt * sizeof(raftgpu_append_resp), cudaMemcpyHostToDevice, a->s_h2d));
+        off += cnt;
+    }
+    const uint64_t wave0 = off;
+    std::vector<uint64_t> wave_sizes;
+    uint64_t ov = 0;
+    for (auto &w : s.overflow_waves) {
+        if (ov + w.size() > a->overflow_records)
+            return fail(a, RAFTGPU_ERR_FULL, "overflow staging full");
+        memcpy(s.h_overflow + ov, w.data(), w.size() * sizeof(raftgpu_append_resp));
+        wave_sizes.push_back(w.size());
+        ov += w.size();
+    }
+    if (ov)
+        CK(a, cudaMemcpyAsync(s.d_recs + wave0, s.h_overflow, ov * sizeof(raftgpu_append_resp),
+                              cudaMemcpyHostToDevice, a->s_h2d));
+    CK(a, cudaEventRecord(s.ev_h2d, a->s_h2d));
+
+    // compute: apply per wave, then one recompute pass over [0, hi)
+    CK(a, cudaStreamWaitEvent(a->s_compute, s.ev_h2d, 0));
+    uint8_t *d_res = (flags & RAFTGPU_STEP_READ_RESULTS) ? s.d_results : nullptr;
+    int32_t rc = launch_apply(a, a->s_compute, s.d_recs, wave0, d_res);
+    if (rc != RAFTGPU_OK) return rc;
+    uint64_t woff = wave0;
+    for (uint64_t wsz : wave_sizes) {
+        rc = launch_apply(a, a->s_compute, s.d_recs + woff, wsz, d_res ? d_res + woff : nullptr);
+        if (rc != RAFTGPU_OK) return rc;
+        woff += wsz;
+    }
+    CK(a, cudaMemsetAsync(s.d_step_adv, 0, 4, a->s_compute));
+    const uint32_t hi = a->hi;
+    rc = launch_recompute(a, a->s_compute, 0, hi, s.d_adv_bitmap,
+                          (flags & RAFTGPU_STEP_READ_COMMITTED) ? s.d_commit_out : nullptr, nullptr,
+                          nullptr, s.d_step_adv);
+    if (rc != RAFTGPU_OK) return rc;
+    CK(a, cudaEventRecord(s.ev_compute, a->s_compute));
+
+    // D2H of the results
+    CK(a, cudaStreamWaitEvent(a->s_d2h, s.ev_compute, 0));
+    CK(a, cudaMemcpyAsync(s.h_step_adv, s.d_step_adv, 4, cudaMemcpyDeviceToHost, a->s_d2h));
+    if (hi)
+        CK(a, cudaMemcpyAsync(s.h_adv_bitmap, s.d_adv_bitmap, 4ull * ((hi + 31) / 32),
+                              cudaMemcpyDeviceToHost, a->s_d2h));
+    if ((flags & RAFTGPU_STEP_READ_COMMITTED) && hi)
+        CK(a, cudaMemcpyAsync(s.h_committed, s.d_commit_out, 8ull * hi, cudaMemcpyDeviceToHost, a->s_d2h));
+    if (d_res && woff)
+        CK(a, cudaMemcpyAsync(s.h_results, s.d_results, woff, cudaMemcpyDeviceToHost, a->s_d2h));
+    CK(a, cudaEventRecord(s.ev_done, a->s_d2h));
+
+    s.in_flight = true;
+    s.flags = flags;
+    s.result.n_records = woff;
+    s.result.n_waves = static_cast<uint32_t>((wave0 ? 1 : 0) + wave_sizes.size());
+    s.result.n_groups = hi;
+    a->pending = a->fill;
+    // flip: the other set becomes the fill target (it must have been waited for)
+    const int other = 1 - a->fill;
+    rc = reclaim_set(a, a->sets[other]);
+    if (rc != RAFTGPU_OK) return rc;
+    a->fill = other;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_step_wait(raftgpu_arena *a, raftgpu_step_result *out) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (a->pending < 0) return fail(a, RAFTGPU_ERR_INVALID, "no step in flight");
+    StagingSet &s = a->sets[a->pending];
+    CK(a, cudaEventSynchronize(s.ev_done));
+    s.in_flight = false;
+    s.result.n_advanced = *s.h_step_adv;
+    if (out) *out = s.result;
+    a->last_done = a->pending;
+    a->pending = -1;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_step(raftgpu_arena *a, uint32_t flags, raftgpu_step_result *out) {
+    int32_t rc = raftgpu_step_begin(a, flags);
+    if (rc != RAFTGPU_OK) return rc;
+    return raftgpu_step_wait(a, out);
+}
+
+int32_t raftgpu_step_results(raftgpu_arena *a, const uint32_t **adv_bitmap, const uint64_t **committed,
+                             const uint8_t **record_results) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (a->last_done < 0) return fail(a, RAFTGPU_ERR_INVALID, "no completed step");
+    StagingSet &s = a->sets[a->last_done];
+    if (adv_bitmap) *adv_bitmap = s.h_adv_bitmap;
+    if (committed) *committed = (s.flags & RAFTGPU_STEP_READ_COMMITTED) ? s.h_committed : nullptr;
+    if (record_results) *record_results = (s.flags & RAFTGPU_STEP_READ_RESULTS) ? s.h_results : nullptr;
+    return RAFTGPU_OK;
+}
+
+// ---- votes ------------------------------------------------------------------
+
+int32_t raftgpu_reset_votes(raftgpu_arena *a, uint32_t g) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    return sync_op(a, [&](cudaStream_t st) {
+        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 4, 0, 0, nullptr);
+    });
+}
+
+int32_t raftgpu_record_vote(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, int32_t vote) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
+    return sync_op(a, [&](cudaStream_t st) {
+        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 5, peer_slot, vote ? 2 : 1, nullptr);
+    });
+}
+
+int32_t raftgpu_tally_votes(raftgpu_arena *a, void *stream, uint32_t first, uint32_t n, uint32_t *d_out) {
+    if (!a || !d_out) return RAFTGPU_ERR_INVALID;
+    if (static_cast<uint64_t>(first) + n > a->cap) return RAFTGPU_ERR_RANGE;
+    if (n == 0) return RAFTGPU_OK;
+    CK(a, cudaSetDevice(a->device));
+    tally_kernel<<<div_up(n, 256), 256, 0, pick_stream(a, stream)>>>(a->cols, first, n, d_out,
+                                                                   a->d_counters);
+    CKL(a);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_vote_result(raftgpu_arena *a, uint32_t g, int32_t *out_result, uint32_t *out_granted,
+                            uint32_t *out_rejected) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    CK(a, cudaSetDevice(a->device));
+    uint32_t *d = static_cast<uint32_t *>(a->d_scratch) + 16;  // offset 64
+    tally_kernel<<<1, 32, 0, a->s_compute>>>(a->cols, g, 1, d - g, a->d_counters);
+    CKL(a);
+    CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(a->h_scratch) + 64, d, 4, cudaMemcpyDeviceToHost,
+                          a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    const uint32_t w = *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(a->h_scratch) + 64);
+    if (out_result) *out_result = w & 0xff;
+    if (out_granted) *out_granted = (w >> 8) & 0xff;
+    if (out_rejected) *out_rejected = (w >> 16) & 0xff;
+    return RAFTGPU_OK;
+}
+
+// ---- plumbing ---------------------------------------------------------------
+
+int32_t raftgpu_counters_read(raftgpu_arena *a, raftgpu_counters *out) {
+    if (!a || !out) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    static_assert(sizeof(raftgpu_counters) == kCntCount * 8, "counter layout");
+    CK(a, cudaMemcpyAsync(a->h_scratch, a->d_counters, sizeof(*out), cudaMemcpyDeviceToHost,
+                          a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    memcpy(out, a->h_scratch, sizeof(*out));
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_synchronize(raftgpu_arena *a) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    CK(a, cudaDeviceSynchronize());
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_device_alloc(raftgpu_arena *a, uint64_t bytes, void **out) {
+    if (!a || !out) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    uint8_t *p = nullptr;
+    int32_t rc = dev_alloc(a, &p, bytes, false);
+    if (rc != RAFTGPU_OK) return rc;
+    a->user_allocs.push_back(p);
+    *out = p;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_device_free(raftgpu_arena *a, void *p) {
+    if (!a || !p) return RAFTGPU_ERR_INVALID;
+    for (size_t i = 0; i < a->user_allocs.size(); i++) {
+        if (a->user_allocs[i] == p) {
+            a->user_allocs.erase(a->user_allocs.begin() + i);
+            CK(a, cudaSetDevice(a->device));
+            CK(a, cudaFree(p));
+            return RAFTGPU_OK;
+        }
+    }
+    return RAFTGPU_ERR_INVALID;
+}
+
+int32_t raftgpu_memcpy_h2d(raftgpu_arena *a, void *dst, const void *src, uint64_t bytes) {
+    if (!a || !dst || !src) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    CK(a, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_memcpy_d2h(raftgpu_arena *a, void *dst, const void *src, uint64_t bytes) {
+    if (!a || !dst || !src) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    CK(a, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    return RAFTGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- commit-index recomputes/s on synthetic AppendResponse streams.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU baseline arm (the oracle port)
+
+One "step" = one pass of the hot path over one batch: apply ONE round of synthetic
+AppendResponses (about 3.5 records per group) to a 1M-group x 5-peer arena and
+recompute the commit index of every group (Raft::maybe_commit).  `value` = groups recomputed
+per second over all GPUs with the records already resident in HBM; `e2e` = the same through
+raftgpu_enqueue_append_resp / raftgpu_step with HOST buffers (H2D + D2H inside the timed
+region).  Multi-GPU: groups shard across ranks, no data-path collective; NCCL only reduces
+the per-rank counters and times.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "commit_index_recomputes_per_s"
+UNIT = "recomputes/s"
+N_GROUPS = 1_000_000          # BASELINE configs[2]: the headline config, per GPU
+K_PEERS = 5
+SEED = 0x5EED0003
+B_ALG_RECOMPUTE = 8 * K_PEERS + 34   # 74 B per recompute at K = 5
+B_ALG_APPLY = 76                      # bytes per applied AppendResponse
+N_ARENAS = 4                          # rotated so consecutive steps never share L2 contents
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the measured phases run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/raftgpu_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, parts[4:8]):
+                    if v == "Active":
+                        reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def cpu_leg(n_groups, seed, rounds_wanted, threads, budget_s=20.0):
+    """The oracle (oracle/raft_oracle.c: apply + recompute, range-partitioned over `threads`
+    pthreads) on a bounded sample of the same workload.  Only used as the CPU baseline."""
+    B = importlib.import_module("raft-rs_b200").binding
+    from oracle import oracle as O
+    synth = B.Synth(n_groups, seed, k_peers=K_PEERS)
+    cols = O.copy_columns(synth.initial)
+    total, done, times = 0.0, 0, []
+    for _ in range(rounds_wanted):
+        recs = synth.next_round()
+        secs, _ = O.bench_step(cols, recs, threads)
+        times.append(secs)
+        total += secs
+        done += 1
+        if total > budget_s:
+            break
+    return n_groups * done / total, done, times
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  raft-rs is Rust and
+    this image has no rustc/cargo, so the arm runs the pinned C port (oracle/) with every host
+    thread, on the same config / metric as the GPU arm."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    # warmup rounds are part of the same stream; time exactly `steps` rounds after them
+    B = importlib.import_module("raft-rs_b200").binding
+    from oracle import oracle as O
+    synth = B.Synth(N_GROUPS, SEED, k_peers=K_PEERS)
+    cols = O.copy_columns(synth.initial)
+    for _ in range(args.warmup):
+        O.bench_step(cols, synth.next_round(), threads)
+    total = 0.0
+    for _ in range(args.steps):
+        secs, _ = O.bench_step(cols, synth.next_round(), threads)
+        total += secs
+    value = N_GROUPS * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": "cfg3: 1M raft groups x 5 peers, one synthetic AppendResponse round "
+                               "per step (apply + recompute)", "groups": N_GROUPS, "peers": K_PEERS,
+                   "seed": hex(SEED)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} rounds of the cfg3 stream, {threads} pthreads, "
+                                   "oracle/raft_oracle.c (literal algorithm on flat arrays)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--groups", type=int, default=N_GROUPS, help=argparse.SUPPRESS)
+    ap.add_argument("--e2e-threads", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
+    ap.add_argument("--e2e-chunk", type=int, default=4, help="pipelined e2e steps per timed chunk")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    B = importlib.import_module("raft-rs_b200").binding
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference "
+                         "for the CPU baseline arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.groups
+    K, W = args.steps, args.warmup
+    peak_gbs, peak_src = peaks()
+
+    # ---- synthetic inputs: N_ARENAS independent 1M-group stores, K+W rounds in total ----------
+    # Host memory is kept small and reused (one record buffer per generator): fresh host pages
+    # are slow on these VMs; HBM holds all K+W rounds.
+    per_arena = [(W + K + N_ARENAS - 1 - a) // N_ARENAS for a in range(N_ARENAS)]
+    arenas, round_len, d_recs = [], [], []
+    for a in range(N_ARENAS):
+        seed = SEED + 0x100 * a + 0x10000 * rank
+        s = B.Synth(n, seed, k_peers=K_PEERS)
+        ar = B.Arena(n, device=local_rank, n_rings=1, ring_records=4096)
+        assert ar.group_alloc_range(n) == 0
+        ar.load_columns(s.initial)
+        ptrs, lens = [], []
+        for _ in range(per_arena[a]):
+            recs = s.next_round()
+            p = ar.device_alloc(recs.nbytes)
+            ar.h2d(p, recs)
+            ptrs.append(p)
+            lens.append(len(recs))
+        arenas.append(ar)
+        round_len.append(lens)
+        d_recs.append(ptrs)
+        del s
+    schedule = [(i % N_ARENAS, i // N_ARENAS) for i in range(W + K)]  # (arena, round) per step
+
+    stream = torch.cuda.Stream()
+    sh = stream.cuda_stream
+
+    def run_step(i, ev=None):
+        a, r = schedule[i]
+        if ev:
+            ev[0].record(stream)
+        arenas[a].apply_device(d_recs[a][r], round_len[a][r], stream=sh)
+        if ev:
+            ev[1].record(stream)
+        arenas[a].recompute(0, n, stream=sh)
+        if ev:
+            ev[2].record(stream)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    with torch.cuda.stream(stream):
+        # clocks up: the recompute pass is idempotent on unchanged progress
+        t_end = time.perf_counter() + 0.3
+        while time.perf_counter() < t_end:
+            for a in arenas:
+                a.recompute(0, n, stream=sh)
+            stream.synchronize()
+        for i in range(W):
+            run_step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            run_step(W + i, evs[i])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    ms_apply = sum(e[0].elapsed_time(e[1]) for e in evs)
+    ms_recompute = sum(e[1].elapsed_time(e[2]) for e in evs)
+    n_records = sum(round_len[a][r] for a, r in schedule[W:])
+
+    # ---- e2e: host buffers -> enqueue -> step (H2D, kernels, D2H) on a fresh arena ------------
+    # The caller's records sit in ordinary host memory; raftgpu_enqueue_append_resp stages them
+    # into pinned rings (T caller threads, T rings), raftgpu_step_begin DMAs + launches,
+    # raftgpu_step_wait returns once the results are back in host memory.  Steps are timed in
+    # chunks of `chunk` pipelined steps (the next batch is staged while one is in flight); the
+    # records of the following chunk are regenerated between chunks, untimed, into the same few
+    # host buffers.
+    e2e_threads = args.e2e_threads or min(16, max(1, (os.cpu_count() or 2) // 2))
+    chunk = max(2, args.e2e_chunk)
+    e2e_steps = args.e2e_steps or K
+    es = B.Synth(n, SEED + 0x10000 * rank, k_peers=K_PEERS)
+    ea = B.Arena(n, device=local_rank, n_rings=e2e_threads)
+    assert ea.group_alloc_range(n) == 0
+    ea.load_columns(es.initial)
+    pool = ThreadPoolExecutor(e2e_threads)
+    bufs = [np.empty(5 * n + 64, dtype=B.APPEND_RESP_DTYPE) for _ in range(chunk)]
+
+    def split(recs):
+        cuts = [0]
+        for t in range(1, e2e_threads):
+            c = len(recs) * t // e2e_threads
+            while c < len(recs) and recs[c]["flags"] & B.REC_EXT:
+                c += 1
+            cuts.append(c)
+        cuts.append(len(recs))
+        return [recs[cuts[t]:cuts[t + 1]] for t in range(e2e_threads)]
+
+    def enqueue(parts):
+        list(pool.map(lambda t: ea.enqueue(parts[t], ring=t), range(e2e_threads)))
+
+    flags = B.STEP_READ_COMMITTED
+    e2e_s, e2e_timed, h2d_bytes, adv_total, first_chunk = 0.0, 0, 0, 0, True
+    while e2e_timed < e2e_steps:
+        m = min(chunk, e2e_steps - e2e_timed)
+        parts = [split(es.next_round(bufs[j])) for j in range(m)]      # untimed generation
+        if first_chunk:                                                  # untimed warm-up steps
+            for j in range(m):
+                enqueue(parts[j])
+                ea.step(flags)
+            first_chunk = False
+            continue
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        enqueue(parts[0])
+        for j in range(m):
+            ea.step_begin(flags)
+            if j + 1 < m:
+                enqueue(parts[j + 1])     # stage the next batch while this one is in flight
+            adv_total += ea.step_wait().n_advanced
+        e2e_s += time.perf_counter() - t0
+        e2e_timed += m
+        h2d_bytes += sum(sum(x.nbytes for x in pj) for pj in parts)
+    h2d = h2d_bytes / e2e_timed
+    d2h = 8 * n + 4 * ((n + 31) // 32) + 4
+    clocks = sampler.stop()
+
+    # ---- aggregate over ranks (NCCL: counters and times only) -----------------------------------
+    cnt = [a.counters() for a in arenas]
+    local = torch.tensor([ms_total, e2e_s, float(n * K), float(n * e2e_timed),
+                          float(sum(c["recomputes"] for c in cnt)),
+                          float(sum(c["advanced"] for c in cnt)),
+                          float(sum(c["records"] for c in cnt))], dtype=torch.float64, device="cuda")
+    mx, sm = local.clone(), local.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    ms_max, e2e_max = mx[0].item(), mx[1].item()
+    value = sm[2].item() / (ms_max * 1e-3)
+    e2e_value = sm[3].item() / e2e_max
+
+    if rank == 0:
+        kernels = []
+        for name, ms, units, b_alg in (("apply_kernel", ms_apply, n_records, B_ALG_APPLY),
+                                       ("recompute_kernel", ms_recompute, n * K, B_ALG_RECOMPUTE)):
+            gbs = units * b_alg / (ms * 1e-3) / 1e9
+            kernels.append({"kernel": name, "avg_us": 1e3 * ms / K, "share": ms / ms_total,
+                            "alg_bytes_per_launch": units * b_alg / K, "achieved": gbs,
+                            "frac": gbs / peak_gbs})
+        dom = max(kernels, key=lambda k: k["avg_us"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {
+                "workload": "cfg3: 1M raft groups x 5 peers per GPU, one synthetic AppendResponse "
+                            "round per step (apply + recompute)",
+                "groups_per_gpu": n, "peers": K_PEERS, "seed": hex(SEED),
+                "records_per_step": n_records / K,
+                "l2": f"inputs larger than L2: {N_ARENAS} arenas rotated, fresh records every step",
+                "parallelism": f"groups sharded over {world} GPU(s), no data-path collective",
+            },
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"],
+                         "peak": peak_gbs, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                         "peak_source": peak_src},
+            "kernels": kernels,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_timed, "ms_per_step": 1e3 * e2e_max / e2e_timed,
+                    "host_threads": e2e_threads, "pipelined_chunk": chunk,
+                    "api": "raftgpu_enqueue_append_resp + raftgpu_step_begin/_wait (READ_COMMITTED)"},
+            "gpu_launches": 2 * K,
+            "clocks": clocks,
+            "counters": {"recomputes": sm[4].item(), "advanced": sm[5].item(), "records": sm[6].item()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, done, _ = cpu_leg(n, SEED, 64, threads, budget_s=15.0)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{done} rounds of the same cfg3 stream (apply + recompute), {threads} "
+                          "pthreads, oracle/raft_oracle.c"}
+        print(json.dumps(line), flush=True)
+    for a in arenas:
+        a.close()
+    ea.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -235,15 +235,22 @@ class Synth:
         rc = lib().raftgpu_synth_init(C.byref(self._sc), seed, k_peers, int(joint))
         if rc != OK:
             raise RaftGpuError(rc, "raftgpu_synth_init")
-        self.initial = copy_columns(self.cols)  # what an arena / the oracle is loaded with
+        # what an arena / the oracle is loaded with (rounds only advance the sim_* state)
+        self.initial = self.cols
         self.round_no = 0
+        self._buf = None
 
     def max_records_per_round(self) -> int:
         return self.n_groups * (2 * (self.k_union - 1) + 1)
 
     def next_round(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Returns a VIEW into a buffer that the next call overwrites (copy it to keep it):
+        fresh host pages are expensive on the GPU boxes' VMs, so one buffer is reused."""
         if out is None:
-            out = np.zeros(self.max_records_per_round(), dtype=APPEND_RESP_DTYPE)
+            if self._buf is None:
+                cap = min(self.max_records_per_round(), 5 * self.n_groups + 64)
+                self._buf = np.empty(cap, dtype=APPEND_RESP_DTYPE)
+            out = self._buf
         n = C.c_uint64()
         rc = lib().raftgpu_synth_round(C.byref(self._sc), self.seed, self.round_no, self.k_union,
                                        out.ctypes.data, len(out), C.byref(n))

@@ -1,0 +1,430 @@
+"""GPU parity tests proper: the CUDA path, through the C-ABI, against the oracle.
+
+Bit-exact (integer / index work): golden vectors replayed THROUGH the GPU, the
+reference's table tests, full element-wise comparison of every column on the
+synthetic streams (BASELINE configs 2-4), and size-independent properties at the
+full sizes.  Run with ``-m gpu`` on a B200.
+"""
+import ctypes as C
+import os
+import random
+
+import numpy as np
+import pytest
+
+from helpers import B, O, assert_columns_equal, bitmap_to_bool, checksum
+from oracle import datadriven as dd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    a = B.Arena(4096)
+    yield a
+    a.close()
+
+
+# --------------------------------------------------------------------------- goldens via GPU
+
+class GpuQuorum:
+    """Evaluates the quorum functions on the GPU: voter ids are mapped to peer slots of one
+    arena group, acked indexes become its matched / commit_group_id columns."""
+
+    def __init__(self, arena):
+        self.a = arena
+        self.g = arena.group_alloc()
+
+    def _setup(self, incoming, outgoing, lookup, gc):
+        ids = []
+        for i in list(incoming) + list(outgoing):
+            if i not in ids:
+                ids.append(i)
+        assert len(ids) <= B.SLOTS
+        slot = {i: s for s, i in enumerate(ids)}
+        m_in = sum(1 << slot[i] for i in set(incoming))
+        m_out = sum(1 << slot[i] for i in set(outgoing))
+        self.a.group_set_conf(self.g, 0, 0, 0, None, 1)            # drop every Progress
+        self.a.group_set_conf(self.g, m_in, m_out, 0, None, 1)
+        self.a.set_group_commit(self.g, gc)
+        for i, s in slot.items():
+            p = self.a.progress_get(self.g, s)
+            p.matched, p.commit_group_id = lookup.get(i, (0, 0))   # missing voter == (0, 0)
+            self.a.progress_set(self.g, s, p)
+        return slot
+
+    def joint(self, incoming, outgoing, lookup, gc):
+        self._setup(incoming, outgoing, lookup, gc)
+        return self.a.maximal_committed_index(self.g)
+
+    def majority(self, voters, lookup, gc):
+        return self.joint(voters, [], lookup, gc)
+
+    def joint_vote(self, incoming, outgoing, votes):
+        slot = self._setup(incoming, outgoing, {}, False)
+        self.a.reset_votes(self.g)
+        for i, v in votes.items():
+            if i in slot:
+                self.a.record_vote(self.g, slot[i], v)
+        return self.a.vote_result(self.g)[2]
+
+    def majority_vote(self, voters, votes):
+        return self.joint_vote(voters, [], votes)
+
+    def impl(self):
+        return dd.Impl(self.majority, self.joint, self.majority_vote, self.joint_vote)
+
+
+@pytest.mark.parametrize("name,count", [("majority_commit.txt", 16), ("joint_commit.txt", 50),
+                                        ("joint_group_commit.txt", 14), ("majority_vote.txt", 22),
+                                        ("joint_vote.txt", 39)])
+def test_golden_vectors_through_the_gpu(small, golden_dir, name, count):
+    q = GpuQuorum(small)
+    cases = dd.replay_file(os.path.join(golden_dir, "quorum", name), q.impl())
+    assert len(cases) == count
+    for d, actual in cases:
+        assert actual == d.expected, f"{d.pos}\n--- gpu\n{actual}--- expected\n{d.expected}"
+    small.group_free(q.g)
+
+
+# --------------------------------------------------------------------------- table tests via GPU
+
+def load_one(arena, cols):
+    g = arena.group_alloc()
+    for name, (col, dt, per_peer) in B.COLUMNS.items():
+        arr = getattr(cols, name)
+        if per_peer:
+            for s in range(B.SLOTS):
+                arena.column_write(col, s, g, arr[s, :1])
+        else:
+            arena.column_write(col, 0, g, arr[:1])
+    return g
+
+
+def read_one(arena, g):
+    return arena.read_columns(1, first=g)
+
+
+def apply_recs(arena, recs, g):
+    recs = recs.copy()
+    recs["group"] = g
+    arena.enqueue(recs)
+    r = arena.step(B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS)
+    _, _, res = arena.step_results(arena.get_info().hi, int(r.n_records))
+    return r, res.copy()
+
+
+def progress_cols(state, matched, next_idx, pending_snapshot=0, paused=False):
+    c = O.new_columns(1, 1)
+    c.meta[0] = O.make_meta(0b11, 0, 0, 0)
+    c.matched[1, 0], c.next_idx[1, 0], c.pending_snapshot[1, 0] = matched, next_idx, pending_snapshot
+    c.pflags[1, 0] = state | (O.PF_PAUSED if paused else 0)
+    c.pflags[0, 0] = O.STATE_REPLICATE
+    c.term_start[0] = O.U64_MAX
+    return c
+
+
+def rec(slot, index, commit=0, reject=False, hint=0, request_snapshot=0, local=False):
+    if reject:
+        r = np.zeros(2, dtype=B.APPEND_RESP_DTYPE)
+        r[0] = (0, slot, B.REC_REJECT, 0, index, commit)
+        r[1] = (0, slot, B.REC_EXT, 0, hint, request_snapshot)
+        return r
+    r = np.zeros(1, dtype=B.APPEND_RESP_DTYPE)
+    r[0] = (0, slot, B.REC_LOCAL if local else 0, 0, index, commit)
+    return r
+
+
+# src/tracker/progress.rs:351-373 test_progress_update
+@pytest.mark.parametrize("update,wm,wn,wok", [(2, 3, 5, False), (3, 3, 5, False), (4, 4, 5, True),
+                                               (5, 5, 6, True)])
+def test_progress_update_on_gpu(small, update, wm, wn, wok):
+    g = load_one(small, progress_cols(O.STATE_REPLICATE, 3, 5))
+    _, res = apply_recs(small, rec(1, update), g)
+    got = read_one(small, g)
+    assert (int(got.matched[1, 0]), int(got.next_idx[1, 0])) == (wm, wn)
+    assert bool(res[0] & B.RES_OK) == wok
+    small.group_free(g)
+
+
+# src/tracker/progress.rs:375-412 test_progress_maybe_decr
+@pytest.mark.parametrize("state,m,n,rejected,last,w,wn", [
+    (1, 5, 10, 5, 5, False, 10), (1, 5, 10, 4, 4, False, 10), (1, 5, 10, 9, 9, True, 6),
+    (0, 0, 0, 0, 0, False, 0), (0, 0, 10, 5, 5, False, 10), (0, 0, 10, 9, 9, True, 9),
+    (0, 0, 2, 1, 1, True, 1), (0, 0, 1, 0, 0, True, 1), (0, 0, 10, 9, 2, True, 3),
+    (0, 0, 10, 9, 0, True, 1)])
+def test_progress_maybe_decr_on_gpu(small, state, m, n, rejected, last, w, wn):
+    cols = progress_cols(state, m, n, paused=True)
+    g = load_one(small, cols)
+    _, res = apply_recs(small, rec(1, rejected, reject=True, hint=last), g)
+    got = read_one(small, g)
+    assert bool(res[0] & B.RES_OK) == w
+    assert (int(got.matched[1, 0]), int(got.next_idx[1, 0])) == (m, wn)
+    want = O.copy_columns(cols)
+    O.arena_apply(want, rec(1, rejected, reject=True, hint=last), mode=0)
+    assert_columns_equal(got, want, 1)
+    small.group_free(g)
+
+
+def one_group(matches, gids=None, group_commit=False, committed=0, term_start=1, last_index=None):
+    n = len(matches)
+    c = O.new_columns(1, 1)
+    for s, m in enumerate(matches):
+        c.matched[s, 0], c.next_idx[s, 0] = m, m + 1
+        if gids:
+            c.commit_group_id[s, 0] = gids[s]
+    c.meta[0] = O.make_meta((1 << n) - 1, 0, 0, 0, group_commit)
+    c.committed[0], c.term_start[0] = committed, term_start
+    c.last_index[0] = max(matches) if last_index is None else last_index
+    return c
+
+
+# harness/tests/integration_cases/test_raft.rs:1145-1240 test_commit
+@pytest.mark.parametrize("matches,logs,sm_term,want", [
+    ([1], [(1, 1)], 1, 1), ([1], [(1, 1)], 2, 0), ([2], [(1, 1), (2, 2)], 2, 2),
+    ([1], [(2, 1)], 2, 1),
+    ([2, 1, 1], [(1, 1), (2, 2)], 1, 1), ([2, 1, 1], [(1, 1), (1, 2)], 2, 0),
+    ([2, 1, 2], [(1, 1), (2, 2)], 2, 2), ([2, 1, 2], [(1, 1), (1, 2)], 2, 0),
+    ([2, 1, 1, 1], [(1, 1), (2, 2)], 1, 1), ([2, 1, 1, 1], [(1, 1), (1, 2)], 2, 0),
+    ([2, 1, 1, 2], [(1, 1), (2, 2)], 1, 1), ([2, 1, 1, 2], [(1, 1), (1, 2)], 2, 0),
+    ([2, 1, 2, 2], [(1, 1), (2, 2)], 2, 2), ([2, 1, 2, 2], [(1, 1), (1, 2)], 2, 0)])
+def test_commit_on_gpu(small, matches, logs, sm_term, want):
+    own = [i for t, i in logs if t == sm_term]
+    g = load_one(small, one_group(matches, term_start=min(own) if own else O.U64_MAX,
+                                  last_index=logs[-1][1]))
+    adv, committed = small.maybe_commit(g)
+    assert committed == want and adv == (want > 0)
+    small.group_free(g)
+
+
+# test_raft.rs:5092-5163 test_group_commit
+@pytest.mark.parametrize("matches,gids,g_w,q_w", [
+    ([1], [0], 1, 1), ([1], [1], 1, 1),
+    ([2, 2, 1], [1, 2, 1], 2, 2), ([2, 2, 1], [1, 1, 2], 1, 2), ([2, 2, 1], [1, 0, 1], 1, 2),
+    ([2, 2, 1], [0, 0, 0], 1, 2),
+    ([4, 2, 1, 3], [0, 0, 0, 0], 1, 2), ([4, 2, 1, 3], [1, 0, 0, 0], 1, 2),
+    ([4, 2, 1, 3], [0, 1, 0, 2], 2, 2), ([4, 2, 1, 3], [0, 2, 1, 0], 1, 2),
+    ([4, 2, 1, 3], [1, 1, 1, 1], 2, 2), ([4, 2, 1, 3], [1, 1, 2, 1], 1, 2),
+    ([4, 2, 1, 3], [1, 2, 1, 1], 2, 2), ([4, 2, 1, 3], [4, 3, 2, 1], 2, 2)])
+def test_group_commit_on_gpu(small, matches, gids, g_w, q_w):
+    g = load_one(small, one_group(matches, term_start=min(matches)))
+    for s, gid in enumerate(gids):
+        if gid:
+            small.assign_commit_group(g, s, gid)
+    small.set_group_commit(g, True)
+    assert small.maybe_commit(g)[1] == g_w
+    small.set_group_commit(g, False)
+    assert small.maybe_commit(g)[1] == q_w
+    small.group_free(g)
+
+
+def test_group_commit_random_vs_oracle(small):
+    rng = random.Random(2024)
+    g = small.group_alloc()
+    for _ in range(300):
+        inc, out = rng.randrange(1, 256), rng.choice([0, rng.randrange(0, 256)])
+        c = O.new_columns(1, 1)
+        c.meta[0] = O.make_meta(inc, out, 0, None, True)
+        for s in range(8):
+            c.matched[s, 0] = rng.randrange(0, 12)
+            c.commit_group_id[s, 0] = rng.randrange(0, 4)
+        for name, (col, dt, per_peer) in B.COLUMNS.items():
+            arr = getattr(c, name)
+            if per_peer:
+                for s in range(B.SLOTS):
+                    small.column_write(col, s, g, arr[s, :1])
+            else:
+                small.column_write(col, 0, g, arr[:1])
+        assert small.maximal_committed_index(g) == O.arena_mci(c, 0), (inc, out)
+    small.group_free(g)
+
+
+# --------------------------------------------------------------------------- lifecycle
+
+def test_group_lifecycle_mirrors_raft_new_reset_become_leader(small):
+    g = small.group_alloc()
+    # Raft::new: confchange::restore adds three voters with next_idx = last_index + 1 = 1
+    small.group_set_conf(g, 0b111, 0, 0, 0, 1)
+    for s in range(3):
+        p = small.progress_get(g, s)
+        assert (p.matched, p.next_idx, p.state, p.recent_active, p.present) == (0, 1, 0, 1, 1)
+    with pytest.raises(B.RaftGpuError) as e:
+        small.progress_get(g, 5)
+    assert e.value.status == B.ERR_PEER_NOT_FOUND
+    # Raft::reset at last_index 7, committed 4, persisted 7  (raft.rs:942-971)
+    small.group_reset(g, B.NO_TERM_START, 7, 4, 7)
+    p0, p1 = small.progress_get(g, 0), small.progress_get(g, 1)
+    assert (p0.matched, p0.next_idx, p0.committed_index, p0.recent_active) == (7, 8, 4, 0)
+    assert (p1.matched, p1.next_idx, p1.state) == (0, 8, B.STATE_PROBE)
+    assert small.maybe_commit(g) == (False, 4)                  # follower: no quorum commit
+    # become_leader (raft.rs:1162-1203): self Replicate, noop appended at 8 = term_start
+    small.group_become_leader(g)
+    st = small.group_get(g)
+    assert (st.term_start, st.last_index, st.committed) == (8, 8, 4)
+    assert small.progress_get(g, 0).state == B.STATE_REPLICATE
+    # leader persists the noop, one follower acks it -> commit 8
+    recs = np.concatenate([rec(0, 8, commit=8, local=True), rec(1, 8, commit=4)])
+    r, res = apply_recs(small, recs, g)
+    assert small.group_get(g).committed == 8 and r.n_advanced >= 1
+    # RaftLog::commit_to (raft_log.rs:286-300)
+    assert small.group_commit_to(g, 3) == B.OK and small.group_get(g).committed == 8
+    assert small.group_commit_to(g, 9) == B.ERR_COMMIT_RANGE
+    # apply_conf removing a voter drops its Progress
+    small.group_set_conf(g, 0b011, 0, 0, 0, 9)
+    with pytest.raises(B.RaftGpuError):
+        small.progress_get(g, 2)
+    small.group_free(g)
+
+
+def test_enqueue_splits_duplicate_cells_into_waves(small):
+    """Several responses of one peer in one batch keep their arrival order
+    (raft.rs:1559: messages are stepped one at a time)."""
+    cols = one_group([20, 2, 2], term_start=1, last_index=20)
+    cols.pflags[1, 0], cols.pending_snapshot[1, 0] = O.STATE_SNAPSHOT, 8
+    cols.pflags[0, 0] = cols.pflags[2, 0] = O.STATE_REPLICATE
+    g = load_one(small, cols)
+    # Snapshot peer: 9 aborts the snapshot (-> Probe), 12 then flips Probe -> Replicate;
+    # in the other order the result differs, so order must be preserved.
+    recs = np.concatenate([rec(1, 9), rec(1, 12), rec(2, 5), rec(1, 3), rec(2, 5, reject=True, hint=5)])
+    want = O.copy_columns(cols)
+    want_res = O.arena_apply(want, recs, mode=0)
+    O.arena_recompute(want)
+    r, res = apply_recs(small, recs, g)
+    assert r.n_waves == 3 and r.n_records == len(recs)
+    got = read_one(small, g)
+    assert_columns_equal(got, want, 1)
+    assert int(got.pflags[1, 0]) & 3 == O.STATE_REPLICATE and int(got.committed[0]) == 12
+    # results come back in submission order: wave 0 first, then later waves
+    assert sorted(res.tolist()) == sorted(want_res.tolist())
+    small.group_free(g)
+
+
+# --------------------------------------------------------------------------- synthetic streams
+
+CONFIGS = {
+    "cfg2_100k_x5": dict(n=100_000, seed=0x5EED0002, joint=False, rounds=12),
+    "cfg3_1m_x5": dict(n=1_000_000, seed=0x5EED0003, joint=False, rounds=4),
+    "cfg4_1m_x7_joint": dict(n=1_000_000, seed=0x5EED0004, joint=True, rounds=4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_synthetic_stream_elementwise(name):
+    cfg = CONFIGS[name]
+    n = cfg["n"]
+    synth = B.Synth(n, cfg["seed"], joint=cfg["joint"])
+    arena = B.Arena(n)
+    assert arena.group_alloc_range(n) == 0
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    total_adv = 0
+    for rnd in range(cfg["rounds"]):
+        recs = synth.next_round().copy()
+        half = len(recs) // 2
+        while recs[half]["flags"] & B.REC_EXT:
+            half += 1
+        arena.enqueue(recs[:half], ring=0)          # two rings, as two caller threads would
+        arena.enqueue(recs[half:], ring=1)
+        r = arena.step(B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS)
+        bm, com, res = arena.step_results(n, int(r.n_records))
+        want_res = O.arena_apply(ref, recs, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        assert r.n_waves == 1 and r.n_records == len(recs)
+        assert r.n_advanced == want_adv
+        assert np.array_equal(res, want_res), f"{name} round {rnd}: per-record results differ"
+        assert np.array_equal(bm, want_bm[: len(bm)])
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+        total_adv += want_adv
+        got = arena.read_columns(n)
+        assert_columns_equal(got, ref, n, f"{name} round {rnd}")
+    assert total_adv > n  # the stream really advances commit indexes
+    cnt = arena.counters()
+    assert cnt["recomputes"] == n * cfg["rounds"] and cnt["advanced"] == total_adv
+    arena.close()
+
+
+def test_mci_and_properties_at_full_size():
+    """1M x 7 joint: maximal_committed_index for every group vs the oracle, plus
+    size-independent properties: idempotence, monotone commit, joint = min of halves."""
+    n = 1_000_000
+    synth = B.Synth(n, 0x5EED0004, joint=True)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(synth.initial)
+    d_mci, d_gc = arena.device_alloc(8 * arena.cap), arena.device_alloc(arena.cap)
+    d_bm = arena.device_alloc(arena.cap // 8)
+    arena.recompute(0, n, d_adv=d_bm, d_mci=d_mci, d_gc=d_gc)
+    mci = np.zeros(arena.cap, dtype=np.uint64)
+    bm1 = np.zeros(arena.cap // 32, dtype=np.uint32)
+    arena.d2h(mci, d_mci)
+    arena.d2h(bm1, d_bm)
+    ref = O.copy_columns(synth.initial)
+    want_adv, want_bm, want_mci, _ = O.arena_recompute(ref, want_mci=True)
+    assert np.array_equal(mci[:n], want_mci[:n])
+    assert checksum(mci[:n]) == checksum(want_mci[:n])
+    assert np.array_equal(bm1[: len(want_bm)], want_bm)
+    committed1 = arena.column_read(B.COL_COMMITTED, 0, 0, n, np.uint64)
+    assert np.array_equal(committed1, ref.committed[:n])
+    assert np.all(committed1 >= synth.initial.committed[:n])          # never decreases
+    # idempotence: a second pass over unchanged progress advances nothing
+    arena.recompute(0, n, d_adv=d_bm)
+    arena.d2h(bm1, d_bm)
+    assert not bm1.any()
+    assert np.array_equal(arena.column_read(B.COL_COMMITTED, 0, 0, n, np.uint64), committed1)
+    # joint = min(incoming-only, outgoing-only): re-run with each half as a plain majority
+    meta = synth.initial.meta[:n].copy()
+    halves = []
+    for shift in (0, 8):
+        m = ((meta >> shift) & 0xFF) | (meta & 0xFF000000)
+        arena.column_write(B.COL_META, 0, 0, m.astype(np.uint32))
+        arena.recompute(0, n, d_mci=d_mci)
+        arena.d2h(mci, d_mci)
+        halves.append(mci[:n].copy())
+    assert np.array_equal(np.minimum(halves[0], halves[1]), want_mci[:n])
+    arena.close()
+
+
+def test_partial_ranges_and_bitmap_edges():
+    n = 10_000
+    synth = B.Synth(n, 0x5EED0002)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    d_bm = arena.device_alloc(arena.cap // 8)
+    bm = np.full(arena.cap // 32, 0xFFFFFFFF, dtype=np.uint32)
+    arena.h2d(d_bm, bm)
+    first, cnt = 37, 4321   # neither end on a 32-group boundary
+    arena.recompute(first, cnt, d_adv=d_bm)
+    arena.d2h(bm, d_bm)
+    want_bm = np.full(arena.cap // 32, 0xFFFFFFFF, dtype=np.uint32)
+    for g in range(first, first + cnt):
+        if not O.arena_maybe_commit(ref, g):
+            want_bm[g >> 5] &= ~np.uint32(1 << (g & 31))
+    assert np.array_equal(bm, want_bm)
+    assert np.array_equal(arena.column_read(B.COL_COMMITTED, 0, 0, n, np.uint64), ref.committed[:n])
+    arena.close()
+
+
+def test_vote_tally_batched_vs_oracle():
+    n = 50_000
+    rng = np.random.default_rng(7)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    c = O.new_columns(arena.cap, n)
+    inc = rng.integers(0, 256, n, dtype=np.uint32)
+    out = np.where(rng.random(n) < 0.5, 0, rng.integers(0, 256, n)).astype(np.uint32)
+    c.meta[:n] = inc | (out << 8)
+    votes = rng.integers(0, 3, (B.SLOTS, arena.cap), dtype=np.uint8)
+    arena.column_write(B.COL_META, 0, 0, c.meta[:n])
+    for s in range(B.SLOTS):
+        arena.column_write(B.COL_VOTES, s, 0, votes[s, :n])
+    d_out = arena.device_alloc(4 * arena.cap)
+    arena.tally_votes(0, n, d_out)
+    got = np.zeros(arena.cap, dtype=np.uint32)
+    arena.d2h(got, d_out)
+    for g in rng.integers(0, n, 3000):
+        gr, rj, r = O.arena_vote_result(c, votes, int(g))
+        assert int(got[g]) == r | (gr << 8) | (rj << 16)
+    arena.close()

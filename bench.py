@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
     ap.add_argument("--e2e-chunk", type=int, default=4, help="pipelined e2e steps per timed chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="device-resident loop only (for ncu): no clock warm loop, no e2e, no CPU leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -234,7 +236,7 @@ def main():
     sampler.start()
     with torch.cuda.stream(stream):
         # clocks up: the recompute pass is idempotent on unchanged progress
-        t_end = time.perf_counter() + 0.3
+        t_end = time.perf_counter() + (0.0 if args.profile else 0.3)
         while time.perf_counter() < t_end:
             for a in arenas:
                 a.recompute(0, n, stream=sh)
@@ -269,7 +271,7 @@ def main():
     # host buffers.
     e2e_threads = args.e2e_threads or min(16, max(1, (os.cpu_count() or 2) // 2))
     chunk = max(2, args.e2e_chunk)
-    e2e_steps = args.e2e_steps or K
+    e2e_steps = 0 if args.profile else (args.e2e_steps or K)
     es = B.Synth(n, SEED + 0x10000 * rank, k_peers=K_PEERS)
     ea = B.Arena(n, device=local_rank, n_rings=e2e_threads)
     assert ea.group_alloc_range(n) == 0
@@ -314,7 +316,7 @@ def main():
         e2e_s += time.perf_counter() - t0
         e2e_timed += m
         h2d_bytes += sum(sum(x.nbytes for x in pj) for pj in parts)
-    h2d = h2d_bytes / e2e_timed
+    h2d = h2d_bytes / max(1, e2e_timed)
     d2h = 8 * n + 4 * ((n + 31) // 32) + 4
     clocks = sampler.stop()
 
@@ -330,7 +332,7 @@ def main():
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     ms_max, e2e_max = mx[0].item(), mx[1].item()
     value = sm[2].item() / (ms_max * 1e-3)
-    e2e_value = sm[3].item() / e2e_max
+    e2e_value = sm[3].item() / e2e_max if e2e_max > 0 else None
 
     if rank == 0:
         kernels = []
@@ -358,14 +360,15 @@ def main():
                          "peak_source": peak_src},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_timed, "ms_per_step": 1e3 * e2e_max / e2e_timed,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_timed,
+                    "ms_per_step": 1e3 * e2e_max / max(1, e2e_timed),
                     "host_threads": e2e_threads, "pipelined_chunk": chunk,
                     "api": "raftgpu_enqueue_append_resp + raftgpu_step_begin/_wait (READ_COMMITTED)"},
             "gpu_launches": 2 * K,
             "clocks": clocks,
             "counters": {"recomputes": sm[4].item(), "advanced": sm[5].item(), "records": sm[6].item()},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.profile:
             threads = os.cpu_count() or 1
             v, done, _ = cpu_leg(n, SEED, 64, threads, budget_s=15.0)
             line["cpu_baseline"] = {

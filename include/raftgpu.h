@@ -318,11 +318,15 @@ int32_t raftgpu_step(raftgpu_arena *arena, uint32_t flags, raftgpu_step_result *
 /* Results of the last completed step, in arena-owned pinned memory, valid until
  * the next raftgpu_step_wait: adv_bitmap has bit g set iff group g advanced
  * (LightReady.commit_index, raw_node.rs:643-650); committed[g] is meaningful
- * for advanced groups when RAFTGPU_STEP_READ_COMMITTED was set; record_results
- * holds one byte per record in submission order (wave 0 rings in ring order,
- * then later waves) when RAFTGPU_STEP_READ_RESULTS was set. */
+ * for advanced groups when RAFTGPU_STEP_READ_COMMITTED was set. */
 int32_t raftgpu_step_results(raftgpu_arena *arena, const uint32_t **adv_bitmap,
-                             const uint64_t **committed, const uint8_t **record_results);
+                             const uint64_t **committed);
+/* Per-record result bytes (RAFTGPU_RES_*) of the last completed step for the
+ * records enqueued on `ring`, in that ring's enqueue order (EXT records get 0);
+ * needs RAFTGPU_STEP_READ_RESULTS.  *out_n = records enqueued on the ring; with
+ * out == NULL only the count is returned. */
+int32_t raftgpu_step_record_results(raftgpu_arena *arena, uint32_t ring, uint8_t *out,
+                                    uint64_t out_capacity, uint64_t *out_n);
 
 /* ---- votes ----------------------------------------- */
 

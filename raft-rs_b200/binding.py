@@ -154,7 +154,8 @@ def lib() -> C.CDLL:
             "raftgpu_step_begin": ([vp, u32], i32),
             "raftgpu_step_wait": ([vp, C.POINTER(StepResult)], i32),
             "raftgpu_step": ([vp, u32, C.POINTER(StepResult)], i32),
-            "raftgpu_step_results": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)], i32),
+            "raftgpu_step_results": ([vp, C.POINTER(vp), C.POINTER(vp)], i32),
+            "raftgpu_step_record_results": ([vp, u32, vp, u64, C.POINTER(u64)], i32),
             "raftgpu_reset_votes": ([vp, u32], i32),
             "raftgpu_record_vote": ([vp, u32, u32, i32], i32),
             "raftgpu_tally_votes": ([vp, vp, u32, u32, vp], i32),
@@ -445,17 +446,25 @@ class Arena:
         self._ck(self._L.raftgpu_step(self._h, flags, C.byref(r)), "step")
         return r
 
-    def step_results(self, n_groups: int, n_records: int = 0):
-        """(adv_bitmap u32[], committed u64[] | None, record results u8[] | None) views."""
-        pa, pc, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._ck(self._L.raftgpu_step_results(self._h, C.byref(pa), C.byref(pc), C.byref(pr)),
-                 "step_results")
+    def step_results(self, n_groups: int):
+        """(adv_bitmap u32[], committed u64[] | None) views into the arena's pinned results."""
+        pa, pc = C.c_void_p(), C.c_void_p()
+        self._ck(self._L.raftgpu_step_results(self._h, C.byref(pa), C.byref(pc)), "step_results")
         words = (n_groups + 31) // 32
         bm = np.ctypeslib.as_array(C.cast(pa, C.POINTER(C.c_uint32)), shape=(words,))
         com = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_uint64)), shape=(n_groups,)) if pc.value else None
-        res = np.ctypeslib.as_array(C.cast(pr, C.POINTER(C.c_uint8)), shape=(n_records,)) \
-            if pr.value and n_records else None
-        return bm, com, res
+        return bm, com
+
+    def record_results(self, ring: int = 0) -> np.ndarray:
+        """Result bytes of the records enqueued on `ring` in the last step, in enqueue order."""
+        n = C.c_uint64()
+        self._ck(self._L.raftgpu_step_record_results(self._h, ring, None, 0, C.byref(n)),
+                 "step_record_results")
+        out = np.zeros(n.value, dtype=np.uint8)
+        if n.value:
+            self._ck(self._L.raftgpu_step_record_results(self._h, ring, out.ctypes.data, n.value,
+                                                         C.byref(n)), "step_record_results")
+        return out
 
     # -- votes
     def reset_votes(self, g):

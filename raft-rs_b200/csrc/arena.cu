@@ -4,6 +4,7 @@
 // The arena owns every byte of device and pinned memory.  There is no CPU
 // compute path: without a CUDA device arena creation fails with
 // RAFTGPU_ERR_NO_DEVICE and nothing else can be called.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -20,22 +21,40 @@ using namespace raftgpu;
 
 namespace {
 
-constexpr int kNumSets = 2;  // double-buffered staging
+constexpr int kNumSets = 2;        // double-buffered staging
+constexpr uint32_t kChunk = 8192;  // records per staging chunk (192 KiB)
+
+struct OverflowRec {
+    raftgpu_append_resp rec;
+    uint32_t ring;
+    uint64_t seq;  // position in the ring's enqueue order
+};
+
+// One caller thread's staging ring: a list of chunks of the set's shared pinned
+// buffer.  Only its owner thread touches it between steps.
+struct Ring {
+    std::vector<uint32_t> chunks;        // chunk indices, in fill order
+    uint32_t fill = kChunk;              // records used in the last chunk (kChunk = need a new one)
+    uint64_t seq = 0;                    // records enqueued on this ring (wave 0 + overflow)
+    std::vector<uint64_t> overflow_seq;  // seq numbers that went to a later wave (ascending)
+};
 
 struct StagingSet {
     // host (pinned)
-    raftgpu_append_resp *h_recs = nullptr;  // [n_rings][ring_records] wave-0 records
+    raftgpu_append_resp *h_recs = nullptr;      // [n_chunks][kChunk] wave-0 records, shared by all rings
     raftgpu_append_resp *h_overflow = nullptr;  // later waves, packed at submit time
     uint32_t *h_adv_bitmap = nullptr;
     uint64_t *h_committed = nullptr;
     uint8_t *h_results = nullptr;
     uint32_t *h_step_adv = nullptr;
     // host (pageable)
-    std::vector<uint64_t> ring_count;
+    std::vector<Ring> rings;
+    std::atomic<uint32_t> next_chunk{0};
     uint8_t *touched = nullptr;  // [cap] one bit per peer slot: cell has a record in wave 0
     std::mutex overflow_mu;
-    std::unordered_map<uint64_t, uint32_t> overflow_depth;       // cell -> waves used beyond 0
-    std::vector<std::vector<raftgpu_append_resp>> overflow_waves;  // wave w+1 records
+    std::unordered_map<uint64_t, uint32_t> overflow_depth;      // cell -> waves used beyond 0
+    std::vector<std::vector<OverflowRec>> overflow_waves;       // wave w+1 records
+    std::vector<std::pair<uint32_t, uint64_t>> overflow_order;  // (ring, seq) per submitted overflow rec
     // device
     raftgpu_append_resp *d_recs = nullptr;
     uint32_t *d_adv_bitmap = nullptr;
@@ -47,6 +66,7 @@ struct StagingSet {
     bool in_flight = false;
     bool dirty = false;  // touched[] has bits set
     uint32_t flags = 0;
+    uint64_t wave0_slots = 0;  // staged wave-0 slots (chunks used * kChunk)
     raftgpu_step_result result{};
 };
 
@@ -56,8 +76,10 @@ struct raftgpu_arena {
     int device = 0;
     uint32_t cap = 0;
     uint32_t n_rings = 0;
-    uint32_t ring_records = 0;
+    uint32_t n_chunks = 0;  // chunks in each set's shared staging buffer
     uint64_t overflow_records = 0;
+    uint32_t voter_hint = 0;                 // superset of every group's voter slots (recompute_kernel)
+    int grid_recompute = 0, grid_apply = 0;  // persistent grid sizes (blocks)
     Columns cols{};
     unsigned long long *d_counters = nullptr;
     void *d_scratch = nullptr;  // 256 B for single-group queries
@@ -93,15 +115,14 @@ int32_t fail(raftgpu_arena *a, int32_t code, const std::string &msg) {
     do {                                                                                     \
         cudaError_t e_ = (call);                                                             \
         if (e_ != cudaSuccess) {                                                             \
-            return fail((a), RAFTGPU_ERR_CUDA,                                               \
-                        std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+            return fail((a), RAFTGPU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
         }                                                                                    \
     } while (0)
 
-#define CKL(a)                                                                               \
-    do {                                                                                     \
-        cudaError_t e_ = cudaGetLastError();                                                 \
-        if (e_ != cudaSuccess)                                                               \
+#define CKL(a)                                                                                    \
+    do {                                                                                          \
+        cudaError_t e_ = cudaGetLastError();                                                      \
+        if (e_ != cudaSuccess)                                                                    \
             return fail((a), RAFTGPU_ERR_CUDA, std::string("launch: ") + cudaGetErrorString(e_)); \
     } while (0)
 
@@ -124,17 +145,15 @@ int32_t pin_alloc(raftgpu_arena *a, T **p, size_t count) {
     if (e != cudaSuccess)
         return fail(a, RAFTGPU_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     a->pinned_bytes += bytes;
-    memset(*p, 0, bytes);
     return RAFTGPU_OK;
 }
 
-inline bool group_ok(const raftgpu_arena *a, uint32_t g) {
-    return g < a->cap && a->allocated[g];
-}
+inline bool group_ok(const raftgpu_arena *a, uint32_t g) { return g < a->cap && a->allocated[g]; }
 
 inline uint32_t present_mask(uint32_t meta) {
     return RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
 }
+inline uint32_t voter_mask(uint32_t meta) { return RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta); }
 
 inline cudaStream_t pick_stream(raftgpu_arena *a, void *stream) {
     return stream ? static_cast<cudaStream_t>(stream) : a->s_compute;
@@ -142,22 +161,24 @@ inline cudaStream_t pick_stream(raftgpu_arena *a, void *stream) {
 
 inline uint32_t div_up(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 
-int32_t launch_recompute(raftgpu_arena *a, cudaStream_t st, uint32_t first, uint32_t n,
+int32_t launch_recompute(raftgpu_arena *a, cudaStream_t st, uint32_t first, uint32_t n, uint32_t hint,
                          uint32_t *d_adv, uint64_t *d_commit, uint64_t *d_mci, uint8_t *d_gc,
                          uint32_t *d_step_adv) {
     if (n == 0) return RAFTGPU_OK;
     const uint32_t base = first & ~31u;
     const uint64_t threads = static_cast<uint64_t>(first - base) + n;
-    recompute_kernel<<<div_up(threads, 256), 256, 0, st>>>(a->cols, first, n, d_adv, d_commit, d_mci,
-                                                          d_gc, d_step_adv, a->d_counters);
+    const uint32_t blocks = std::min<uint32_t>(div_up(threads, 256), static_cast<uint32_t>(a->grid_recompute));
+    recompute_kernel<<<blocks, 256, 0, st>>>(a->cols, first, n, hint, d_adv, d_commit, d_mci, d_gc,
+                                            d_step_adv, a->d_counters);
     CKL(a);
     return RAFTGPU_OK;
 }
 
-int32_t launch_apply(raftgpu_arena *a, cudaStream_t st, const raftgpu_append_resp *d_recs,
-                     uint64_t n, uint8_t *d_results) {
+int32_t launch_apply(raftgpu_arena *a, cudaStream_t st, const raftgpu_append_resp *d_recs, uint64_t n,
+                     uint8_t *d_results) {
     if (n == 0) return RAFTGPU_OK;
-    apply_kernel<<<div_up(n, 256), 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
+    const uint32_t blocks = std::min<uint32_t>(div_up(n, 256), static_cast<uint32_t>(a->grid_apply));
+    apply_kernel<<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
     CKL(a);
     return RAFTGPU_OK;
 }
@@ -224,9 +245,12 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     // pad the column stride so every column (and every slot row of it) is 128-byte aligned
     a->cap = (max_groups + 127u) & ~127u;
     a->n_rings = n_rings ? n_rings : 16;
-    a->ring_records =
-        ring_records ? ring_records
-                     : static_cast<uint32_t>(std::max<uint64_t>(4096, (5ull * a->cap) / a->n_rings));
+    // staging capacity per step, shared by all rings: ring_records * n_rings when given, else
+    // ~5 records per group (a full round of a 5-peer deployment is ~3.5); plus one partially
+    // filled chunk per ring
+    const uint64_t want = ring_records ? static_cast<uint64_t>(ring_records) * a->n_rings
+                                       : std::max<uint64_t>(4096, 5ull * a->cap);
+    a->n_chunks = div_up(want, kChunk) + a->n_rings;
     a->overflow_records = std::max<uint64_t>(4096, a->cap / 4);
     int32_t rc = RAFTGPU_OK;
     auto bail = [&](int32_t code) {
@@ -234,24 +258,29 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
         destroy(a);
         return code;
     };
-#define TRY(x)                       \
-    do {                             \
-        rc = (x);                    \
+#define TRY(x)                                 \
+    do {                                       \
+        rc = (x);                              \
         if (rc != RAFTGPU_OK) return bail(rc); \
     } while (0)
-#define TRYC(call)                                                                   \
-    do {                                                                             \
-        cudaError_t e_ = (call);                                                     \
-        if (e_ != cudaSuccess) {                                                     \
-            a->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);      \
-            return bail(RAFTGPU_ERR_CUDA);                                           \
-        }                                                                            \
+#define TRYC(call)                                                              \
+    do {                                                                        \
+        cudaError_t e_ = (call);                                                \
+        if (e_ != cudaSuccess) {                                                \
+            a->last_error = std::string(#call) + ": " + cudaGetErrorString(e_); \
+            return bail(RAFTGPU_ERR_CUDA);                                      \
+        }                                                                       \
     } while (0)
     TRYC(cudaSetDevice(device));
     cudaDeviceProp prop{};
     TRYC(cudaGetDeviceProperties(&prop, device));
     a->sm_count = prop.multiProcessorCount;
     a->l2_bytes = static_cast<uint64_t>(prop.l2CacheSize);
+    int occ = 0;
+    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, recompute_kernel, 256, 0));
+    a->grid_recompute = std::max(1, occ) * a->sm_count;
+    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel, 256, 0));
+    a->grid_apply = std::max(1, occ) * a->sm_count;
     TRYC(cudaStreamCreateWithFlags(&a->s_compute, cudaStreamNonBlocking));
     TRYC(cudaStreamCreateWithFlags(&a->s_h2d, cudaStreamNonBlocking));
     TRYC(cudaStreamCreateWithFlags(&a->s_d2h, cudaStreamNonBlocking));
@@ -276,16 +305,16 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     TRY(dev_alloc(a, reinterpret_cast<uint8_t **>(&a->d_scratch), 256));
     TRY(pin_alloc(a, reinterpret_cast<uint8_t **>(&a->h_scratch), 256));
 
-    const uint64_t ring_total = static_cast<uint64_t>(a->n_rings) * a->ring_records;
-    const uint64_t rec_total = ring_total + a->overflow_records;
+    const uint64_t wave0_total = static_cast<uint64_t>(a->n_chunks) * kChunk;
+    const uint64_t rec_total = wave0_total + a->overflow_records;
     for (auto &s : a->sets) {
-        TRY(pin_alloc(a, &s.h_recs, ring_total));
+        TRY(pin_alloc(a, &s.h_recs, wave0_total));
         TRY(pin_alloc(a, &s.h_overflow, a->overflow_records));
         TRY(pin_alloc(a, &s.h_adv_bitmap, a->cap / 32));
         TRY(pin_alloc(a, &s.h_committed, a->cap));
         TRY(pin_alloc(a, &s.h_results, rec_total));
         TRY(pin_alloc(a, &s.h_step_adv, 4));
-        s.ring_count.assign(a->n_rings, 0);
+        s.rings.assign(a->n_rings, Ring());
         s.touched = static_cast<uint8_t *>(calloc(a->cap, 1));
         if (!s.touched) return bail(RAFTGPU_ERR_NOMEM);
         TRY(dev_alloc(a, &s.d_recs, rec_total, false));
@@ -302,15 +331,11 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     TRYC(cudaDeviceSynchronize());
 #undef TRY
 #undef TRYC
-    // groups beyond max_groups exist only as padding of the column stride
-    a->cap = a->cap;  // stride
-    a->allocated.resize(a->cap);
     *out = a;
-    (void)max_groups;
     return RAFTGPU_OK;
 }
 
-// Single-thread control-plane kernel + sync on the compute stream.
+// Control-plane kernel(s) + sync on the compute stream.
 template <typename F>
 int32_t sync_op(raftgpu_arena *a, F &&launch) {
     CK(a, cudaSetDevice(a->device));
@@ -346,21 +371,28 @@ bool column_desc(raftgpu_arena *a, int32_t col, ColumnDesc *d) {
 }
 
 // Move a duplicate-cell record (and the EXT record of a reject) to a later wave.
-void push_overflow(StagingSet &s, uint64_t cell, const raftgpu_append_resp *r, int n_recs) {
+void push_overflow(StagingSet &s, uint64_t cell, const raftgpu_append_resp *r, int n_recs, uint32_t ring,
+                   uint64_t seq) {
     std::lock_guard<std::mutex> lk(s.overflow_mu);
     const uint32_t depth = s.overflow_depth[cell]++;  // 0 -> wave 1
     if (s.overflow_waves.size() <= depth) s.overflow_waves.resize(depth + 1);
-    for (int k = 0; k < n_recs; k++) s.overflow_waves[depth].push_back(r[k]);
+    for (int k = 0; k < n_recs; k++) s.overflow_waves[depth].push_back(OverflowRec{r[k], ring, seq + k});
 }
 
+// make a finished set reusable for filling
 int32_t reclaim_set(raftgpu_arena *a, StagingSet &s) {
-    // make a finished set reusable for filling
     if (s.in_flight) return RAFTGPU_ERR_BUSY;
     if (s.dirty) {
         memset(s.touched, 0, a->cap);
         s.dirty = false;
     }
-    std::fill(s.ring_count.begin(), s.ring_count.end(), 0);
+    for (auto &r : s.rings) {
+        r.chunks.clear();
+        r.fill = kChunk;
+        r.seq = 0;
+        r.overflow_seq.clear();
+    }
+    s.next_chunk.store(0);
     s.overflow_depth.clear();
     s.overflow_waves.clear();
     return RAFTGPU_OK;
@@ -487,7 +519,10 @@ int32_t raftgpu_group_set_conf(raftgpu_arena *a, uint32_t g, uint32_t incoming_m
     int32_t rc = sync_op(a, [&](cudaStream_t st) {
         conf_kernel<<<1, 1, 0, st>>>(a->cols, g, meta, now & ~was, was & ~now, next_idx);
     });
-    if (rc == RAFTGPU_OK) a->h_meta[g] = meta;
+    if (rc == RAFTGPU_OK) {
+        a->h_meta[g] = meta;
+        a->voter_hint |= voter_mask(meta);
+    }
     return rc;
 }
 
@@ -594,8 +629,8 @@ int32_t raftgpu_assign_commit_group(raftgpu_arena *a, uint32_t g, uint32_t peer_
     });
 }
 
-int32_t raftgpu_column_write(raftgpu_arena *a, int32_t column, uint32_t peer_slot,
-                             uint32_t first_group, uint32_t n, const void *host_src) {
+int32_t raftgpu_column_write(raftgpu_arena *a, int32_t column, uint32_t peer_slot, uint32_t first_group,
+                             uint32_t n, const void *host_src) {
     ColumnDesc d;
     if (!a || !host_src || !column_desc(a, column, &d)) return RAFTGPU_ERR_INVALID;
     if (static_cast<uint64_t>(first_group) + n > a->cap || (d.per_peer && peer_slot >= RAFTGPU_SLOTS))
@@ -605,12 +640,20 @@ int32_t raftgpu_column_write(raftgpu_arena *a, int32_t column, uint32_t peer_slo
     CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(d.base) + off, host_src, n * d.elem,
                           cudaMemcpyHostToDevice, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));
-    if (column == RAFTGPU_COL_META) memcpy(&a->h_meta[first_group], host_src, n * 4ull);
+    if (column == RAFTGPU_COL_META) {
+        const uint32_t *m = static_cast<const uint32_t *>(host_src);
+        uint32_t hint = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            a->h_meta[first_group + i] = m[i];
+            hint |= voter_mask(m[i]);
+        }
+        a->voter_hint |= hint;
+    }
     return RAFTGPU_OK;
 }
 
-int32_t raftgpu_column_read(raftgpu_arena *a, int32_t column, uint32_t peer_slot,
-                            uint32_t first_group, uint32_t n, void *host_dst) {
+int32_t raftgpu_column_read(raftgpu_arena *a, int32_t column, uint32_t peer_slot, uint32_t first_group,
+                            uint32_t n, void *host_dst) {
     ColumnDesc d;
     if (!a || !host_dst || !column_desc(a, column, &d)) return RAFTGPU_ERR_INVALID;
     if (static_cast<uint64_t>(first_group) + n > a->cap || (d.per_peer && peer_slot >= RAFTGPU_SLOTS))
@@ -630,10 +673,7 @@ int32_t raftgpu_maximal_committed_index(raftgpu_arena *a, uint32_t g, uint64_t *
     if (!a || !out_index) return RAFTGPU_ERR_INVALID;
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
-    // The query must not commit: run the pass on a scratch copy of `committed`
-    // semantics by reading mci only.  The kernel's commit step is idempotent with
-    // Raft::maybe_commit, but maximal_committed_index alone (tracker.rs:294-298)
-    // has no side effect, so mask the commit by using the mci-only launch below.
+    // tracker.rs:294-298 has no side effect: the query kernel only evaluates the quorum.
     uint64_t *d_mci = static_cast<uint64_t *>(a->d_scratch);
     uint8_t *d_gc = static_cast<uint8_t *>(a->d_scratch) + 8;
     mci_kernel<<<1, 32, 0, a->s_compute>>>(a->cols, g, d_mci, d_gc);
@@ -645,25 +685,23 @@ int32_t raftgpu_maximal_committed_index(raftgpu_arena *a, uint32_t g, uint64_t *
     return RAFTGPU_OK;
 }
 
-int32_t raftgpu_maybe_commit(raftgpu_arena *a, uint32_t g, int32_t *out_advanced,
-                             uint64_t *out_committed) {
+int32_t raftgpu_maybe_commit(raftgpu_arena *a, uint32_t g, int32_t *out_advanced, uint64_t *out_committed) {
     if (!a) return RAFTGPU_ERR_INVALID;
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
     uint32_t *d_word = static_cast<uint32_t *>(a->d_scratch) + 8;  // offset 32
     CK(a, cudaMemsetAsync(d_word, 0, 4, a->s_compute));
-    // bitmap pointer is indexed by g >> 5 from group 0: bias it so word (g >> 5) lands on d_word
-    int32_t rc = launch_recompute(a, a->s_compute, g, 1, d_word - (g >> 5), nullptr, nullptr, nullptr,
-                                  nullptr);
+    // the bitmap pointer is indexed by g >> 5 from group 0: bias it so that word lands on d_word
+    int32_t rc = launch_recompute(a, a->s_compute, g, 1, voter_mask(a->h_meta[g]), d_word - (g >> 5),
+                                  nullptr, nullptr, nullptr, nullptr);
     if (rc != RAFTGPU_OK) return rc;
-    CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(a->h_scratch) + 32, d_word, 4, cudaMemcpyDeviceToHost,
-                          a->s_compute));
-    CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(a->h_scratch) + 40, a->cols.committed + g, 8,
-                          cudaMemcpyDeviceToHost, a->s_compute));
+    uint8_t *hs = static_cast<uint8_t *>(a->h_scratch);
+    CK(a, cudaMemcpyAsync(hs + 32, d_word, 4, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaMemcpyAsync(hs + 40, a->cols.committed + g, 8, cudaMemcpyDeviceToHost, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));
-    const uint32_t word = *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(a->h_scratch) + 32);
+    const uint32_t word = *reinterpret_cast<uint32_t *>(hs + 32);
     if (out_advanced) *out_advanced = (word >> (g & 31)) & 1u;
-    if (out_committed) *out_committed = *reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(a->h_scratch) + 40);
+    if (out_committed) *out_committed = *reinterpret_cast<uint64_t *>(hs + 40);
     return RAFTGPU_OK;
 }
 
@@ -673,8 +711,8 @@ int32_t raftgpu_recompute(raftgpu_arena *a, void *stream, uint32_t first, uint32
     if (!a) return RAFTGPU_ERR_INVALID;
     if (static_cast<uint64_t>(first) + n > a->cap) return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
-    return launch_recompute(a, pick_stream(a, stream), first, n, d_adv_bitmap, d_commit_out, d_mci_out,
-                            d_gc_out, nullptr);
+    return launch_recompute(a, pick_stream(a, stream), first, n, a->voter_hint, d_adv_bitmap,
+                            d_commit_out, d_mci_out, d_gc_out, nullptr);
 }
 
 int32_t raftgpu_apply_device(raftgpu_arena *a, void *stream, const raftgpu_append_resp *d_records,
@@ -690,14 +728,18 @@ int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftg
     if (ring >= a->n_rings) return RAFTGPU_ERR_RANGE;
     StagingSet &s = a->sets[a->fill];
     if (s.in_flight) return RAFTGPU_ERR_BUSY;
-    raftgpu_append_resp *dst = s.h_recs + static_cast<size_t>(ring) * a->ring_records;
-    uint64_t cnt = s.ring_count[ring];
+    Ring &rg = s.rings[ring];
+    raftgpu_append_resp *dst =
+        rg.chunks.empty() ? nullptr : s.h_recs + static_cast<size_t>(rg.chunks.back()) * kChunk;
+    uint32_t fill = rg.fill;
+    uint64_t seq = rg.seq;
     s.dirty = true;
+    int32_t rc = RAFTGPU_OK;
     for (uint64_t i = 0; i < n; i++) {
         const raftgpu_append_resp &r = recs[i];
         if (r.flags & RAFTGPU_REC_EXT) continue;  // copied together with its REJECT
-        const int n_recs = ((r.flags & RAFTGPU_REC_REJECT) && i + 1 < n &&
-                            (recs[i + 1].flags & RAFTGPU_REC_EXT)) ? 2 : 1;
+        const int n_recs =
+            ((r.flags & RAFTGPU_REC_REJECT) && i + 1 < n && (recs[i + 1].flags & RAFTGPU_REC_EXT)) ? 2 : 1;
         bool dup = false;
         if (r.group < a->cap && r.peer_slot < RAFTGPU_SLOTS) {
             const uint8_t bit = static_cast<uint8_t>(1u << r.peer_slot);
@@ -706,18 +748,33 @@ int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftg
             t |= bit;
         }
         if (dup) {
-            push_overflow(s, (static_cast<uint64_t>(r.group) << 3) | r.peer_slot, &r, n_recs);
+            push_overflow(s, (static_cast<uint64_t>(r.group) << 3) | r.peer_slot, &r, n_recs, ring, seq);
+            for (int k = 0; k < n_recs; k++) rg.overflow_seq.push_back(seq + k);
+            seq += n_recs;
             continue;
         }
-        if (cnt + n_recs > a->ring_records) {
-            s.ring_count[ring] = cnt;
-            return fail(a, RAFTGPU_ERR_FULL, "staging ring full");
+        if (fill + n_recs > kChunk) {
+            // pad the tail of the chunk with no-op records (EXT records are skipped by the kernel)
+            for (; dst && fill < kChunk; fill++) {
+                dst[fill] = raftgpu_append_resp{0, 0, RAFTGPU_REC_EXT, 0, 0, 0};
+            }
+            const uint32_t ch = s.next_chunk.fetch_add(1);
+            if (ch >= a->n_chunks) {
+                rc = fail(a, RAFTGPU_ERR_FULL, "staging ring full");
+                fill = kChunk;
+                break;
+            }
+            rg.chunks.push_back(ch);
+            dst = s.h_recs + static_cast<size_t>(ch) * kChunk;
+            fill = 0;
         }
-        dst[cnt++] = r;
-        if (n_recs == 2) dst[cnt++] = recs[i + 1];
+        dst[fill++] = r;
+        if (n_recs == 2) dst[fill++] = recs[i + 1];
+        seq += n_recs;
     }
-    s.ring_count[ring] = cnt;
-    return RAFTGPU_OK;
+    rg.fill = fill;
+    rg.seq = seq;
+    return rc;
 }
 
 int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
@@ -725,24 +782,29 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     if (a->pending >= 0) return fail(a, RAFTGPU_ERR_BUSY, "previous step not waited for");
     CK(a, cudaSetDevice(a->device));
     StagingSet &s = a->sets[a->fill];
-    // H2D: wave 0 = the rings back to back, then the later waves
-    uint64_t off = 0;
-    for (uint32_t r = 0; r < a->n_rings; r++) {
-        const uint64_t cnt = s.ring_count[r];
-        if (!cnt) continue;
-        CK(a, cudaMemcpyAsync(s.d_recs + off, s.h_recs + static_cast<size_t>(r) * a->ring_records,
-                              cnt * sizeof(raftgpu_append_resp), cudaMemcpyHostToDevice, a->s_h2d));
-        off += cnt;
+    // pad every ring's last chunk, then ONE H2D of the used prefix of the shared buffer
+    uint64_t n_real = 0;
+    for (auto &rg : s.rings) {
+        n_real += rg.seq - rg.overflow_seq.size();
+        if (rg.chunks.empty()) continue;
+        raftgpu_append_resp *dst = s.h_recs + static_cast<size_t>(rg.chunks.back()) * kChunk;
+        for (; rg.fill < kChunk; rg.fill++) dst[rg.fill] = raftgpu_append_resp{0, 0, RAFTGPU_REC_EXT, 0, 0, 0};
     }
-    const uint64_t wave0 = off;
+    const uint32_t used_chunks = std::min(s.next_chunk.load(), a->n_chunks);
+    const uint64_t wave0 = static_cast<uint64_t>(used_chunks) * kChunk;
+    if (wave0)
+        CK(a, cudaMemcpyAsync(s.d_recs, s.h_recs, wave0 * sizeof(raftgpu_append_resp),
+                              cudaMemcpyHostToDevice, a->s_h2d));
     std::vector<uint64_t> wave_sizes;
     uint64_t ov = 0;
+    s.overflow_order.clear();
     for (auto &w : s.overflow_waves) {
-        if (ov + w.size() > a->overflow_records)
-            return fail(a, RAFTGPU_ERR_FULL, "overflow staging full");
-        memcpy(s.h_overflow + ov, w.data(), w.size() * sizeof(raftgpu_append_resp));
+        if (ov + w.size() > a->overflow_records) return fail(a, RAFTGPU_ERR_FULL, "overflow staging full");
+        for (const OverflowRec &o : w) {
+            s.h_overflow[ov++] = o.rec;
+            s.overflow_order.emplace_back(o.ring, o.seq);
+        }
         wave_sizes.push_back(w.size());
-        ov += w.size();
     }
     if (ov)
         CK(a, cudaMemcpyAsync(s.d_recs + wave0, s.h_overflow, ov * sizeof(raftgpu_append_resp),
@@ -762,9 +824,9 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     }
     CK(a, cudaMemsetAsync(s.d_step_adv, 0, 4, a->s_compute));
     const uint32_t hi = a->hi;
-    rc = launch_recompute(a, a->s_compute, 0, hi, s.d_adv_bitmap,
-                          (flags & RAFTGPU_STEP_READ_COMMITTED) ? s.d_commit_out : nullptr, nullptr,
-                          nullptr, s.d_step_adv);
+    rc = launch_recompute(a, a->s_compute, 0, hi, a->voter_hint, s.d_adv_bitmap,
+                          (flags & RAFTGPU_STEP_READ_COMMITTED) ? s.d_commit_out : nullptr, nullptr, nullptr,
+                          s.d_step_adv);
     if (rc != RAFTGPU_OK) return rc;
     CK(a, cudaEventRecord(s.ev_compute, a->s_compute));
 
@@ -782,14 +844,16 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
 
     s.in_flight = true;
     s.flags = flags;
-    s.result.n_records = woff;
-    s.result.n_waves = static_cast<uint32_t>((wave0 ? 1 : 0) + wave_sizes.size());
+    s.wave0_slots = wave0;
+    s.result.n_records = n_real + ov;
+    s.result.n_waves = static_cast<uint32_t>((n_real ? 1 : 0) + wave_sizes.size());
     s.result.n_groups = hi;
     a->pending = a->fill;
-    // flip: the other set becomes the fill target (it must have been waited for)
+    // flip: the other set becomes the fill target (its step must have been waited for)
     const int other = 1 - a->fill;
     rc = reclaim_set(a, a->sets[other]);
     if (rc != RAFTGPU_OK) return rc;
+    if (a->last_done == other) a->last_done = -1;  // its results are gone
     a->fill = other;
     return RAFTGPU_OK;
 }
@@ -813,14 +877,47 @@ int32_t raftgpu_step(raftgpu_arena *a, uint32_t flags, raftgpu_step_result *out)
     return raftgpu_step_wait(a, out);
 }
 
-int32_t raftgpu_step_results(raftgpu_arena *a, const uint32_t **adv_bitmap, const uint64_t **committed,
-                             const uint8_t **record_results) {
+int32_t raftgpu_step_results(raftgpu_arena *a, const uint32_t **adv_bitmap, const uint64_t **committed) {
     if (!a) return RAFTGPU_ERR_INVALID;
     if (a->last_done < 0) return fail(a, RAFTGPU_ERR_INVALID, "no completed step");
     StagingSet &s = a->sets[a->last_done];
     if (adv_bitmap) *adv_bitmap = s.h_adv_bitmap;
     if (committed) *committed = (s.flags & RAFTGPU_STEP_READ_COMMITTED) ? s.h_committed : nullptr;
-    if (record_results) *record_results = (s.flags & RAFTGPU_STEP_READ_RESULTS) ? s.h_results : nullptr;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_step_record_results(raftgpu_arena *a, uint32_t ring, uint8_t *out, uint64_t cap,
+                                    uint64_t *out_n) {
+    if (!a || !out_n) return RAFTGPU_ERR_INVALID;
+    if (ring >= a->n_rings) return RAFTGPU_ERR_RANGE;
+    if (a->last_done < 0) return fail(a, RAFTGPU_ERR_INVALID, "no completed step");
+    StagingSet &s = a->sets[a->last_done];
+    if (!(s.flags & RAFTGPU_STEP_READ_RESULTS))
+        return fail(a, RAFTGPU_ERR_INVALID, "step ran without RAFTGPU_STEP_READ_RESULTS");
+    const Ring &rg = s.rings[ring];
+    *out_n = rg.seq;
+    if (!out) return RAFTGPU_OK;
+    if (cap < rg.seq) return RAFTGPU_ERR_INVALID;
+    // later-wave records of this ring, by seq
+    for (size_t k = 0; k < s.overflow_order.size(); k++)
+        if (s.overflow_order[k].first == ring) out[s.overflow_order[k].second] = s.h_results[s.wave0_slots + k];
+    // wave-0 records fill the remaining seq positions in chunk order
+    size_t ov = 0;
+    uint64_t seq = 0;
+    for (size_t ci = 0; ci < rg.chunks.size() && seq < rg.seq; ci++) {
+        const uint8_t *res = s.h_results + static_cast<size_t>(rg.chunks[ci]) * kChunk;
+        const raftgpu_append_resp *src = s.h_recs + static_cast<size_t>(rg.chunks[ci]) * kChunk;
+        for (uint32_t k = 0; k < kChunk && seq < rg.seq; k++) {
+            // padding: an EXT record that does not follow a REJECT of the same chunk
+            if ((src[k].flags & RAFTGPU_REC_EXT) && (k == 0 || !(src[k - 1].flags & RAFTGPU_REC_REJECT))) continue;
+            while (ov < rg.overflow_seq.size() && rg.overflow_seq[ov] == seq) {
+                ov++;
+                seq++;
+            }
+            if (seq >= rg.seq) break;
+            out[seq++] = res[k];
+        }
+    }
     return RAFTGPU_OK;
 }
 
@@ -829,9 +926,7 @@ int32_t raftgpu_step_results(raftgpu_arena *a, const uint32_t **adv_bitmap, cons
 int32_t raftgpu_reset_votes(raftgpu_arena *a, uint32_t g) {
     if (!a) return RAFTGPU_ERR_INVALID;
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
-    return sync_op(a, [&](cudaStream_t st) {
-        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 4, 0, 0, nullptr);
-    });
+    return sync_op(a, [&](cudaStream_t st) { group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 4, 0, 0, nullptr); });
 }
 
 int32_t raftgpu_record_vote(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, int32_t vote) {
@@ -847,8 +942,7 @@ int32_t raftgpu_tally_votes(raftgpu_arena *a, void *stream, uint32_t first, uint
     if (static_cast<uint64_t>(first) + n > a->cap) return RAFTGPU_ERR_RANGE;
     if (n == 0) return RAFTGPU_OK;
     CK(a, cudaSetDevice(a->device));
-    tally_kernel<<<div_up(n, 256), 256, 0, pick_stream(a, stream)>>>(a->cols, first, n, d_out,
-                                                                   a->d_counters);
+    tally_kernel<<<div_up(n, 256), 256, 0, pick_stream(a, stream)>>>(a->cols, first, n, d_out, a->d_counters);
     CKL(a);
     return RAFTGPU_OK;
 }
@@ -861,10 +955,10 @@ int32_t raftgpu_vote_result(raftgpu_arena *a, uint32_t g, int32_t *out_result, u
     uint32_t *d = static_cast<uint32_t *>(a->d_scratch) + 16;  // offset 64
     tally_kernel<<<1, 32, 0, a->s_compute>>>(a->cols, g, 1, d - g, a->d_counters);
     CKL(a);
-    CK(a, cudaMemcpyAsync(static_cast<uint8_t *>(a->h_scratch) + 64, d, 4, cudaMemcpyDeviceToHost,
-                          a->s_compute));
+    uint8_t *hs = static_cast<uint8_t *>(a->h_scratch);
+    CK(a, cudaMemcpyAsync(hs + 64, d, 4, cudaMemcpyDeviceToHost, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));
-    const uint32_t w = *reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(a->h_scratch) + 64);
+    const uint32_t w = *reinterpret_cast<uint32_t *>(hs + 64);
     if (out_result) *out_result = w & 0xff;
     if (out_granted) *out_granted = (w >> 8) & 0xff;
     if (out_rejected) *out_rejected = (w >> 16) & 0xff;
@@ -877,8 +971,7 @@ int32_t raftgpu_counters_read(raftgpu_arena *a, raftgpu_counters *out) {
     if (!a || !out) return RAFTGPU_ERR_INVALID;
     CK(a, cudaSetDevice(a->device));
     static_assert(sizeof(raftgpu_counters) == kCntCount * 8, "counter layout");
-    CK(a, cudaMemcpyAsync(a->h_scratch, a->d_counters, sizeof(*out), cudaMemcpyDeviceToHost,
-                          a->s_compute));
+    CK(a, cudaMemcpyAsync(a->h_scratch, a->d_counters, sizeof(*out), cudaMemcpyDeviceToHost, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));
     memcpy(out, a->h_scratch, sizeof(*out));
     return RAFTGPU_OK;

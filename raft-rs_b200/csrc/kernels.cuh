@@ -51,24 +51,50 @@ __device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > 
 // MajorityConfig::committed_index without group commit (majority.rs:70-101):
 // the q-th largest acked index of the voters in `mask`, q = n/2 + 1
 // (util.rs:118-120); the empty config yields u64::MAX (majority.rs:71-75).
-// Non-members are zeroed, which leaves the top-q ranks of the members intact
-// (q <= n), so the selection runs over all 8 slots branch-free: the answer is
-// the largest value that at least q slots are >= to.
+
+// compare-exchange, larger value first
+__device__ __forceinline__ void cex(uint64_t &a, uint64_t &b) {
+    const bool lt = a < b;
+    const uint64_t hi = lt ? b : a, lo = lt ? a : b;
+    a = hi;
+    b = lo;
+}
+
+// General form.  Non-members are zeroed, which leaves the top-q ranks of the
+// members intact (q <= n); a 19-comparator network sorts the 8 slots in
+// descending order (the reference's stable sort_by, majority.rs:95 -- ties are
+// equal values, so any order of them selects the same index) and the q-th
+// element is picked.
 __device__ __forceinline__ uint64_t quorum_index(const uint64_t (&v)[kSlots], uint32_t mask) {
     if (mask == 0) return UINT64_MAX;
     const uint32_t q = (static_cast<uint32_t>(__popc(mask)) >> 1) + 1;
-    uint64_t w[kSlots];
-#pragma unroll
-    for (int i = 0; i < kSlots; i++) w[i] = ((mask >> i) & 1u) ? v[i] : 0ull;
-    uint64_t best = 0;
-#pragma unroll
-    for (int i = 0; i < kSlots; i++) {
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int j = 0; j < kSlots; j++) cnt += (w[j] >= w[i]) ? 1u : 0u;
-        if (cnt >= q && w[i] > best) best = w[i];
-    }
-    return best;
+    uint64_t w0 = (mask & 1u) ? v[0] : 0, w1 = (mask & 2u) ? v[1] : 0, w2 = (mask & 4u) ? v[2] : 0,
+             w3 = (mask & 8u) ? v[3] : 0, w4 = (mask & 16u) ? v[4] : 0, w5 = (mask & 32u) ? v[5] : 0,
+             w6 = (mask & 64u) ? v[6] : 0, w7 = (mask & 128u) ? v[7] : 0;
+    // Batcher / optimal 19-comparator network for 8 inputs
+    cex(w0, w1); cex(w2, w3); cex(w4, w5); cex(w6, w7);
+    cex(w0, w2); cex(w1, w3); cex(w4, w6); cex(w5, w7);
+    cex(w1, w2); cex(w5, w6); cex(w0, w4); cex(w3, w7);
+    cex(w1, w5); cex(w2, w6);
+    cex(w1, w4); cex(w3, w6);
+    cex(w2, w4); cex(w3, w5);
+    cex(w3, w4);
+    // q in 1..5 for up to 8 voters
+    uint64_t r = w0;
+    r = q == 2 ? w1 : r;
+    r = q == 3 ? w2 : r;
+    r = q == 4 ? w3 : r;
+    r = q == 5 ? w4 : r;
+    return r;
+}
+
+// The common 5-voter case (q = 3): the median, by the classic 10 min/max form
+// med5(a..e) = med3(e, max(min(a,b),min(c,d)), min(max(a,b),max(c,d))).
+__device__ __forceinline__ uint64_t median5(uint64_t a, uint64_t b, uint64_t c, uint64_t d,
+                                            uint64_t e) {
+    const uint64_t lo = umax64(umin64(a, b), umin64(c, d));
+    const uint64_t hi = umin64(umax64(a, b), umax64(c, d));
+    return umax64(umin64(lo, hi), umin64(umax64(lo, hi), e));
 }
 
 // MajorityConfig::committed_index WITH group commit (majority.rs:70-124), the
@@ -165,11 +191,26 @@ __global__ void mci_kernel(Columns c, uint32_t g, uint64_t *out_mci, uint8_t *ou
     *out_gc = use_gc ? 1 : 0;
 }
 
-// Warp-aggregated counter bump: one atomic per warp.
-__device__ __forceinline__ void warp_count(unsigned long long *counters, int which, bool pred) {
-    const unsigned ballot = __ballot_sync(0xffffffffu, pred);
-    if ((threadIdx.x & 31) == 0 && ballot != 0)
-        atomicAdd(&counters[which], static_cast<unsigned long long>(__popc(ballot)));
+// Block-level counter flush: per-thread tallies -> warp shuffle reduce -> shared
+// -> ONE global atomic per counter per block.  (v1 issued one atomic per warp per
+// counter; ~10^5 same-address atomics serialise in L2 and dominated both kernels.)
+template <int kN>
+__device__ __forceinline__ void block_flush_counts(const uint32_t (&local)[kN], const int (&which)[kN],
+                                                   unsigned long long *counters,
+                                                   uint32_t *extra_u32 /* nullable, gets local[1] */) {
+    __shared__ uint32_t s_cnt[kN];
+    if (threadIdx.x < kN) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kN; k++) {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, local[k]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[k], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < kN && s_cnt[threadIdx.x]) {
+        atomicAdd(&counters[which[threadIdx.x]], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+        if (extra_u32 && threadIdx.x == 1) atomicAdd(extra_u32, s_cnt[1]);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -180,49 +221,92 @@ __device__ __forceinline__ void warp_count(unsigned long long *counters, int whi
 //        committed = mci; prs[self].update_committed      raft.rs:896-900
 // term(mci) == term is the range test term_start <= mci <= last_index.
 //
-// One thread per group; thread t of the grid handles group (first & ~31) + t so
-// that a warp always covers exactly one 32-bit word of the advanced bitmap.
+// Persistent grid: each warp walks 32-group tiles (one word of the advanced
+// bitmap) with a grid stride.  `hint` is a superset guess of the voter slots in
+// this arena (the host keeps the union of all voter masks): the matched loads of
+// the hinted slots are issued together with meta / committed / term_start /
+// last_index, so a tile costs ONE round trip to HBM instead of two (meta first,
+// then the slots it names).  Voter slots outside the hint are fetched after
+// meta arrives -- correct for any hint, fast for a tight one.
 // Algorithmic bytes per group: 8K (matched) + 4 (meta) + 24 (committed,
 // term_start, last_index) read, 8 written when advanced.
 __global__ void __launch_bounds__(256)
-recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t *__restrict__ adv_bitmap,
-                 uint64_t *__restrict__ commit_out, uint64_t *__restrict__ mci_out,
-                 uint8_t *__restrict__ gc_out, uint32_t *__restrict__ step_advanced,
-                 unsigned long long *__restrict__ counters) {
+recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint,
+                 uint32_t *__restrict__ adv_bitmap, uint64_t *__restrict__ commit_out,
+                 uint64_t *__restrict__ mci_out, uint8_t *__restrict__ gc_out,
+                 uint32_t *__restrict__ step_advanced, unsigned long long *__restrict__ counters) {
     const uint32_t base = first & ~31u;
-    const uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const uint64_t g64 = base + t;
-    const bool active = g64 >= first && g64 < static_cast<uint64_t>(first) + n;
-    const uint32_t g = static_cast<uint32_t>(g64);
+    const uint32_t n_tiles = static_cast<uint32_t>((static_cast<uint64_t>(first - base) + n + 31) >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint64_t end = static_cast<uint64_t>(first) + n;
+    uint32_t local[2] = {0, 0};  // recomputes, advanced
 
-    bool advanced = false;
-    if (active) {
-        const uint32_t meta = c.meta[g];
-        const uint64_t committed = c.committed[g];
-        const uint64_t term_start = c.term_start[g];
-        const uint64_t last_index = c.last_index[g];
-        uint64_t mci;
-        bool use_gc;
-        group_mci(c, g, meta, mci, use_gc);
-        if (mci_out) mci_out[g] = mci;
-        if (gc_out) gc_out[g] = use_gc ? 1 : 0;
+    for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
+        const uint64_t g64 = static_cast<uint64_t>(base) + (static_cast<uint64_t>(tile) << 5) + lane;
+        const bool active = g64 >= first && g64 < end;
+        const uint32_t g = static_cast<uint32_t>(g64);
+        bool advanced = false;
+        if (active) {
+            // one batch of independent loads
+            const uint32_t meta = c.meta[g];
+            uint64_t v[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; s++)
+                v[s] = ((hint >> s) & 1u) ? c.matched[static_cast<size_t>(s) * c.cap + g] : 0ull;
+            const uint64_t committed = c.committed[g];
+            const uint64_t term_start = c.term_start[g];
+            const uint64_t last_index = c.last_index[g];
 
-        // RaftLog::maybe_commit, raft_log.rs:488, in range form.
-        advanced = mci > committed && mci >= term_start && mci <= last_index;
-        if (advanced) {
-            c.committed[g] = mci;  // commit_to: mci <= last_index, never the fatal! branch
-            if (commit_out) commit_out[g] = mci;
-            if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
-                const size_t cell = static_cast<size_t>(RAFTGPU_META_SELF(meta)) * c.cap + g;
-                if (mci > c.peer_committed[cell]) c.peer_committed[cell] = mci;
+            const uint32_t in = RAFTGPU_META_IN(meta), out = RAFTGPU_META_OUT(meta);
+            const uint32_t voters = in | out;
+            const uint32_t missing = voters & ~hint;
+            if (missing) {  // hint was too small for this group: second trip for the rest
+#pragma unroll
+                for (int s = 0; s < kSlots; s++)
+                    if ((missing >> s) & 1u) v[s] = c.matched[static_cast<size_t>(s) * c.cap + g];
+            }
+            uint64_t mci;
+            bool use_gc;
+            if ((meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT)) == 0x1fu) {
+                // 5 voters in slots 0..4, no joint config, no group commit: q = 3 = the median
+                mci = median5(v[0], v[1], v[2], v[3], v[4]);
+                use_gc = false;
+            } else if (!(meta & RAFTGPU_META_GROUP_COMMIT)) {
+                const uint64_t i_idx = quorum_index(v, in);
+                const uint64_t o_idx = quorum_index(v, out);  // empty outgoing => u64::MAX
+                mci = umin64(i_idx, o_idx);                    // joint.rs:50
+                use_gc = (in == 0) && (out == 0);              // majority.rs:71-75 vs :99-101
+            } else {
+                uint64_t gid[kSlots];
+                for (int s = 0; s < kSlots; s++)
+                    gid[s] = ((voters >> s) & 1u)
+                                 ? c.commit_group_id[static_cast<size_t>(s) * c.cap + g] : 0ull;
+                uint64_t i_idx, o_idx;
+                bool i_gc, o_gc;
+                majority_group_commit(v, gid, in, &i_idx, &i_gc);
+                majority_group_commit(v, gid, out, &o_idx, &o_gc);
+                mci = umin64(i_idx, o_idx);
+                use_gc = i_gc && o_gc;
+            }
+            if (mci_out) mci_out[g] = mci;
+            if (gc_out) gc_out[g] = use_gc ? 1 : 0;
+
+            // RaftLog::maybe_commit, raft_log.rs:488, in range form.
+            advanced = mci > committed && mci >= term_start && mci <= last_index;
+            if (advanced) {
+                c.committed[g] = mci;  // commit_to: mci <= last_index, never the fatal! branch
+                if (commit_out) commit_out[g] = mci;
+                if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
+                    const size_t cell = static_cast<size_t>(RAFTGPU_META_SELF(meta)) * c.cap + g;
+                    if (mci > c.peer_committed[cell]) c.peer_committed[cell] = mci;
+                }
             }
         }
-    }
-
-    const unsigned act = __ballot_sync(0xffffffffu, active);
-    const unsigned adv = __ballot_sync(0xffffffffu, advanced);
-    if ((threadIdx.x & 31) == 0 && act != 0) {
-        if (adv_bitmap) {
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        const unsigned adv = __ballot_sync(0xffffffffu, advanced);
+        if (lane == 0 && act != 0 && adv_bitmap) {
             uint32_t *word = &adv_bitmap[g64 >> 5];
             if (act == 0xffffffffu) {
                 *word = adv;
@@ -231,12 +315,11 @@ recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t *__restrict__ a
                 if (adv) atomicOr(word, adv);
             }
         }
-        atomicAdd(&counters[kCntRecomputes], static_cast<unsigned long long>(__popc(act)));
-        if (adv) {
-            atomicAdd(&counters[kCntAdvanced], static_cast<unsigned long long>(__popc(adv)));
-            if (step_advanced) atomicAdd(step_advanced, static_cast<uint32_t>(__popc(adv)));
-        }
+        local[0] += active ? 1u : 0u;
+        local[1] += advanced ? 1u : 0u;
     }
+    const int which[2] = {kCntRecomputes, kCntAdvanced};
+    block_flush_counts<2>(local, which, counters, step_advanced);
 }
 
 // ---------------------------------------------------------------------------
@@ -254,16 +337,22 @@ __device__ __forceinline__ void reset_state(Cell &p, uint32_t state, uint64_t *p
 }
 
 // apply_kernel: the per-message prefix of Raft::handle_append_response
-// (raft.rs:1663-1743) for one wave of records, one thread per record.  Within a
-// wave every (group, peer) cell is touched by at most one record, so threads
-// never race on a cell and no atomics are needed on the columns.
+// (raft.rs:1663-1743) for one wave of records, one thread per record, persistent
+// grid-stride loop.  Within a wave every (group, peer) cell is touched by at most
+// one record, so threads never race on a cell and no atomics are needed on the
+// columns.  The record names its cell, so meta and the cell's matched / next_idx /
+// pflags / committed_index are fetched in ONE batch of independent loads.
+// Algorithmic bytes per record: 24 (record) + RMW of matched, next_idx,
+// committed_index (48) + flag byte and meta (~4) = 76.
 __global__ void __launch_bounds__(256)
 apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n,
              uint8_t *__restrict__ results, unsigned long long *__restrict__ counters) {
-    const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    bool is_record = false, updated = false, is_reject = false, decremented = false,
-         no_progress = false;
-    if (i < n) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    uint32_t local[5] = {0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress
+    // keep whole warps in the loop so the flush below runs converged
+    const uint64_t n_pad = (n + 31) & ~31ull;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        if (i >= n) continue;
         const uint64_t *p = reinterpret_cast<const uint64_t *>(recs + i);
         const uint64_t w0 = p[0];
         const uint64_t index = p[1];
@@ -273,22 +362,24 @@ apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n
         const uint32_t rflags = static_cast<uint32_t>(w0 >> 40) & 0xffu;
         uint32_t res = 0;
         if (!(rflags & RAFTGPU_REC_EXT)) {
-            is_record = true;
-            uint32_t present = 0;
-            if (g < c.cap && slot < kSlots) {
-                const uint32_t meta = c.meta[g];
-                present = RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
-            }
-            if (!((present >> slot) & 1u)) {
+            local[0]++;
+            const bool in_range = g < c.cap && slot < kSlots;
+            const size_t cell = in_range ? static_cast<size_t>(slot) * c.cap + g : 0;
+            // one batch of independent loads (cell 0 / group 0 is a harmless stand-in when
+            // the record is out of range; nothing is written in that case)
+            const uint32_t meta = c.meta[in_range ? g : 0];
+            Cell pr;
+            pr.matched = c.matched[cell];
+            pr.next_idx = c.next_idx[cell];
+            pr.flags = c.pflags[cell];
+            const uint64_t peer_committed = c.peer_committed[cell];
+            const uint32_t present =
+                RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
+            if (!in_range || !((present >> slot) & 1u)) {
                 // raft.rs:1663-1673: no progress available for m.from
-                no_progress = true;
+                local[4]++;
                 res = RAFTGPU_RES_NO_PROGRESS;
             } else {
-                const size_t cell = static_cast<size_t>(slot) * c.cap + g;
-                Cell pr;
-                pr.matched = c.matched[cell];
-                pr.next_idx = c.next_idx[cell];
-                pr.flags = c.pflags[cell];
                 const uint64_t matched0 = pr.matched, next0 = pr.next_idx;
                 const uint32_t flags0 = pr.flags;
                 const uint32_t state = pr.flags & RAFTGPU_PF_STATE_MASK;
@@ -300,17 +391,17 @@ apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n
                     if (pr.matched < index) {  // progress.rs:138-150
                         pr.matched = index;
                         pr.flags &= ~RAFTGPU_PF_PAUSED;
-                        updated = true;
+                        local[1]++;
                         res = RAFTGPU_RES_OK;
                     }
                     if (pr.next_idx < index + 1) pr.next_idx = index + 1;
                 } else {
                     pr.flags |= RAFTGPU_PF_RECENT_ACTIVE;  // raft.rs:1674
                     // raft.rs:1677 pr.update_committed(m.commit), progress.rs:153-157
-                    if (commit > c.peer_committed[cell]) c.peer_committed[cell] = commit;
+                    if (commit > peer_committed) c.peer_committed[cell] = commit;
 
                     if (rflags & RAFTGPU_REC_REJECT) {
-                        is_reject = true;
+                        local[2]++;
                         uint64_t hint = 0, request_snapshot = RAFTGPU_INVALID_INDEX;
                         if (i + 1 < n) {
                             const uint64_t *e = reinterpret_cast<const uint64_t *>(recs + i + 1);
@@ -346,7 +437,7 @@ apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n
                             ok = true;
                         }
                         if (ok) {
-                            decremented = true;
+                            local[3]++;
                             res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
                             if (state == RAFTGPU_STATE_REPLICATE) {
                                 // raft.rs:1716-1718 become_probe (progress.rs:95-107, not Snapshot)
@@ -370,7 +461,7 @@ apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n
                         }
                         if (pr.next_idx < index + 1) pr.next_idx = index + 1;
                         if (need_update) {
-                            updated = true;
+                            local[1]++;
                             res = RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u);
                             if (state == RAFTGPU_STATE_PROBE) {
                                 // raft.rs:1730 become_replicate, progress.rs:110-114
@@ -395,11 +486,8 @@ apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n
         }
         if (results) results[i] = static_cast<uint8_t>(res);
     }
-    warp_count(counters, kCntRecords, is_record);
-    warp_count(counters, kCntUpdates, updated);
-    warp_count(counters, kCntRejects, is_reject);
-    warp_count(counters, kCntDecrements, decremented);
-    warp_count(counters, kCntNoProgress, no_progress);
+    const int which[5] = {kCntRecords, kCntUpdates, kCntRejects, kCntDecrements, kCntNoProgress};
+    block_flush_counts<5>(local, which, counters, nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -442,7 +530,9 @@ tally_kernel(Columns c, uint32_t first, uint32_t n, uint32_t *__restrict__ out,
         const uint32_t voters = in | outm;  // tracker.rs:320-322
         out[g] = r | (__popc(yes & voters) << 8) | (__popc(no & voters) << 16);
     }
-    warp_count(counters, kCntVotes, active);
+    const uint32_t local[1] = {active ? 1u : 0u};
+    const int which[1] = {kCntVotes};
+    block_flush_counts<1>(local, which, counters, nullptr);
 }
 
 // ---------------------------------------------------------------------------

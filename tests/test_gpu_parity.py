@@ -110,8 +110,7 @@ def apply_recs(arena, recs, g):
     recs["group"] = g
     arena.enqueue(recs)
     r = arena.step(B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS)
-    _, _, res = arena.step_results(arena.get_info().hi, int(r.n_records))
-    return r, res.copy()
+    return r, arena.record_results(0)
 
 
 def progress_cols(state, matched, next_idx, pending_snapshot=0, paused=False):
@@ -294,8 +293,8 @@ def test_enqueue_splits_duplicate_cells_into_waves(small):
     got = read_one(small, g)
     assert_columns_equal(got, want, 1)
     assert int(got.pflags[1, 0]) & 3 == O.STATE_REPLICATE and int(got.committed[0]) == 12
-    # results come back in submission order: wave 0 first, then later waves
-    assert sorted(res.tolist()) == sorted(want_res.tolist())
+    # results come back per ring in ENQUEUE order, whichever wave a record ran in
+    assert np.array_equal(res, want_res)
     small.group_free(g)
 
 
@@ -326,7 +325,8 @@ def test_synthetic_stream_elementwise(name):
         arena.enqueue(recs[:half], ring=0)          # two rings, as two caller threads would
         arena.enqueue(recs[half:], ring=1)
         r = arena.step(B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS)
-        bm, com, res = arena.step_results(n, int(r.n_records))
+        bm, com = arena.step_results(n)
+        res = np.concatenate([arena.record_results(0), arena.record_results(1)])
         want_res = O.arena_apply(ref, recs, mode=0)
         want_adv, want_bm, _, _ = O.arena_recompute(ref)
         assert r.n_waves == 1 and r.n_records == len(recs)

@@ -101,6 +101,20 @@ class ClockSampler:
         return out
 
 
+def gpu_local_cpus(torch, device: int):
+    """CPUs on the NUMA node the GPU's PCIe root hangs off (sysfs local_cpulist)."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        cpus = set()
+        for tok in open(path).read().strip().split(","):
+            lo, _, hi = tok.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus & os.sched_getaffinity(0)
+    except Exception:
+        return set()
+
+
 def cpu_leg(n_groups, seed, rounds_wanted, threads, budget_s=20.0):
     """The oracle (oracle/raft_oracle.c: apply + recompute, range-partitioned over `threads`
     pthreads) on a bounded sample of the same workload.  Only used as the CPU baseline."""
@@ -187,6 +201,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference "
                          "for the CPU baseline arm)")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    local_cpus = gpu_local_cpus(torch, local_rank)
+    if local_cpus:
+        # like `numactl --cpunodebind`: host staging threads and their buffers next to the GPU
+        os.sched_setaffinity(0, local_cpus)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -269,7 +288,7 @@ def main():
     # chunks of `chunk` pipelined steps (the next batch is staged while one is in flight); the
     # records of the following chunk are regenerated between chunks, untimed, into the same few
     # host buffers.
-    e2e_threads = args.e2e_threads or min(16, max(1, (os.cpu_count() or 2) // 2))
+    e2e_threads = args.e2e_threads or min(32, max(1, len(os.sched_getaffinity(0)) // 2))
     chunk = max(2, args.e2e_chunk)
     e2e_steps = 0 if args.profile else (args.e2e_steps or K)
     es = B.Synth(n, SEED + 0x10000 * rank, k_peers=K_PEERS)
@@ -294,6 +313,7 @@ def main():
 
     flags = B.STEP_READ_COMMITTED
     e2e_s, e2e_timed, h2d_bytes, adv_total, first_chunk = 0.0, 0, 0, 0, True
+    phase = [0.0, 0.0, 0.0]   # host seconds in enqueue / step_begin / step_wait
     while e2e_timed < e2e_steps:
         m = min(chunk, e2e_steps - e2e_timed)
         parts = [split(es.next_round(bufs[j])) for j in range(m)]      # untimed generation
@@ -308,11 +328,19 @@ def main():
             dist.barrier()
         t0 = time.perf_counter()
         enqueue(parts[0])
+        phase[0] += time.perf_counter() - t0
         for j in range(m):
+            ta = time.perf_counter()
             ea.step_begin(flags)
+            tb = time.perf_counter()
             if j + 1 < m:
                 enqueue(parts[j + 1])     # stage the next batch while this one is in flight
+            tc = time.perf_counter()
             adv_total += ea.step_wait().n_advanced
+            td = time.perf_counter()
+            phase[1] += tb - ta
+            phase[0] += tc - tb
+            phase[2] += td - tc
         e2e_s += time.perf_counter() - t0
         e2e_timed += m
         h2d_bytes += sum(sum(x.nbytes for x in pj) for pj in parts)
@@ -363,13 +391,18 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": e2e_timed,
                     "ms_per_step": 1e3 * e2e_max / max(1, e2e_timed),
                     "host_threads": e2e_threads, "pipelined_chunk": chunk,
+                    "host_cpus_bound": len(local_cpus) or None,
+                    "host_ms_per_step": {"enqueue": 1e3 * phase[0] / max(1, e2e_timed),
+                                         "step_begin": 1e3 * phase[1] / max(1, e2e_timed),
+                                         "step_wait": 1e3 * phase[2] / max(1, e2e_timed)},
                     "api": "raftgpu_enqueue_append_resp + raftgpu_step_begin/_wait (READ_COMMITTED)"},
             "gpu_launches": 2 * K,
             "clocks": clocks,
             "counters": {"recomputes": sm[4].item(), "advanced": sm[5].item(), "records": sm[6].item()},
         }
         if world == 1 and not args.no_cpu_baseline and not args.profile:
-            threads = os.cpu_count() or 1
+            os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core
+            threads = len(all_cpus)
             v, done, _ = cpu_leg(n, SEED, 64, threads, budget_s=15.0)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",

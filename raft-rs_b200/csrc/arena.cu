@@ -6,6 +6,7 @@
 // RAFTGPU_ERR_NO_DEVICE and nothing else can be called.
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,6 +15,8 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+
+#include <sched.h>
 
 #include "kernels.cuh"
 
@@ -79,7 +82,12 @@ struct raftgpu_arena {
     uint32_t n_chunks = 0;  // chunks in each set's shared staging buffer
     uint64_t overflow_records = 0;
     uint32_t voter_hint = 0;                 // superset of every group's voter slots (recompute_kernel)
-    int grid_recompute = 0, grid_apply = 0;  // persistent grid sizes (blocks)
+    int grid_recompute = 0, grid_recompute5 = 0, grid_apply = 0;  // persistent grid sizes (blocks)
+    uint32_t n_simple5 = 0;                  // groups whose meta is the plain 5-voter configuration
+    bool force_general = false;              // RAFTGPU_FORCE_GENERAL=1: never take the simple5 kernels
+    bool use_tma = false;                    // RAFTGPU_TMA=1 selects the TMA-fed recompute kernel
+    uint32_t tma_smem = 0;                   // dynamic shared memory for the TMA stage ring
+    int tma_stages_cap = 0;                  // RAFTGPU_TMA_STAGES (tuning knob)
     Columns cols{};
     unsigned long long *d_counters = nullptr;
     void *d_scratch = nullptr;  // 256 B for single-group queries
@@ -89,6 +97,8 @@ struct raftgpu_arena {
     int fill = 0;        // set currently being filled by enqueue
     int last_done = -1;  // set whose results raftgpu_step_results exposes
     int pending = -1;    // set submitted by step_begin and not yet waited for
+    // control plane: single-group calls share the scratch buffers and the meta mirror
+    std::mutex ctl_mu;
     // group allocation
     std::mutex alloc_mu;
     std::vector<uint32_t> free_list;
@@ -105,6 +115,50 @@ struct raftgpu_arena {
 namespace {
 
 thread_local std::string g_create_error;
+
+// Pinned staging must live on the NUMA node the GPU's PCIe root hangs off: DMA reads of
+// remote-socket memory cross the inter-socket link and lose about half of the H2D bandwidth
+// (measured on the 2-socket B200 hosts: 27 GB/s remote vs ~55 GB/s local).  cudaHostAlloc
+// places pages by first touch, so the allocating thread is moved onto the GPU-local CPUs
+// (sysfs local_cpulist of the device) for the duration of the allocations.
+struct LocalCpuGuard {
+    cpu_set_t saved;
+    bool active = false;
+    explicit LocalCpuGuard(int device) {
+        char bus[32] = {0};
+        if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return;
+        for (char *p = bus; *p; p++) *p = static_cast<char>(tolower(*p));
+        std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) return;
+        char line[512] = {0};
+        const bool ok = fgets(line, sizeof(line), f) != nullptr;
+        fclose(f);
+        if (!ok) return;
+        cpu_set_t want;
+        CPU_ZERO(&want);
+        int n_set = 0;
+        for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+            int lo = 0, hi = 0;
+            const int k = sscanf(tok, "%d-%d", &lo, &hi);
+            if (k == 1) hi = lo;
+            if (k < 1) continue;
+            for (int c = lo; c <= hi && c < CPU_SETSIZE; c++) {
+                CPU_SET(c, &want);
+                n_set++;
+            }
+        }
+        if (!n_set) return;
+        if (sched_getaffinity(0, sizeof(saved), &saved) != 0) return;
+        cpu_set_t both;
+        CPU_AND(&both, &want, &saved);  // stay inside the cpuset we are allowed to use
+        if (CPU_COUNT(&both) == 0) return;
+        if (sched_setaffinity(0, sizeof(both), &both) == 0) active = true;
+    }
+    ~LocalCpuGuard() {
+        if (active) sched_setaffinity(0, sizeof(saved), &saved);
+    }
+};
 
 int32_t fail(raftgpu_arena *a, int32_t code, const std::string &msg) {
     if (a) a->last_error = msg;
@@ -145,6 +199,7 @@ int32_t pin_alloc(raftgpu_arena *a, T **p, size_t count) {
     if (e != cudaSuccess)
         return fail(a, RAFTGPU_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     a->pinned_bytes += bytes;
+    memset(*p, 0, bytes);  // first touch decides the NUMA node
     return RAFTGPU_OK;
 }
 
@@ -161,15 +216,57 @@ inline cudaStream_t pick_stream(raftgpu_arena *a, void *stream) {
 
 inline uint32_t div_up(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 
+// True when every group of [first, first+n) is the plain 5-voter configuration in slots 0..4
+// (no joint half, no group commit): the host's meta mirror is authoritative, so the kernels
+// specialised for that case need no per-group check.
+inline bool is_simple5(uint32_t meta) { return (meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT)) == 0x1fu; }
+inline bool range_simple5(const raftgpu_arena *a, uint32_t first, uint32_t n) {
+    return a->n_simple5 == a->hi && static_cast<uint64_t>(first) + n <= a->hi;
+}
+inline void set_meta(raftgpu_arena *a, uint32_t g, uint32_t meta) {
+    a->n_simple5 += static_cast<uint32_t>(is_simple5(meta)) - static_cast<uint32_t>(is_simple5(a->h_meta[g]));
+    a->h_meta[g] = meta;
+    a->voter_hint |= voter_mask(meta);
+}
+
 int32_t launch_recompute(raftgpu_arena *a, cudaStream_t st, uint32_t first, uint32_t n, uint32_t hint,
                          uint32_t *d_adv, uint64_t *d_commit, uint64_t *d_mci, uint8_t *d_gc,
                          uint32_t *d_step_adv) {
     if (n == 0) return RAFTGPU_OK;
+    const bool simple5 = range_simple5(a, first, n) && !a->force_general;
+    if (simple5) hint = 0x1fu;
+    if (a->use_tma && n >= 16u * kTile && hint != 0) {
+        // TMA-fed pipeline: one persistent CTA per SM, as many stages as fit in shared memory
+        const uint32_t stage_bytes =
+            (static_cast<uint32_t>(__builtin_popcount(hint & 0xffu)) + 3u) * kTile * 8u + kTile * 4u;
+        int stages = std::min<int>(kMaxStages, static_cast<int>(a->tma_smem / stage_bytes));
+        if (a->tma_stages_cap > 0) stages = std::min(stages, a->tma_stages_cap);
+        if (stages >= 2) {
+            const uint32_t base = first - (first % kTile);
+            const uint32_t tiles = div_up(static_cast<uint64_t>(first - base) + n, kTile);
+            const uint32_t blocks = std::min<uint32_t>(tiles, static_cast<uint32_t>(a->sm_count));
+            const size_t smem = static_cast<size_t>(stages) * stage_bytes;
+            if (simple5)
+                recompute_tma_kernel<true><<<blocks, kTmaThreads, smem, st>>>(
+                    a->cols, first, n, hint, stages, d_adv, d_commit, d_mci, d_gc, d_step_adv, a->d_counters);
+            else
+                recompute_tma_kernel<false><<<blocks, kTmaThreads, smem, st>>>(
+                    a->cols, first, n, hint, stages, d_adv, d_commit, d_mci, d_gc, d_step_adv, a->d_counters);
+            CKL(a);
+            return RAFTGPU_OK;
+        }
+    }
     const uint32_t base = first & ~31u;
     const uint64_t threads = static_cast<uint64_t>(first - base) + n;
-    const uint32_t blocks = std::min<uint32_t>(div_up(threads, 256), static_cast<uint32_t>(a->grid_recompute));
-    recompute_kernel<<<blocks, 256, 0, st>>>(a->cols, first, n, hint, d_adv, d_commit, d_mci, d_gc,
-                                            d_step_adv, a->d_counters);
+    if (simple5) {
+        const uint32_t blocks = std::min<uint32_t>(div_up(threads, 256), static_cast<uint32_t>(a->grid_recompute5));
+        recompute_kernel<true><<<blocks, 256, 0, st>>>(a->cols, first, n, hint, d_adv, d_commit, d_mci, d_gc,
+                                                      d_step_adv, a->d_counters);
+    } else {
+        const uint32_t blocks = std::min<uint32_t>(div_up(threads, 256), static_cast<uint32_t>(a->grid_recompute));
+        recompute_kernel<false><<<blocks, 256, 0, st>>>(a->cols, first, n, hint, d_adv, d_commit, d_mci, d_gc,
+                                                       d_step_adv, a->d_counters);
+    }
     CKL(a);
     return RAFTGPU_OK;
 }
@@ -277,10 +374,25 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     a->sm_count = prop.multiProcessorCount;
     a->l2_bytes = static_cast<uint64_t>(prop.l2CacheSize);
     int occ = 0;
-    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, recompute_kernel, 256, 0));
+    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, recompute_kernel<false>, 256, 0));
     a->grid_recompute = std::max(1, occ) * a->sm_count;
+    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, recompute_kernel<true>, 256, 0));
+    a->grid_recompute5 = std::max(1, occ) * a->sm_count;
     TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel, 256, 0));
     a->grid_apply = std::max(1, occ) * a->sm_count;
+    a->tma_smem = 200u * 1024u;
+    TRYC(cudaFuncSetAttribute(recompute_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(a->tma_smem)));
+    TRYC(cudaFuncSetAttribute(recompute_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(a->tma_smem)));
+    {
+        const char *e = getenv("RAFTGPU_TMA");
+        a->use_tma = e && e[0] == '1';
+        const char *f = getenv("RAFTGPU_FORCE_GENERAL");
+        a->force_general = f && f[0] == '1';
+        const char *t = getenv("RAFTGPU_TMA_STAGES");
+        if (t) a->tma_stages_cap = atoi(t);
+    }
     TRYC(cudaStreamCreateWithFlags(&a->s_compute, cudaStreamNonBlocking));
     TRYC(cudaStreamCreateWithFlags(&a->s_h2d, cudaStreamNonBlocking));
     TRYC(cudaStreamCreateWithFlags(&a->s_d2h, cudaStreamNonBlocking));
@@ -307,6 +419,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
 
     const uint64_t wave0_total = static_cast<uint64_t>(a->n_chunks) * kChunk;
     const uint64_t rec_total = wave0_total + a->overflow_records;
+    LocalCpuGuard numa_guard(device);  // pinned pages on the GPU-local NUMA node
     for (auto &s : a->sets) {
         TRY(pin_alloc(a, &s.h_recs, wave0_total));
         TRY(pin_alloc(a, &s.h_overflow, a->overflow_records));
@@ -487,6 +600,7 @@ int32_t raftgpu_group_alloc_range(raftgpu_arena *a, uint32_t n, uint32_t *out_fi
 
 int32_t raftgpu_group_free(raftgpu_arena *a, uint32_t g) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     // an empty configuration with no term range is inert in every kernel
     int32_t rc = sync_op(a, [&](cudaStream_t st) {
@@ -497,7 +611,7 @@ int32_t raftgpu_group_free(raftgpu_arena *a, uint32_t g) {
     CK(a, cudaMemsetAsync(a->cols.committed + g, 0, 8, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));
     std::lock_guard<std::mutex> lk(a->alloc_mu);
-    a->h_meta[g] = 0;
+    set_meta(a, g, 0);
     a->allocated[g] = 0;
     a->n_alloc--;
     a->free_list.push_back(g);
@@ -508,6 +622,7 @@ int32_t raftgpu_group_set_conf(raftgpu_arena *a, uint32_t g, uint32_t incoming_m
                                uint32_t outgoing_mask, uint32_t learner_mask, int32_t self_slot,
                                uint64_t next_idx) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     if ((incoming_mask | outgoing_mask | learner_mask) > 0xffu || self_slot >= RAFTGPU_SLOTS)
         return RAFTGPU_ERR_INVALID;
@@ -519,16 +634,14 @@ int32_t raftgpu_group_set_conf(raftgpu_arena *a, uint32_t g, uint32_t incoming_m
     int32_t rc = sync_op(a, [&](cudaStream_t st) {
         conf_kernel<<<1, 1, 0, st>>>(a->cols, g, meta, now & ~was, was & ~now, next_idx);
     });
-    if (rc == RAFTGPU_OK) {
-        a->h_meta[g] = meta;
-        a->voter_hint |= voter_mask(meta);
-    }
+    if (rc == RAFTGPU_OK) set_meta(a, g, meta);
     return rc;
 }
 
 int32_t raftgpu_group_reset(raftgpu_arena *a, uint32_t g, uint64_t term_start, uint64_t last_index,
                             uint64_t committed, uint64_t persisted) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     return sync_op(a, [&](cudaStream_t st) {
         reset_kernel<<<1, 1, 0, st>>>(a->cols, g, term_start, last_index, committed, persisted);
@@ -537,6 +650,7 @@ int32_t raftgpu_group_reset(raftgpu_arena *a, uint32_t g, uint64_t term_start, u
 
 int32_t raftgpu_group_become_leader(raftgpu_arena *a, uint32_t g) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     return sync_op(a, [&](cudaStream_t st) { become_leader_kernel<<<1, 1, 0, st>>>(a->cols, g); });
 }
@@ -544,6 +658,7 @@ int32_t raftgpu_group_become_leader(raftgpu_arena *a, uint32_t g) {
 int32_t raftgpu_group_set_log_bounds(raftgpu_arena *a, uint32_t g, uint64_t term_start,
                                      uint64_t last_index) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     return sync_op(a, [&](cudaStream_t st) {
         group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 0, term_start, last_index, nullptr);
@@ -552,6 +667,7 @@ int32_t raftgpu_group_set_log_bounds(raftgpu_arena *a, uint32_t g, uint64_t term
 
 int32_t raftgpu_group_commit_to(raftgpu_arena *a, uint32_t g, uint64_t to_commit) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     uint32_t *d = static_cast<uint32_t *>(a->d_scratch);
     uint32_t *h = static_cast<uint32_t *>(a->h_scratch);
@@ -566,6 +682,7 @@ int32_t raftgpu_group_commit_to(raftgpu_arena *a, uint32_t g, uint64_t to_commit
 
 int32_t raftgpu_group_get(raftgpu_arena *a, uint32_t g, raftgpu_group_state *out) {
     if (!a || !out) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     auto *d = static_cast<raftgpu_group_state *>(a->d_scratch);
     CK(a, cudaSetDevice(a->device));
@@ -579,6 +696,7 @@ int32_t raftgpu_group_get(raftgpu_arena *a, uint32_t g, raftgpu_group_state *out
 
 int32_t raftgpu_progress_get(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, raftgpu_progress *out) {
     if (!a || !out) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
     auto *d = static_cast<raftgpu_progress *>(a->d_scratch);
     CK(a, cudaSetDevice(a->device));
@@ -593,6 +711,7 @@ int32_t raftgpu_progress_get(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, r
 int32_t raftgpu_progress_set(raftgpu_arena *a, uint32_t g, uint32_t peer_slot,
                              const raftgpu_progress *in) {
     if (!a || !in) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
     if (!((present_mask(a->h_meta[g]) >> peer_slot) & 1u)) return RAFTGPU_ERR_PEER_NOT_FOUND;
     if (in->state > RAFTGPU_STATE_SNAPSHOT) return RAFTGPU_ERR_INVALID;
@@ -604,23 +723,22 @@ int32_t raftgpu_progress_set(raftgpu_arena *a, uint32_t g, uint32_t peer_slot,
 
 int32_t raftgpu_set_group_commit(raftgpu_arena *a, uint32_t g, int32_t enable) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     int32_t rc = sync_op(a, [&](cudaStream_t st) {
         group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 2, RAFTGPU_META_GROUP_COMMIT, enable ? 1 : 0,
                                         nullptr);
     });
-    if (rc == RAFTGPU_OK) {
-        if (enable)
-            a->h_meta[g] |= RAFTGPU_META_GROUP_COMMIT;
-        else
-            a->h_meta[g] &= ~RAFTGPU_META_GROUP_COMMIT;
-    }
+    if (rc == RAFTGPU_OK)
+        set_meta(a, g, enable ? (a->h_meta[g] | RAFTGPU_META_GROUP_COMMIT)
+                              : (a->h_meta[g] & ~RAFTGPU_META_GROUP_COMMIT));
     return rc;
 }
 
 int32_t raftgpu_assign_commit_group(raftgpu_arena *a, uint32_t g, uint32_t peer_slot,
                                     uint64_t commit_group_id) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
     // raft.rs:534-540: unknown peers are skipped silently
     if (!((present_mask(a->h_meta[g]) >> peer_slot) & 1u)) return RAFTGPU_OK;
@@ -633,6 +751,7 @@ int32_t raftgpu_column_write(raftgpu_arena *a, int32_t column, uint32_t peer_slo
                              uint32_t n, const void *host_src) {
     ColumnDesc d;
     if (!a || !host_src || !column_desc(a, column, &d)) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (static_cast<uint64_t>(first_group) + n > a->cap || (d.per_peer && peer_slot >= RAFTGPU_SLOTS))
         return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
@@ -642,12 +761,7 @@ int32_t raftgpu_column_write(raftgpu_arena *a, int32_t column, uint32_t peer_slo
     CK(a, cudaStreamSynchronize(a->s_compute));
     if (column == RAFTGPU_COL_META) {
         const uint32_t *m = static_cast<const uint32_t *>(host_src);
-        uint32_t hint = 0;
-        for (uint32_t i = 0; i < n; i++) {
-            a->h_meta[first_group + i] = m[i];
-            hint |= voter_mask(m[i]);
-        }
-        a->voter_hint |= hint;
+        for (uint32_t i = 0; i < n; i++) set_meta(a, first_group + i, m[i]);
     }
     return RAFTGPU_OK;
 }
@@ -656,6 +770,7 @@ int32_t raftgpu_column_read(raftgpu_arena *a, int32_t column, uint32_t peer_slot
                             uint32_t n, void *host_dst) {
     ColumnDesc d;
     if (!a || !host_dst || !column_desc(a, column, &d)) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (static_cast<uint64_t>(first_group) + n > a->cap || (d.per_peer && peer_slot >= RAFTGPU_SLOTS))
         return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
@@ -671,6 +786,7 @@ int32_t raftgpu_column_read(raftgpu_arena *a, int32_t column, uint32_t peer_slot
 int32_t raftgpu_maximal_committed_index(raftgpu_arena *a, uint32_t g, uint64_t *out_index,
                                         int32_t *out_use_group_commit) {
     if (!a || !out_index) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
     // tracker.rs:294-298 has no side effect: the query kernel only evaluates the quorum.
@@ -687,6 +803,7 @@ int32_t raftgpu_maximal_committed_index(raftgpu_arena *a, uint32_t g, uint64_t *
 
 int32_t raftgpu_maybe_commit(raftgpu_arena *a, uint32_t g, int32_t *out_advanced, uint64_t *out_committed) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
     uint32_t *d_word = static_cast<uint32_t *>(a->d_scratch) + 8;  // offset 32
@@ -925,12 +1042,14 @@ int32_t raftgpu_step_record_results(raftgpu_arena *a, uint32_t ring, uint8_t *ou
 
 int32_t raftgpu_reset_votes(raftgpu_arena *a, uint32_t g) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     return sync_op(a, [&](cudaStream_t st) { group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 4, 0, 0, nullptr); });
 }
 
 int32_t raftgpu_record_vote(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, int32_t vote) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
     return sync_op(a, [&](cudaStream_t st) {
         group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 5, peer_slot, vote ? 2 : 1, nullptr);
@@ -950,6 +1069,7 @@ int32_t raftgpu_tally_votes(raftgpu_arena *a, void *stream, uint32_t first, uint
 int32_t raftgpu_vote_result(raftgpu_arena *a, uint32_t g, int32_t *out_result, uint32_t *out_granted,
                             uint32_t *out_rejected) {
     if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
     CK(a, cudaSetDevice(a->device));
     uint32_t *d = static_cast<uint32_t *>(a->d_scratch) + 16;  // offset 64
@@ -969,6 +1089,7 @@ int32_t raftgpu_vote_result(raftgpu_arena *a, uint32_t g, int32_t *out_result, u
 
 int32_t raftgpu_counters_read(raftgpu_arena *a, raftgpu_counters *out) {
     if (!a || !out) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     CK(a, cudaSetDevice(a->device));
     static_assert(sizeof(raftgpu_counters) == kCntCount * 8, "counter layout");
     CK(a, cudaMemcpyAsync(a->h_scratch, a->d_counters, sizeof(*out), cudaMemcpyDeviceToHost, a->s_compute));
@@ -986,6 +1107,7 @@ int32_t raftgpu_synchronize(raftgpu_arena *a) {
 
 int32_t raftgpu_device_alloc(raftgpu_arena *a, uint64_t bytes, void **out) {
     if (!a || !out) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     CK(a, cudaSetDevice(a->device));
     uint8_t *p = nullptr;
     int32_t rc = dev_alloc(a, &p, bytes, false);
@@ -997,6 +1119,7 @@ int32_t raftgpu_device_alloc(raftgpu_arena *a, uint64_t bytes, void **out) {
 
 int32_t raftgpu_device_free(raftgpu_arena *a, void *p) {
     if (!a || !p) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     for (size_t i = 0; i < a->user_allocs.size(); i++) {
         if (a->user_allocs[i] == p) {
             a->user_allocs.erase(a->user_allocs.begin() + i);
@@ -1010,6 +1133,7 @@ int32_t raftgpu_device_free(raftgpu_arena *a, void *p) {
 
 int32_t raftgpu_memcpy_h2d(raftgpu_arena *a, void *dst, const void *src, uint64_t bytes) {
     if (!a || !dst || !src) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     CK(a, cudaSetDevice(a->device));
     CK(a, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));
@@ -1018,6 +1142,7 @@ int32_t raftgpu_memcpy_h2d(raftgpu_arena *a, void *dst, const void *src, uint64_
 
 int32_t raftgpu_memcpy_d2h(raftgpu_arena *a, void *dst, const void *src, uint64_t bytes) {
     if (!a || !dst || !src) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
     CK(a, cudaSetDevice(a->device));
     CK(a, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));

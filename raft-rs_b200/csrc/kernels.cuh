@@ -214,27 +214,109 @@ __device__ __forceinline__ void block_flush_counts(const uint32_t (&local)[kN], 
 }
 
 // ---------------------------------------------------------------------------
-// recompute_kernel: one Raft::maybe_commit (raft.rs:893-904) per group.
+// The recompute pass: one Raft::maybe_commit (raft.rs:893-904) per group.
 //   mci  = ProgressTracker::maximal_committed_index      tracker.rs:294-298
 //        = min(incoming.committed_index, outgoing.committed_index)   joint.rs:47-51
 //   if mci > committed && term(mci) == term              raft_log.rs:487-499
 //        committed = mci; prs[self].update_committed      raft.rs:896-900
 // term(mci) == term is the range test term_start <= mci <= last_index.
-//
-// Persistent grid: each warp walks 32-group tiles (one word of the advanced
-// bitmap) with a grid stride.  `hint` is a superset guess of the voter slots in
-// this arena (the host keeps the union of all voter masks): the matched loads of
-// the hinted slots are issued together with meta / committed / term_start /
-// last_index, so a tile costs ONE round trip to HBM instead of two (meta first,
-// then the slots it names).  Voter slots outside the hint are fetched after
-// meta arrives -- correct for any hint, fast for a tight one.
 // Algorithmic bytes per group: 8K (matched) + 4 (meta) + 24 (committed,
 // term_start, last_index) read, 8 written when advanced.
-__global__ void __launch_bounds__(256)
-recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint,
+//
+// Two feeds (LDG, TMA) x two specialisations.  kSimple5 = the host has verified
+// from its mirror of the meta column that EVERY group in the range is the plain
+// 5-voter configuration in slots 0..4 (no joint half, no group commit): the
+// kernel then carries no mask logic and no general selection network, which
+// roughly halves its instructions and registers.  The general form handles any
+// configuration; `hint` is a superset guess of the voter slots in the range (the
+// host keeps the union of all voter masks) so that the matched loads of the
+// hinted slots are issued together with meta / committed / term_start /
+// last_index -- ONE round trip to HBM instead of two.  Voter slots outside the
+// hint are fetched after meta arrives: correct for any hint, fast for a tight one.
+
+// maximal_committed_index of one group from its matched values v[].
+template <bool kSimple5>
+__device__ __forceinline__ void eval_mci(const Columns &c, uint32_t g, uint32_t meta, uint64_t (&v)[kSlots],
+                                         uint32_t hint, uint64_t &mci, bool &use_gc) {
+    if constexpr (kSimple5) {
+        mci = median5(v[0], v[1], v[2], v[3], v[4]);  // 5 voters: q = 3 = the median
+        use_gc = false;
+    } else {
+        const uint32_t in = RAFTGPU_META_IN(meta), out = RAFTGPU_META_OUT(meta);
+        const uint32_t voters = in | out;
+        const uint32_t missing = voters & ~hint;
+        if (missing) {  // hint was too small for this group: second trip for the rest
+#pragma unroll
+            for (int s = 0; s < kSlots; s++)
+                if ((missing >> s) & 1u) v[s] = c.matched[static_cast<size_t>(s) * c.cap + g];
+        }
+        if ((meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT)) == 0x1fu) {
+            mci = median5(v[0], v[1], v[2], v[3], v[4]);
+            use_gc = false;
+        } else if (!(meta & RAFTGPU_META_GROUP_COMMIT)) {
+            const uint64_t i_idx = quorum_index(v, in);
+            const uint64_t o_idx = quorum_index(v, out);  // empty outgoing => u64::MAX
+            mci = umin64(i_idx, o_idx);                    // joint.rs:50
+            use_gc = (in == 0) && (out == 0);              // majority.rs:71-75 vs :99-101
+        } else {
+            uint64_t gid[kSlots];
+            for (int s = 0; s < kSlots; s++)
+                gid[s] = ((voters >> s) & 1u) ? c.commit_group_id[static_cast<size_t>(s) * c.cap + g] : 0ull;
+            uint64_t i_idx, o_idx;
+            bool i_gc, o_gc;
+            majority_group_commit(v, gid, in, &i_idx, &i_gc);
+            majority_group_commit(v, gid, out, &o_idx, &o_gc);
+            mci = umin64(i_idx, o_idx);
+            use_gc = i_gc && o_gc;
+        }
+    }
+}
+
+// RaftLog::maybe_commit (raft_log.rs:487-499, range form) + raft.rs:896-900.
+__device__ __forceinline__ bool commit_group(const Columns &c, uint32_t g, uint32_t meta, uint64_t mci,
+                                             bool use_gc, uint64_t committed, uint64_t term_start,
+                                             uint64_t last_index, uint64_t *commit_out, uint64_t *mci_out,
+                                             uint8_t *gc_out) {
+    if (mci_out) mci_out[g] = mci;
+    if (gc_out) gc_out[g] = use_gc ? 1 : 0;
+    const bool advanced = mci > committed && mci >= term_start && mci <= last_index;
+    if (advanced) {
+        c.committed[g] = mci;  // commit_to: mci <= last_index, never the fatal! branch
+        if (commit_out) commit_out[g] = mci;
+        if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
+            const size_t cell = static_cast<size_t>(RAFTGPU_META_SELF(meta)) * c.cap + g;
+            if (mci > c.peer_committed[cell]) c.peer_committed[cell] = mci;
+        }
+    }
+    return advanced;
+}
+
+// One word of the advanced bitmap per warp-tile.
+__device__ __forceinline__ void publish_tile(uint32_t *adv_bitmap, uint64_t g64, uint32_t lane, bool active,
+                                             bool advanced, uint32_t (&local)[2]) {
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    const unsigned adv = __ballot_sync(0xffffffffu, advanced);
+    if (lane == 0 && act != 0 && adv_bitmap) {
+        uint32_t *word = &adv_bitmap[g64 >> 5];
+        if (act == 0xffffffffu) {
+            *word = adv;
+        } else {  // range starts / ends inside this word: leave the other bits alone
+            atomicAnd(word, ~act);
+            if (adv) atomicOr(word, adv);
+        }
+    }
+    local[0] += active ? 1u : 0u;
+    local[1] += advanced ? 1u : 0u;
+}
+
+// ---- LDG feed: persistent grid, each warp walks 32-group tiles with a grid stride.
+template <bool kSimple5>
+__global__ void __launch_bounds__(256, kSimple5 ? 6 : 4)
+recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint_arg,
                  uint32_t *__restrict__ adv_bitmap, uint64_t *__restrict__ commit_out,
                  uint64_t *__restrict__ mci_out, uint8_t *__restrict__ gc_out,
                  uint32_t *__restrict__ step_advanced, unsigned long long *__restrict__ counters) {
+    const uint32_t hint = kSimple5 ? 0x1fu : hint_arg;
     const uint32_t base = first & ~31u;
     const uint32_t n_tiles = static_cast<uint32_t>((static_cast<uint64_t>(first - base) + n + 31) >> 5);
     const uint32_t lane = threadIdx.x & 31;
@@ -258,65 +340,182 @@ recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint,
             const uint64_t committed = c.committed[g];
             const uint64_t term_start = c.term_start[g];
             const uint64_t last_index = c.last_index[g];
-
-            const uint32_t in = RAFTGPU_META_IN(meta), out = RAFTGPU_META_OUT(meta);
-            const uint32_t voters = in | out;
-            const uint32_t missing = voters & ~hint;
-            if (missing) {  // hint was too small for this group: second trip for the rest
-#pragma unroll
-                for (int s = 0; s < kSlots; s++)
-                    if ((missing >> s) & 1u) v[s] = c.matched[static_cast<size_t>(s) * c.cap + g];
-            }
             uint64_t mci;
             bool use_gc;
-            if ((meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT)) == 0x1fu) {
-                // 5 voters in slots 0..4, no joint config, no group commit: q = 3 = the median
-                mci = median5(v[0], v[1], v[2], v[3], v[4]);
-                use_gc = false;
-            } else if (!(meta & RAFTGPU_META_GROUP_COMMIT)) {
-                const uint64_t i_idx = quorum_index(v, in);
-                const uint64_t o_idx = quorum_index(v, out);  // empty outgoing => u64::MAX
-                mci = umin64(i_idx, o_idx);                    // joint.rs:50
-                use_gc = (in == 0) && (out == 0);              // majority.rs:71-75 vs :99-101
-            } else {
-                uint64_t gid[kSlots];
-                for (int s = 0; s < kSlots; s++)
-                    gid[s] = ((voters >> s) & 1u)
-                                 ? c.commit_group_id[static_cast<size_t>(s) * c.cap + g] : 0ull;
-                uint64_t i_idx, o_idx;
-                bool i_gc, o_gc;
-                majority_group_commit(v, gid, in, &i_idx, &i_gc);
-                majority_group_commit(v, gid, out, &o_idx, &o_gc);
-                mci = umin64(i_idx, o_idx);
-                use_gc = i_gc && o_gc;
-            }
-            if (mci_out) mci_out[g] = mci;
-            if (gc_out) gc_out[g] = use_gc ? 1 : 0;
+            eval_mci<kSimple5>(c, g, meta, v, hint, mci, use_gc);
+            advanced = commit_group(c, g, meta, mci, use_gc, committed, term_start, last_index, commit_out,
+                                    mci_out, gc_out);
+        }
+        publish_tile(adv_bitmap, g64, lane, active, advanced, local);
+    }
+    const int which[2] = {kCntRecomputes, kCntAdvanced};
+    block_flush_counts<2>(local, which, counters, step_advanced);
+}
 
-            // RaftLog::maybe_commit, raft_log.rs:488, in range form.
-            advanced = mci > committed && mci >= term_start && mci <= last_index;
-            if (advanced) {
-                c.committed[g] = mci;  // commit_to: mci <= last_index, never the fatal! branch
-                if (commit_out) commit_out[g] = mci;
-                if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
-                    const size_t cell = static_cast<size_t>(RAFTGPU_META_SELF(meta)) * c.cap + g;
-                    if (mci > c.peer_committed[cell]) c.peer_committed[cell] = mci;
+// ---- TMA feed.
+// The LDG feed is long-scoreboard bound: the bytes it keeps in flight are capped
+// by registers x occupancy.  Here a producer warp streams whole column tiles into
+// a ring of shared-memory stages with 1-D bulk copies (cp.async.bulk, SASS
+// UBLKCP) that complete on an mbarrier, so up to ~200 KB per SM are in flight
+// whatever the consumer warps are doing; the consumers only touch shared memory
+// and write `committed` back with coalesced stores.
+//
+//   stage layout:  [rows][kTile] u64   rows = hinted matched slots (ascending),
+//                                      then committed, term_start, last_index
+//                  [kTile] u32         meta
+//   full[stage]  : producer arms with expect_tx(bytes); the copies complete it
+//   empty[stage] : one arrival per consumer warp releases the stage
+constexpr int kTile = 512;               // groups per stage = consumer threads
+constexpr int kTmaThreads = kTile + 32;  // + one producer warp
+constexpr int kMaxStages = 12;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA: global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <bool kSimple5>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+recompute_tma_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint_arg, int n_stages,
+                     uint32_t *__restrict__ adv_bitmap, uint64_t *__restrict__ commit_out,
+                     uint64_t *__restrict__ mci_out, uint8_t *__restrict__ gc_out,
+                     uint32_t *__restrict__ step_advanced, unsigned long long *__restrict__ counters) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+
+    const uint32_t hint = kSimple5 ? 0x1fu : hint_arg;
+    const uint32_t n_hint = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint & 0xffu));
+    const uint32_t rows = n_hint + 3;
+    const uint32_t stage_bytes = rows * kTile * 8 + kTile * 4;
+    const uint32_t base = first - (first % kTile);
+    const uint64_t end = static_cast<uint64_t>(first) + n;
+    const uint32_t n_tiles = static_cast<uint32_t>((end - base + kTile - 1) / kTile);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kTile / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t local[2] = {0, 0};  // recomputes, advanced
+    if (warp == kTile / 32) {
+        // ===== producer warp: lane 0 arms the stage, then one lane per row issues its copy =====
+        // row -> source: rows [0, n_hint) = matched of the r-th hinted slot, then committed,
+        // term_start, last_index, and row `rows` = meta (u32)
+        const uint8_t *src_base = nullptr;
+        uint32_t elem = 8;
+        if (lane < n_hint) {
+            uint32_t seen = 0;
+            for (int s = 0; s < kSlots; s++) {
+                if (!((hint >> s) & 1u)) continue;
+                if (seen == lane)
+                    src_base = reinterpret_cast<const uint8_t *>(c.matched + static_cast<size_t>(s) * c.cap);
+                seen++;
+            }
+        } else if (lane == n_hint) {
+            src_base = reinterpret_cast<const uint8_t *>(c.committed);
+        } else if (lane == n_hint + 1) {
+            src_base = reinterpret_cast<const uint8_t *>(c.term_start);
+        } else if (lane == n_hint + 2) {
+            src_base = reinterpret_cast<const uint8_t *>(c.last_index);
+        } else if (lane == rows) {
+            src_base = reinterpret_cast<const uint8_t *>(c.meta);
+            elem = 4;
+        }
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int st = it % n_stages;
+            const uint32_t ph = (it / n_stages) & 1u;
+            const uint64_t g0 = static_cast<uint64_t>(base) + static_cast<uint64_t>(tile) * kTile;
+            uint32_t ng = static_cast<uint32_t>(end - g0 < kTile ? end - g0 : kTile);
+            ng = (ng + 3u) & ~3u;  // 16-byte multiples for the u32 row; stays inside the padded stride
+            if (lane == 0) {
+                mbar_wait(&empty_bar[st], ph ^ 1u);  // fresh barrier: the parity-1 wait passes at once
+                mbar_expect_tx(&full_bar[st], rows * ng * 8 + ng * 4);
+            }
+            __syncwarp();
+            if (src_base) {
+                uint8_t *sb = smem + static_cast<size_t>(st) * stage_bytes;
+                tma_load_1d(sb + static_cast<size_t>(lane) * kTile * 8, src_base + g0 * elem, ng * elem,
+                            &full_bar[st]);
+            }
+        }
+    } else {
+        // ===== consumers: one group per thread per tile =====
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int st = it % n_stages;
+            const uint32_t ph = (it / n_stages) & 1u;
+            const uint64_t g64 = static_cast<uint64_t>(base) + static_cast<uint64_t>(tile) * kTile + threadIdx.x;
+            const bool active = g64 >= first && g64 < end;
+            const uint32_t g = static_cast<uint32_t>(g64);
+            const uint8_t *sb = smem + static_cast<size_t>(st) * stage_bytes;
+            const uint64_t *row = reinterpret_cast<const uint64_t *>(sb) + threadIdx.x;
+            mbar_wait(&full_bar[st], ph);
+            // everything this thread needs from the stage, into registers
+            const uint32_t meta =
+                reinterpret_cast<const uint32_t *>(sb + static_cast<size_t>(rows) * kTile * 8)[threadIdx.x];
+            uint64_t v[kSlots];
+            uint32_t r = 0;
+#pragma unroll
+            for (int s = 0; s < kSlots; s++) {
+                v[s] = 0;
+                if ((hint >> s) & 1u) {
+                    v[s] = row[static_cast<size_t>(r) * kTile];
+                    r++;
                 }
             }
-        }
-        const unsigned act = __ballot_sync(0xffffffffu, active);
-        const unsigned adv = __ballot_sync(0xffffffffu, advanced);
-        if (lane == 0 && act != 0 && adv_bitmap) {
-            uint32_t *word = &adv_bitmap[g64 >> 5];
-            if (act == 0xffffffffu) {
-                *word = adv;
-            } else {  // range starts / ends inside this word: leave the other bits alone
-                atomicAnd(word, ~act);
-                if (adv) atomicOr(word, adv);
+            const uint64_t committed = row[static_cast<size_t>(n_hint) * kTile];
+            const uint64_t term_start = row[static_cast<size_t>(n_hint + 1) * kTile];
+            const uint64_t last_index = row[static_cast<size_t>(n_hint + 2) * kTile];
+            // the stage can be refilled as soon as every lane of this warp has its values
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            bool advanced = false;
+            if (active) {
+                uint64_t mci;
+                bool use_gc;
+                eval_mci<kSimple5>(c, g, meta, v, hint, mci, use_gc);
+                advanced = commit_group(c, g, meta, mci, use_gc, committed, term_start, last_index,
+                                        commit_out, mci_out, gc_out);
             }
+            publish_tile(adv_bitmap, g64, lane, active, advanced, local);
         }
-        local[0] += active ? 1u : 0u;
-        local[1] += advanced ? 1u : 0u;
     }
     const int which[2] = {kCntRecomputes, kCntAdvanced};
     block_flush_counts<2>(local, which, counters, step_advanced);
@@ -340,151 +539,200 @@ __device__ __forceinline__ void reset_state(Cell &p, uint32_t state, uint64_t *p
 // (raft.rs:1663-1743) for one wave of records, one thread per record, persistent
 // grid-stride loop.  Within a wave every (group, peer) cell is touched by at most
 // one record, so threads never race on a cell and no atomics are needed on the
-// columns.  The record names its cell, so meta and the cell's matched / next_idx /
-// pflags / committed_index are fetched in ONE batch of independent loads.
+// columns.
+//
+// The loop is software-pipelined three deep, because the work is two dependent
+// HBM round trips (the record names the cell; the cell decides the update):
+//   iteration k issues   the record load of element k+2,
+//                        the cell loads (meta, matched, next_idx, pflags,
+//                        committed_index) of element k+1,
+//   and computes / stores element k,
+// so every load has a whole iteration to land and each thread keeps ~53 B in
+// flight all the time instead of alternating between the two phases.
 // Algorithmic bytes per record: 24 (record) + RMW of matched, next_idx,
 // committed_index (48) + flag byte and meta (~4) = 76.
+struct RecRegs {
+    uint64_t w0, index, commit;
+};
+struct CellRegs {
+    uint32_t meta;
+    uint32_t flags;
+    uint64_t matched, next_idx, peer_committed;
+};
+
+__device__ __forceinline__ RecRegs load_rec(const raftgpu_append_resp *recs, uint64_t i, uint64_t n) {
+    RecRegs r;
+    if (i < n) {
+        const uint64_t *p = reinterpret_cast<const uint64_t *>(recs + i);
+        r.w0 = p[0];
+        r.index = p[1];
+        r.commit = p[2];
+    } else {  // past the end: a no-op (EXT) record
+        r.w0 = static_cast<uint64_t>(RAFTGPU_REC_EXT) << 40;
+        r.index = 0;
+        r.commit = 0;
+    }
+    return r;
+}
+
+__device__ __forceinline__ CellRegs load_cell(const Columns &c, const RecRegs &r) {
+    const uint32_t g = static_cast<uint32_t>(r.w0);
+    const uint32_t slot = static_cast<uint32_t>(r.w0 >> 32) & 0xffu;
+    // cell 0 / group 0 is a harmless stand-in for EXT and out-of-range records
+    // (nothing is written for them)
+    const bool ok = !((r.w0 >> 40) & RAFTGPU_REC_EXT) && g < c.cap && slot < kSlots;
+    const size_t cell = ok ? static_cast<size_t>(slot) * c.cap + g : 0;
+    CellRegs d;
+    d.meta = c.meta[ok ? g : 0];
+    d.matched = c.matched[cell];
+    d.next_idx = c.next_idx[cell];
+    d.flags = c.pflags[cell];
+    d.peer_committed = c.peer_committed[cell];
+    return d;
+}
+
+// One record against its cell: raft.rs:1663-1743.  Returns the result byte.
+__device__ __forceinline__ uint32_t apply_one(const Columns &c, const raftgpu_append_resp *recs, uint64_t n,
+                                              uint64_t i, const RecRegs &rec, const CellRegs &cd,
+                                              uint32_t (&local)[5]) {
+    const uint64_t index = rec.index, commit = rec.commit;
+    const uint32_t g = static_cast<uint32_t>(rec.w0);
+    const uint32_t slot = static_cast<uint32_t>(rec.w0 >> 32) & 0xffu;
+    const uint32_t rflags = static_cast<uint32_t>(rec.w0 >> 40) & 0xffu;
+    if (rflags & RAFTGPU_REC_EXT) return 0;
+    local[0]++;
+    const bool in_range = g < c.cap && slot < kSlots;
+    const uint32_t present =
+        RAFTGPU_META_IN(cd.meta) | RAFTGPU_META_OUT(cd.meta) | RAFTGPU_META_LEARN(cd.meta);
+    if (!in_range || !((present >> slot) & 1u)) {
+        // raft.rs:1663-1673: no progress available for m.from
+        local[4]++;
+        return RAFTGPU_RES_NO_PROGRESS;
+    }
+    const size_t cell = static_cast<size_t>(slot) * c.cap + g;
+    Cell pr;
+    pr.matched = cd.matched;
+    pr.next_idx = cd.next_idx;
+    pr.flags = cd.flags;
+    const uint32_t state = pr.flags & RAFTGPU_PF_STATE_MASK;
+    uint32_t res = 0;
+
+    if (rflags & RAFTGPU_REC_LOCAL) {
+        // raft.rs:974-991 append_entry: last_index grew
+        if (commit != 0) c.last_index[g] = commit;
+        // raft.rs:1010-1014 on_persist_entries: prs[self].maybe_update(index)
+        if (pr.matched < index) {  // progress.rs:138-150
+            pr.matched = index;
+            pr.flags &= ~RAFTGPU_PF_PAUSED;
+            local[1]++;
+            res = RAFTGPU_RES_OK;
+        }
+        if (pr.next_idx < index + 1) pr.next_idx = index + 1;
+    } else {
+        pr.flags |= RAFTGPU_PF_RECENT_ACTIVE;  // raft.rs:1674
+        // raft.rs:1677 pr.update_committed(m.commit), progress.rs:153-157
+        if (commit > cd.peer_committed) c.peer_committed[cell] = commit;
+
+        if (rflags & RAFTGPU_REC_REJECT) {
+            local[2]++;
+            uint64_t hint = 0, request_snapshot = RAFTGPU_INVALID_INDEX;
+            if (i + 1 < n) {
+                const uint64_t *e = reinterpret_cast<const uint64_t *>(recs + i + 1);
+                if ((e[0] >> 40) & RAFTGPU_REC_EXT) {
+                    hint = e[1];
+                    request_snapshot = e[2];
+                }
+            }
+            // Progress::maybe_decr_to, progress.rs:168-206
+            bool ok;
+            if (state == RAFTGPU_STATE_REPLICATE) {
+                if (index < pr.matched || (index == pr.matched && request_snapshot == RAFTGPU_INVALID_INDEX)) {
+                    ok = false;  // :173-177 stale
+                } else {
+                    if (request_snapshot == RAFTGPU_INVALID_INDEX)
+                        pr.next_idx = pr.matched + 1;  // :178-179
+                    else
+                        c.pending_req_snapshot[cell] = request_snapshot;  // :181
+                    ok = true;
+                }
+            } else if ((pr.next_idx == 0 || pr.next_idx - 1 != index) &&
+                       request_snapshot == RAFTGPU_INVALID_INDEX) {
+                ok = false;  // :188-192 stale
+            } else {
+                if (request_snapshot == RAFTGPU_INVALID_INDEX) {  // :195-199
+                    pr.next_idx = umin64(index, hint + 1);
+                    if (pr.next_idx < 1) pr.next_idx = 1;
+                } else if (c.pending_req_snapshot[cell] == RAFTGPU_INVALID_INDEX) {
+                    c.pending_req_snapshot[cell] = request_snapshot;  // :200-203
+                }
+                pr.flags &= ~RAFTGPU_PF_PAUSED;  // :204 resume()
+                ok = true;
+            }
+            if (ok) {
+                local[3]++;
+                res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
+                if (state == RAFTGPU_STATE_REPLICATE) {
+                    // raft.rs:1716-1718 become_probe (progress.rs:95-107, not Snapshot)
+                    reset_state(pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
+                    pr.next_idx = pr.matched + 1;
+                }
+            }
+        } else {
+            // raft.rs:1724 old_paused = pr.is_paused(), progress.rs:210-216
+            const bool old_paused =
+                state == RAFTGPU_STATE_PROBE
+                    ? (pr.flags & RAFTGPU_PF_PAUSED) != 0
+                    : (state == RAFTGPU_STATE_REPLICATE ? (pr.flags & RAFTGPU_PF_INS_FULL) != 0 : true);
+            // raft.rs:1725 pr.maybe_update(m.index), progress.rs:138-150
+            const bool need_update = pr.matched < index;
+            if (need_update) {
+                pr.matched = index;
+                pr.flags &= ~RAFTGPU_PF_PAUSED;
+            }
+            if (pr.next_idx < index + 1) pr.next_idx = index + 1;
+            if (need_update) {
+                local[1]++;
+                res = RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u);
+                if (state == RAFTGPU_STATE_PROBE) {
+                    // raft.rs:1730 become_replicate, progress.rs:110-114
+                    reset_state(pr, RAFTGPU_STATE_REPLICATE, &c.pending_snapshot[cell]);
+                    pr.next_idx = pr.matched + 1;
+                } else if (state == RAFTGPU_STATE_SNAPSHOT) {
+                    // raft.rs:1731-1741 maybe_snapshot_abort -> become_probe
+                    const uint64_t pending = c.pending_snapshot[cell];
+                    if (pr.matched >= pending) {  // progress.rs:131-134
+                        reset_state(pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
+                        pr.next_idx = umax64(pr.matched + 1, pending + 1);  // :99-102
+                    }
+                }
+                // Replicate: pr.ins.free_to(m.index) -- Inflights stays host-side
+            }
+        }
+    }
+    if (pr.matched != cd.matched) c.matched[cell] = pr.matched;
+    if (pr.next_idx != cd.next_idx) c.next_idx[cell] = pr.next_idx;
+    if (pr.flags != cd.flags) c.pflags[cell] = static_cast<uint8_t>(pr.flags);
+    return res;
+}
+
 __global__ void __launch_bounds__(256)
 apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n,
              uint8_t *__restrict__ results, unsigned long long *__restrict__ counters) {
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t local[5] = {0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress
-    // keep whole warps in the loop so the flush below runs converged
-    const uint64_t n_pad = (n + 31) & ~31ull;
-    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
-        if (i >= n) continue;
-        const uint64_t *p = reinterpret_cast<const uint64_t *>(recs + i);
-        const uint64_t w0 = p[0];
-        const uint64_t index = p[1];
-        const uint64_t commit = p[2];
-        const uint32_t g = static_cast<uint32_t>(w0);
-        const uint32_t slot = static_cast<uint32_t>(w0 >> 32) & 0xffu;
-        const uint32_t rflags = static_cast<uint32_t>(w0 >> 40) & 0xffu;
-        uint32_t res = 0;
-        if (!(rflags & RAFTGPU_REC_EXT)) {
-            local[0]++;
-            const bool in_range = g < c.cap && slot < kSlots;
-            const size_t cell = in_range ? static_cast<size_t>(slot) * c.cap + g : 0;
-            // one batch of independent loads (cell 0 / group 0 is a harmless stand-in when
-            // the record is out of range; nothing is written in that case)
-            const uint32_t meta = c.meta[in_range ? g : 0];
-            Cell pr;
-            pr.matched = c.matched[cell];
-            pr.next_idx = c.next_idx[cell];
-            pr.flags = c.pflags[cell];
-            const uint64_t peer_committed = c.peer_committed[cell];
-            const uint32_t present =
-                RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
-            if (!in_range || !((present >> slot) & 1u)) {
-                // raft.rs:1663-1673: no progress available for m.from
-                local[4]++;
-                res = RAFTGPU_RES_NO_PROGRESS;
-            } else {
-                const uint64_t matched0 = pr.matched, next0 = pr.next_idx;
-                const uint32_t flags0 = pr.flags;
-                const uint32_t state = pr.flags & RAFTGPU_PF_STATE_MASK;
-
-                if (rflags & RAFTGPU_REC_LOCAL) {
-                    // raft.rs:974-991 append_entry: last_index grew
-                    if (commit != 0) c.last_index[g] = commit;
-                    // raft.rs:1010-1014 on_persist_entries: prs[self].maybe_update(index)
-                    if (pr.matched < index) {  // progress.rs:138-150
-                        pr.matched = index;
-                        pr.flags &= ~RAFTGPU_PF_PAUSED;
-                        local[1]++;
-                        res = RAFTGPU_RES_OK;
-                    }
-                    if (pr.next_idx < index + 1) pr.next_idx = index + 1;
-                } else {
-                    pr.flags |= RAFTGPU_PF_RECENT_ACTIVE;  // raft.rs:1674
-                    // raft.rs:1677 pr.update_committed(m.commit), progress.rs:153-157
-                    if (commit > peer_committed) c.peer_committed[cell] = commit;
-
-                    if (rflags & RAFTGPU_REC_REJECT) {
-                        local[2]++;
-                        uint64_t hint = 0, request_snapshot = RAFTGPU_INVALID_INDEX;
-                        if (i + 1 < n) {
-                            const uint64_t *e = reinterpret_cast<const uint64_t *>(recs + i + 1);
-                            if ((e[0] >> 40) & RAFTGPU_REC_EXT) {
-                                hint = e[1];
-                                request_snapshot = e[2];
-                            }
-                        }
-                        // Progress::maybe_decr_to, progress.rs:168-206
-                        bool ok;
-                        if (state == RAFTGPU_STATE_REPLICATE) {
-                            if (index < pr.matched || (index == pr.matched &&
-                                                       request_snapshot == RAFTGPU_INVALID_INDEX)) {
-                                ok = false;  // :173-177 stale
-                            } else {
-                                if (request_snapshot == RAFTGPU_INVALID_INDEX)
-                                    pr.next_idx = pr.matched + 1;  // :178-179
-                                else
-                                    c.pending_req_snapshot[cell] = request_snapshot;  // :181
-                                ok = true;
-                            }
-                        } else if ((pr.next_idx == 0 || pr.next_idx - 1 != index) &&
-                                   request_snapshot == RAFTGPU_INVALID_INDEX) {
-                            ok = false;  // :188-192 stale
-                        } else {
-                            if (request_snapshot == RAFTGPU_INVALID_INDEX) {  // :195-199
-                                pr.next_idx = umin64(index, hint + 1);
-                                if (pr.next_idx < 1) pr.next_idx = 1;
-                            } else if (c.pending_req_snapshot[cell] == RAFTGPU_INVALID_INDEX) {
-                                c.pending_req_snapshot[cell] = request_snapshot;  // :200-203
-                            }
-                            pr.flags &= ~RAFTGPU_PF_PAUSED;  // :204 resume()
-                            ok = true;
-                        }
-                        if (ok) {
-                            local[3]++;
-                            res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
-                            if (state == RAFTGPU_STATE_REPLICATE) {
-                                // raft.rs:1716-1718 become_probe (progress.rs:95-107, not Snapshot)
-                                reset_state(pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
-                                pr.next_idx = pr.matched + 1;
-                            }
-                        }
-                    } else {
-                        // raft.rs:1724 old_paused = pr.is_paused(), progress.rs:210-216
-                        const bool old_paused =
-                            state == RAFTGPU_STATE_PROBE
-                                ? (pr.flags & RAFTGPU_PF_PAUSED) != 0
-                                : (state == RAFTGPU_STATE_REPLICATE
-                                       ? (pr.flags & RAFTGPU_PF_INS_FULL) != 0
-                                       : true);
-                        // raft.rs:1725 pr.maybe_update(m.index), progress.rs:138-150
-                        const bool need_update = pr.matched < index;
-                        if (need_update) {
-                            pr.matched = index;
-                            pr.flags &= ~RAFTGPU_PF_PAUSED;
-                        }
-                        if (pr.next_idx < index + 1) pr.next_idx = index + 1;
-                        if (need_update) {
-                            local[1]++;
-                            res = RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u);
-                            if (state == RAFTGPU_STATE_PROBE) {
-                                // raft.rs:1730 become_replicate, progress.rs:110-114
-                                reset_state(pr, RAFTGPU_STATE_REPLICATE, &c.pending_snapshot[cell]);
-                                pr.next_idx = pr.matched + 1;
-                            } else if (state == RAFTGPU_STATE_SNAPSHOT) {
-                                // raft.rs:1731-1741 maybe_snapshot_abort -> become_probe
-                                const uint64_t pending = c.pending_snapshot[cell];
-                                if (pr.matched >= pending) {  // progress.rs:131-134
-                                    reset_state(pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
-                                    pr.next_idx = umax64(pr.matched + 1, pending + 1);  // :99-102
-                                }
-                            }
-                            // Replicate: pr.ins.free_to(m.index) -- Inflights stays host-side
-                        }
-                    }
-                }
-                if (pr.matched != matched0) c.matched[cell] = pr.matched;
-                if (pr.next_idx != next0) c.next_idx[cell] = pr.next_idx;
-                if (pr.flags != flags0) c.pflags[cell] = static_cast<uint8_t>(pr.flags);
-            }
-        }
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    // prologue: fill the pipeline
+    RecRegs rec_a = load_rec(recs, i, n);
+    RecRegs rec_b = load_rec(recs, i + stride, n);
+    CellRegs cell_a = load_cell(c, rec_a);
+    for (; i < n; i += stride) {
+        const RecRegs rec_c = load_rec(recs, i + 2 * stride, n);  // element k+2: record
+        const CellRegs cell_b = load_cell(c, rec_b);              // element k+1: its cell
+        const uint32_t res = apply_one(c, recs, n, i, rec_a, cell_a, local);  // element k
         if (results) results[i] = static_cast<uint8_t>(res);
+        rec_a = rec_b;
+        cell_a = cell_b;
+        rec_b = rec_c;
     }
     const int which[5] = {kCntRecords, kCntUpdates, kCntRejects, kCntDecrements, kCntNoProgress};
     block_flush_counts<5>(local, which, counters, nullptr);

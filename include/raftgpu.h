@@ -304,6 +304,16 @@ int32_t raftgpu_apply_device(raftgpu_arena *arena, void *stream,
 int32_t raftgpu_enqueue_append_resp(raftgpu_arena *arena, uint32_t ring,
                                     const raftgpu_append_resp *records, uint64_t n);
 
+/* Bulk form of the above for a caller that already holds a whole batch in host memory:
+ * the library splits it over its own staging threads (pinned to the GPU-local CPUs; count
+ * from RAFTGPU_HOST_THREADS, default 16, at most the arena's ring count), one ring each.
+ * RAFTGPU_BULK_SORTED: the caller promises records are in non-decreasing group order, which
+ * lets the threads skip atomics on the per-cell bookkeeping; the order is verified and
+ * RAFTGPU_ERR_INVALID returned (nothing is applied; call raftgpu_step to discard) if not. */
+#define RAFTGPU_BULK_SORTED 0x1u
+int32_t raftgpu_enqueue_bulk(raftgpu_arena *arena, const raftgpu_append_resp *records, uint64_t n,
+                             uint32_t flags);
+
 /* One batched step over everything enqueued: H2D of the staged records, the
  * apply kernel per wave, ONE recompute pass over all allocated groups, D2H of
  * the results.  raftgpu_step = raftgpu_step_begin + raftgpu_step_wait.  Between

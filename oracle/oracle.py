@@ -149,6 +149,8 @@ def lib() -> C.CDLL:
         L.ro_bench_recompute.restype = C.c_double
         L.ro_bench_step.argtypes = [pv, C.c_void_p, sz, i32, p64]
         L.ro_bench_step.restype = C.c_double
+        L.ro_bench_step_fast.argtypes = [pv, C.c_void_p, sz, i32, p64]
+        L.ro_bench_step_fast.restype = C.c_double
         _lib = L
     return _lib
 
@@ -292,8 +294,9 @@ def bench_recompute(c, n_threads: int, iters: int):
     return secs, adv.value
 
 
-def bench_step(c, recs: np.ndarray, n_threads: int):
+def bench_step(c, recs: np.ndarray, n_threads: int, fast: bool = False):
     adv = C.c_uint64()
     v = view(c)
-    secs = lib().ro_bench_step(C.byref(v), recs.ctypes.data, len(recs), n_threads, C.byref(adv))
+    f = lib().ro_bench_step_fast if fast else lib().ro_bench_step
+    secs = f(C.byref(v), recs.ctypes.data, len(recs), n_threads, C.byref(adv))
     return secs, adv.value

@@ -594,6 +594,131 @@ int ro_arena_vote_result(const ro_arena_view *a, const uint8_t *votes, uint32_t 
 }
 
 /* ------------------------------------------------------------------------ */
+/* Tuned CPU path for the baseline arm: same results as the literal functions  */
+/* above (tests/test_oracle_fast.py), but written the way a CPU implementation */
+/* over flat arrays would be: no id lists, no struct copies.                   */
+
+static inline uint64_t fast_quorum_index(const uint64_t *v, uint32_t mask) {
+    if (mask == 0) return UINT64_MAX; /* majority.rs:71-75 */
+    uint64_t w[RO_SLOTS];
+    int n = 0;
+    for (uint32_t s = 0; s < RO_SLOTS; s++)
+        if (mask & (1u << s)) {
+            uint64_t x = v[s];
+            int j = n++;
+            while (j > 0 && w[j - 1] < x) { /* descending insertion sort, majority.rs:95 */
+                w[j] = w[j - 1];
+                j--;
+            }
+            w[j] = x;
+        }
+    return w[n / 2]; /* matched[majority(n) - 1], majority.rs:97-98 */
+}
+
+static inline int fast_maybe_commit(ro_arena_view *a, uint32_t g) {
+    uint32_t meta = a->meta[g];
+    if (meta & RO_META_GROUP_COMMIT) return ro_arena_maybe_commit(a, g); /* rare: literal path */
+    uint32_t in = RO_META_IN(meta), out = RO_META_OUT(meta), voters = in | out;
+    uint64_t v[RO_SLOTS];
+    for (uint32_t s = 0; s < RO_SLOTS; s++)
+        v[s] = (voters & (1u << s)) ? a->matched[(size_t)s * a->cap + g] : 0;
+    uint64_t i_idx = fast_quorum_index(v, in), o_idx = fast_quorum_index(v, out);
+    uint64_t mci = i_idx < o_idx ? i_idx : o_idx; /* joint.rs:50 */
+    if (mci > a->committed[g] && mci >= a->term_start[g] && mci <= a->last_index[g]) {
+        a->committed[g] = mci;
+        if (meta & RO_META_HAS_SELF) {
+            size_t c = (size_t)RO_META_SELF(meta) * a->cap + g;
+            if (mci > a->peer_committed[c]) a->peer_committed[c] = mci;
+        }
+        return 1;
+    }
+    return 0;
+}
+
+static inline void fast_reset_state(ro_arena_view *a, size_t c, uint8_t *f, uint8_t state) {
+    *f = (uint8_t)((*f & ~(RO_PF_PAUSED | RO_PF_INS_FULL | RO_PF_STATE_MASK)) | state);
+    if (a->pending_snapshot[c] != 0) a->pending_snapshot[c] = 0;
+}
+
+/* raft.rs:1663-1743 on the columns in place (batched mode: no per-message commit). */
+static inline void fast_apply_one(ro_arena_view *a, const ro_append_resp *r, const ro_append_resp *ext) {
+    uint32_t g = r->group, slot = r->peer_slot;
+    if (g >= a->cap || slot >= RO_SLOTS) return;
+    uint32_t meta = a->meta[g];
+    if (!((RO_META_IN(meta) | RO_META_OUT(meta) | RO_META_LEARN(meta)) & (1u << slot))) return;
+    size_t c = (size_t)slot * a->cap + g;
+    uint64_t matched = a->matched[c], next = a->next_idx[c];
+    uint8_t f = a->pflags[c];
+    uint8_t state = f & RO_PF_STATE_MASK;
+    uint64_t index = r->index;
+    if (r->flags & RO_REC_LOCAL) {
+        if (r->commit != 0) a->last_index[g] = r->commit;
+        if (matched < index) {
+            matched = index;
+            f &= (uint8_t)~RO_PF_PAUSED;
+        }
+        if (next < index + 1) next = index + 1;
+    } else {
+        f |= RO_PF_RECENT_ACTIVE;
+        if (r->commit > a->peer_committed[c]) a->peer_committed[c] = r->commit;
+        if (r->flags & RO_REC_REJECT) {
+            uint64_t hint = ext ? ext->index : 0, rs = ext ? ext->commit : RO_INVALID_INDEX;
+            int ok;
+            if (state == RO_STATE_REPLICATE) {
+                if (index < matched || (index == matched && rs == RO_INVALID_INDEX)) {
+                    ok = 0;
+                } else {
+                    if (rs == RO_INVALID_INDEX)
+                        next = matched + 1;
+                    else
+                        a->pending_request_snapshot[c] = rs;
+                    ok = 1;
+                }
+            } else if ((next == 0 || next - 1 != index) && rs == RO_INVALID_INDEX) {
+                ok = 0;
+            } else {
+                if (rs == RO_INVALID_INDEX) {
+                    uint64_t h = hint + 1;
+                    next = index < h ? index : h;
+                    if (next < 1) next = 1;
+                } else if (a->pending_request_snapshot[c] == RO_INVALID_INDEX) {
+                    a->pending_request_snapshot[c] = rs;
+                }
+                f &= (uint8_t)~RO_PF_PAUSED;
+                ok = 1;
+            }
+            if (ok && state == RO_STATE_REPLICATE) {
+                fast_reset_state(a, c, &f, RO_STATE_PROBE);
+                next = matched + 1;
+            }
+        } else {
+            int need = matched < index;
+            if (need) {
+                matched = index;
+                f &= (uint8_t)~RO_PF_PAUSED;
+            }
+            if (next < index + 1) next = index + 1;
+            if (need) {
+                if (state == RO_STATE_PROBE) {
+                    fast_reset_state(a, c, &f, RO_STATE_REPLICATE);
+                    next = matched + 1;
+                } else if (state == RO_STATE_SNAPSHOT) {
+                    uint64_t pending = a->pending_snapshot[c];
+                    if (matched >= pending) {
+                        fast_reset_state(a, c, &f, RO_STATE_PROBE);
+                        uint64_t x = matched + 1, y = pending + 1;
+                        next = x > y ? x : y;
+                    }
+                }
+            }
+        }
+    }
+    a->matched[c] = matched;
+    a->next_idx[c] = next;
+    a->pflags[c] = f;
+}
+
+/* ------------------------------------------------------------------------ */
 /* CPU baseline timing                                                       */
 
 static double now_s(void) {
@@ -641,16 +766,76 @@ static size_t lower_bound_group(const ro_append_resp *recs, size_t n, uint32_t g
     return lo;
 }
 
+/* A persistent worker pool: creating 128 threads per step would cost more than the step. */
+typedef struct {
+    int n_threads;
+    pthread_t *th;
+    bench_job *jobs;
+    void *(*fn)(void *);
+    pthread_barrier_t start, done;
+    int stop;
+} ro_pool;
+
+typedef struct {
+    ro_pool *pool;
+    int idx;
+} pool_arg;
+
+static void *pool_worker(void *argp) {
+    pool_arg *pa = (pool_arg *)argp;
+    ro_pool *p = pa->pool;
+    int idx = pa->idx;
+    free(pa);
+    for (;;) {
+        pthread_barrier_wait(&p->start);
+        if (p->stop) return NULL;
+        p->fn(&p->jobs[idx]);
+        pthread_barrier_wait(&p->done);
+    }
+}
+
+static ro_pool *g_pool = NULL;
+
+static ro_pool *get_pool(int n_threads) {
+    if (g_pool && g_pool->n_threads == n_threads) return g_pool;
+    if (g_pool) {
+        g_pool->stop = 1;
+        pthread_barrier_wait(&g_pool->start);
+        for (int t = 1; t < g_pool->n_threads; t++) pthread_join(g_pool->th[t], NULL);
+        pthread_barrier_destroy(&g_pool->start);
+        pthread_barrier_destroy(&g_pool->done);
+        free(g_pool->th);
+        free(g_pool->jobs);
+        free(g_pool);
+        g_pool = NULL;
+    }
+    ro_pool *p = (ro_pool *)calloc(1, sizeof(ro_pool));
+    p->n_threads = n_threads;
+    p->th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    p->jobs = (bench_job *)calloc((size_t)n_threads, sizeof(bench_job));
+    pthread_barrier_init(&p->start, NULL, (unsigned)n_threads);
+    pthread_barrier_init(&p->done, NULL, (unsigned)n_threads);
+    for (int t = 1; t < n_threads; t++) {
+        pool_arg *pa = (pool_arg *)malloc(sizeof(pool_arg));
+        pa->pool = p;
+        pa->idx = t;
+        pthread_create(&p->th[t], NULL, pool_worker, pa);
+    }
+    g_pool = p;
+    return p;
+}
+
 static double run_jobs(ro_arena_view *a, int n_threads, int iters, const ro_append_resp *recs,
                        size_t n_recs, void *(*fn)(void *), uint64_t *advanced_total) {
     if (n_threads < 1) n_threads = 1;
-    bench_job *jobs = (bench_job *)calloc((size_t)n_threads, sizeof(bench_job));
-    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    ro_pool *p = get_pool(n_threads);
+    bench_job *jobs = p->jobs;
     uint32_t per = (a->n_groups + (uint32_t)n_threads - 1) / (uint32_t)n_threads;
     for (int t = 0; t < n_threads; t++) {
         uint32_t first = (uint32_t)t * per;
         if (first > a->n_groups) first = a->n_groups;
         uint32_t n = a->n_groups - first < per ? a->n_groups - first : per;
+        memset(&jobs[t], 0, sizeof(bench_job));
         jobs[t].a = a;
         jobs[t].first = first;
         jobs[t].n = n;
@@ -661,17 +846,32 @@ static double run_jobs(ro_arena_view *a, int n_threads, int iters, const ro_appe
             jobs[t].rec_hi = lower_bound_group(recs, n_recs, first + n);
         }
     }
+    p->fn = fn;
     double t0 = now_s();
-    for (int t = 1; t < n_threads; t++) pthread_create(&th[t], NULL, fn, &jobs[t]);
+    pthread_barrier_wait(&p->start); /* the caller is worker 0 */
     fn(&jobs[0]);
-    for (int t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
+    pthread_barrier_wait(&p->done);
     double t1 = now_s();
     uint64_t adv = 0;
     for (int t = 0; t < n_threads; t++) adv += jobs[t].advanced;
     if (advanced_total) *advanced_total = adv;
-    free(jobs);
-    free(th);
     return t1 - t0;
+}
+
+static void *bench_step_fast_worker(void *arg) {
+    bench_job *j = (bench_job *)arg;
+    const ro_append_resp *recs = j->recs;
+    for (size_t i = j->rec_lo; i < j->rec_hi; i++) {
+        const ro_append_resp *r = &recs[i];
+        if (r->flags & RO_REC_EXT) continue;
+        const ro_append_resp *ext = NULL;
+        if ((r->flags & RO_REC_REJECT) && i + 1 < j->rec_hi && (recs[i + 1].flags & RO_REC_EXT)) ext = &recs[i + 1];
+        fast_apply_one(j->a, r, ext);
+    }
+    uint64_t adv = 0;
+    for (uint32_t g = j->first; g < j->first + j->n; g++) adv += (uint64_t)fast_maybe_commit(j->a, g);
+    j->advanced = adv;
+    return NULL;
 }
 
 double ro_bench_recompute(ro_arena_view *a, int n_threads, int iters, uint64_t *advanced_total) {
@@ -681,4 +881,9 @@ double ro_bench_recompute(ro_arena_view *a, int n_threads, int iters, uint64_t *
 double ro_bench_step(ro_arena_view *a, const ro_append_resp *recs, size_t n_recs, int n_threads,
                      uint64_t *advanced_total) {
     return run_jobs(a, n_threads, 1, recs, n_recs, bench_step_worker, advanced_total);
+}
+
+double ro_bench_step_fast(ro_arena_view *a, const ro_append_resp *recs, size_t n_recs, int n_threads,
+                          uint64_t *advanced_total) {
+    return run_jobs(a, n_threads, 1, recs, n_recs, bench_step_fast_worker, advanced_total);
 }

@@ -246,6 +246,10 @@ double ro_bench_recompute(ro_arena_view *a, int n_threads, int iters, uint64_t *
  * must be sorted by group) then recompute, n_threads pthreads. */
 double ro_bench_step(ro_arena_view *a, const ro_append_resp *recs, size_t n_recs, int n_threads,
                      uint64_t *advanced_total);
+/* Same step through the tuned CPU path (in-place column updates, direct selection):
+ * identical results, what the CPU baseline arm times. */
+double ro_bench_step_fast(ro_arena_view *a, const ro_append_resp *recs, size_t n_recs, int n_threads,
+                          uint64_t *advanced_total);
 
 #ifdef __cplusplus
 }

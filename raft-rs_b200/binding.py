@@ -32,6 +32,7 @@ META_HAS_SELF, META_GROUP_COMMIT = 0x08000000, 0x10000000
 REC_REJECT, REC_LOCAL, REC_EXT = 0x01, 0x02, 0x80
 RES_OK, RES_OLD_PAUSED, RES_NO_PROGRESS, RES_SEND = 0x01, 0x02, 0x04, 0x08
 STEP_READ_COMMITTED, STEP_READ_RESULTS = 0x1, 0x2
+BULK_SORTED = 0x1
 
 (COL_MATCHED, COL_NEXT_IDX, COL_PEER_COMMITTED, COL_PENDING_SNAPSHOT, COL_PENDING_REQ_SNAPSHOT,
  COL_COMMIT_GROUP_ID, COL_PFLAGS, COL_VOTES, COL_META, COL_COMMITTED, COL_TERM_START,
@@ -151,6 +152,7 @@ def lib() -> C.CDLL:
             "raftgpu_recompute": ([vp, vp, u32, u32, vp, vp, vp, vp], i32),
             "raftgpu_apply_device": ([vp, vp, vp, u64, vp], i32),
             "raftgpu_enqueue_append_resp": ([vp, u32, vp, u64], i32),
+            "raftgpu_enqueue_bulk": ([vp, vp, u64, u32], i32),
             "raftgpu_step_begin": ([vp, u32], i32),
             "raftgpu_step_wait": ([vp, C.POINTER(StepResult)], i32),
             "raftgpu_step": ([vp, u32, C.POINTER(StepResult)], i32),
@@ -432,6 +434,11 @@ class Arena:
         assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous
         self._ck(self._L.raftgpu_enqueue_append_resp(self._h, ring, recs.ctypes.data, len(recs)),
                  "enqueue_append_resp")
+
+    def enqueue_bulk(self, recs: np.ndarray, sorted_by_group: bool = False):
+        assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous
+        self._ck(self._L.raftgpu_enqueue_bulk(self._h, recs.ctypes.data, len(recs),
+                                              BULK_SORTED if sorted_by_group else 0), "enqueue_bulk")
 
     def step_begin(self, flags=0):
         self._ck(self._L.raftgpu_step_begin(self._h, flags), "step_begin")

@@ -6,6 +6,9 @@
 // RAFTGPU_ERR_NO_DEVICE and nothing else can be called.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -17,6 +20,9 @@
 #include <vector>
 
 #include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "kernels.cuh"
 
@@ -73,6 +79,54 @@ struct StagingSet {
     raftgpu_step_result result{};
 };
 
+// The library's own staging workers for raftgpu_enqueue_bulk: persistent threads, pinned to
+// the GPU-local CPUs, one staging ring each.
+struct HostPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_start, cv_done;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    std::function<void(int)> job;
+
+    void run(const std::function<void(int)> &fn) {
+        std::unique_lock<std::mutex> lk(mu);
+        job = fn;
+        pending = static_cast<int>(threads.size());
+        generation++;
+        cv_start.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    void worker(int idx, cpu_set_t cpus, bool pin) {
+        if (pin) sched_setaffinity(0, sizeof(cpus), &cpus);
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_start.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                fn = job;
+            }
+            fn(idx);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) cv_done.notify_one();
+            }
+        }
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+            cv_start.notify_all();
+        }
+        for (auto &t : threads) t.join();
+    }
+};
+
 }  // namespace
 
 struct raftgpu_arena {
@@ -110,6 +164,9 @@ struct raftgpu_arena {
     uint64_t l2_bytes = 0, device_bytes = 0, pinned_bytes = 0;
     std::string last_error;
     std::vector<void *> user_allocs;
+    HostPool *pool = nullptr;  // created on first raftgpu_enqueue_bulk
+    cpu_set_t local_cpus;      // GPU-local CPUs (empty when unknown)
+    bool have_local_cpus = false;
 };
 
 namespace {
@@ -123,6 +180,7 @@ thread_local std::string g_create_error;
 // (sysfs local_cpulist of the device) for the duration of the allocations.
 struct LocalCpuGuard {
     cpu_set_t saved;
+    cpu_set_t local;  // the GPU-local CPUs we are allowed to run on
     bool active = false;
     explicit LocalCpuGuard(int device) {
         char bus[32] = {0};
@@ -153,6 +211,7 @@ struct LocalCpuGuard {
         cpu_set_t both;
         CPU_AND(&both, &want, &saved);  // stay inside the cpuset we are allowed to use
         if (CPU_COUNT(&both) == 0) return;
+        local = both;
         if (sched_setaffinity(0, sizeof(both), &both) == 0) active = true;
     }
     ~LocalCpuGuard() {
@@ -319,6 +378,7 @@ void destroy(raftgpu_arena *a) {
     cudaFree(a->d_scratch);
     cudaFreeHost(a->h_scratch);
     for (void *p : a->user_allocs) cudaFree(p);
+    delete a->pool;
     for (auto &s : a->sets) free_set(s);
     if (a->s_compute) cudaStreamDestroy(a->s_compute);
     if (a->s_h2d) cudaStreamDestroy(a->s_h2d);
@@ -420,6 +480,11 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     const uint64_t wave0_total = static_cast<uint64_t>(a->n_chunks) * kChunk;
     const uint64_t rec_total = wave0_total + a->overflow_records;
     LocalCpuGuard numa_guard(device);  // pinned pages on the GPU-local NUMA node
+    CPU_ZERO(&a->local_cpus);
+    if (numa_guard.active) {
+        a->local_cpus = numa_guard.local;
+        a->have_local_cpus = true;
+    }
     for (auto &s : a->sets) {
         TRY(pin_alloc(a, &s.h_recs, wave0_total));
         TRY(pin_alloc(a, &s.h_overflow, a->overflow_records));
@@ -839,30 +904,56 @@ int32_t raftgpu_apply_device(raftgpu_arena *a, void *stream, const raftgpu_appen
     return launch_apply(a, pick_stream(a, stream), d_records, n, d_results);
 }
 
-int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftgpu_append_resp *recs,
-                                    uint64_t n) {
-    if (!a || (!recs && n)) return RAFTGPU_ERR_INVALID;
-    if (ring >= a->n_rings) return RAFTGPU_ERR_RANGE;
-    StagingSet &s = a->sets[a->fill];
-    if (s.in_flight) return RAFTGPU_ERR_BUSY;
+// Streaming store of one record into the pinned ring: the destination is written once and
+// next read by the DMA engine, so bypass the cache (no read-for-ownership traffic).
+static inline void store_rec(raftgpu_append_resp *dst, const raftgpu_append_resp &r) {
+#if defined(__x86_64__)
+    const long long *src = reinterpret_cast<const long long *>(&r);
+    long long *d = reinterpret_cast<long long *>(dst);
+    _mm_stream_si64(d, src[0]);
+    _mm_stream_si64(d + 1, src[1]);
+    _mm_stream_si64(d + 2, src[2]);
+#else
+    *dst = r;
+#endif
+}
+
+// Stage `n` records on one ring.  `sorted` = the caller promised non-decreasing group order
+// (verified here): cells of one group then never straddle two rings, so the per-cell
+// bookkeeping needs no atomics.  Without it the touched bits are updated atomically because
+// another ring's thread may hold records of the same group.
+static int32_t enqueue_ring(raftgpu_arena *a, StagingSet &s, uint32_t ring, const raftgpu_append_resp *recs,
+                            uint64_t n, bool sorted, bool atomic_touch) {
     Ring &rg = s.rings[ring];
     raftgpu_append_resp *dst =
         rg.chunks.empty() ? nullptr : s.h_recs + static_cast<size_t>(rg.chunks.back()) * kChunk;
     uint32_t fill = rg.fill;
     uint64_t seq = rg.seq;
-    s.dirty = true;
     int32_t rc = RAFTGPU_OK;
+    uint32_t prev_group = 0;
+    const raftgpu_append_resp pad{0, 0, RAFTGPU_REC_EXT, 0, 0, 0};
     for (uint64_t i = 0; i < n; i++) {
         const raftgpu_append_resp &r = recs[i];
         if (r.flags & RAFTGPU_REC_EXT) continue;  // copied together with its REJECT
+        if (sorted) {
+            if (r.group < prev_group) {
+                rc = RAFTGPU_ERR_INVALID;
+                break;
+            }
+            prev_group = r.group;
+        }
         const int n_recs =
             ((r.flags & RAFTGPU_REC_REJECT) && i + 1 < n && (recs[i + 1].flags & RAFTGPU_REC_EXT)) ? 2 : 1;
         bool dup = false;
         if (r.group < a->cap && r.peer_slot < RAFTGPU_SLOTS) {
             const uint8_t bit = static_cast<uint8_t>(1u << r.peer_slot);
             uint8_t &t = s.touched[r.group];
-            dup = (t & bit) != 0;
-            t |= bit;
+            if (atomic_touch) {
+                dup = (__atomic_fetch_or(&t, bit, __ATOMIC_RELAXED) & bit) != 0;
+            } else {
+                dup = (t & bit) != 0;
+                t |= bit;
+            }
         }
         if (dup) {
             push_overflow(s, (static_cast<uint64_t>(r.group) << 3) | r.peer_slot, &r, n_recs, ring, seq);
@@ -872,12 +963,10 @@ int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftg
         }
         if (fill + n_recs > kChunk) {
             // pad the tail of the chunk with no-op records (EXT records are skipped by the kernel)
-            for (; dst && fill < kChunk; fill++) {
-                dst[fill] = raftgpu_append_resp{0, 0, RAFTGPU_REC_EXT, 0, 0, 0};
-            }
+            for (; dst && fill < kChunk; fill++) store_rec(&dst[fill], pad);
             const uint32_t ch = s.next_chunk.fetch_add(1);
             if (ch >= a->n_chunks) {
-                rc = fail(a, RAFTGPU_ERR_FULL, "staging ring full");
+                rc = RAFTGPU_ERR_FULL;
                 fill = kChunk;
                 break;
             }
@@ -885,13 +974,77 @@ int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftg
             dst = s.h_recs + static_cast<size_t>(ch) * kChunk;
             fill = 0;
         }
-        dst[fill++] = r;
-        if (n_recs == 2) dst[fill++] = recs[i + 1];
+        store_rec(&dst[fill++], r);
+        if (n_recs == 2) store_rec(&dst[fill++], recs[i + 1]);
         seq += n_recs;
     }
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
     rg.fill = fill;
     rg.seq = seq;
     return rc;
+}
+
+int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftgpu_append_resp *recs,
+                                    uint64_t n) {
+    if (!a || (!recs && n)) return RAFTGPU_ERR_INVALID;
+    if (ring >= a->n_rings) return RAFTGPU_ERR_RANGE;
+    StagingSet &s = a->sets[a->fill];
+    if (s.in_flight) return RAFTGPU_ERR_BUSY;
+    s.dirty = true;
+    const int32_t rc = enqueue_ring(a, s, ring, recs, n, false, false);
+    if (rc == RAFTGPU_ERR_FULL) return fail(a, rc, "staging ring full");
+    return rc;
+}
+
+int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, uint64_t n, uint32_t flags) {
+    if (!a || (!recs && n)) return RAFTGPU_ERR_INVALID;
+    StagingSet &s = a->sets[a->fill];
+    if (s.in_flight) return RAFTGPU_ERR_BUSY;
+    s.dirty = true;
+    const bool sorted = (flags & RAFTGPU_BULK_SORTED) != 0;
+    if (!a->pool) {
+        int want = 16;
+        if (const char *e = getenv("RAFTGPU_HOST_THREADS")) want = atoi(e);
+        int avail = a->have_local_cpus ? CPU_COUNT(&a->local_cpus) : static_cast<int>(std::thread::hardware_concurrency());
+        want = std::max(1, std::min({want, static_cast<int>(a->n_rings), std::max(1, avail)}));
+        a->pool = new HostPool();
+        for (int t = 0; t < want; t++)
+            a->pool->threads.emplace_back(&HostPool::worker, a->pool, t, a->local_cpus, a->have_local_cpus);
+    }
+    const int T = static_cast<int>(a->pool->threads.size());
+    if (n < 4096 || T == 1) {
+        const int32_t rc = enqueue_ring(a, s, 0, recs, n, sorted, false);
+        if (rc == RAFTGPU_ERR_FULL) return fail(a, rc, "staging ring full");
+        if (rc == RAFTGPU_ERR_INVALID) return fail(a, rc, "RAFTGPU_BULK_SORTED but records are not in group order");
+        return rc;
+    }
+    // contiguous slices; a cut never separates a REJECT from its EXT, nor (sorted) one group
+    std::vector<uint64_t> cut(T + 1, n);
+    cut[0] = 0;
+    for (int t = 1; t < T; t++) {
+        uint64_t c = std::max(cut[t - 1], n * t / T);
+        while (c < n && c > 0 &&
+               ((recs[c].flags & RAFTGPU_REC_EXT) || (sorted && recs[c].group == recs[c - 1].group)))
+            c++;
+        cut[t] = c;
+    }
+    std::vector<int32_t> rcs(T, RAFTGPU_OK);
+    a->pool->run([&](int t) {
+        if (cut[t + 1] > cut[t])
+            rcs[t] = enqueue_ring(a, s, static_cast<uint32_t>(t), recs + cut[t], cut[t + 1] - cut[t], sorted, !sorted);
+    });
+    bool order_ok = true;
+    if (sorted)  // slices are internally ordered (checked by the workers); check the seams too
+        for (int t = 1; t < T; t++)
+            if (cut[t] < n && cut[t] > 0 && recs[cut[t]].group < recs[cut[t] - 1].group) order_ok = false;
+    for (int t = 0; t < T; t++) {
+        if (rcs[t] == RAFTGPU_ERR_FULL) return fail(a, RAFTGPU_ERR_FULL, "staging ring full");
+        if (rcs[t] == RAFTGPU_ERR_INVALID) order_ok = false;
+    }
+    if (!order_ok) return fail(a, RAFTGPU_ERR_INVALID, "RAFTGPU_BULK_SORTED but records are not in group order");
+    return RAFTGPU_OK;
 }
 
 int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {

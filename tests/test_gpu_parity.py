@@ -344,6 +344,46 @@ def test_synthetic_stream_elementwise(name):
     arena.close()
 
 
+def test_enqueue_bulk_sorted_unsorted_and_order_check():
+    """raftgpu_enqueue_bulk: the library's own staging threads; same results as the oracle for
+    a sorted batch (fast path), for the same batch shuffled (atomic bookkeeping) and a loud
+    error when SORTED is promised but not true."""
+    n = 200_000
+    synth = B.Synth(n, 0x5EED0002)
+    for shuffled in (False, True):
+        arena = B.Arena(n)
+        arena.group_alloc_range(n)
+        arena.load_columns(synth.initial)
+        ref = O.copy_columns(synth.initial)
+        s2 = B.Synth(n, 0x5EED0002)
+        for rnd in range(3):
+            recs = s2.next_round().copy()
+            if shuffled:
+                # permute whole records but keep each REJECT glued to its EXT
+                main = np.nonzero((recs["flags"] & B.REC_EXT) == 0)[0]
+                perm = np.random.default_rng(rnd).permutation(main)
+                idx = []
+                for i in perm:
+                    idx.append(i)
+                    if recs[i]["flags"] & B.REC_REJECT:
+                        idx.append(i + 1)
+                sub = np.ascontiguousarray(recs[np.array(idx)])
+                arena.enqueue_bulk(sub, sorted_by_group=False)
+            else:
+                arena.enqueue_bulk(recs, sorted_by_group=True)
+            r = arena.step(B.STEP_READ_COMMITTED)
+            O.arena_apply(ref, recs, mode=0)      # one wave: order inside it does not matter
+            want_adv, want_bm, _, _ = O.arena_recompute(ref)
+            assert r.n_waves == 1 and r.n_records == len(recs) and r.n_advanced == want_adv
+            assert_columns_equal(arena.read_columns(n), ref, n, f"bulk shuffled={shuffled} round {rnd}")
+        if not shuffled:
+            bad = s2.next_round().copy()[::-1].copy()
+            with pytest.raises(B.RaftGpuError) as e:
+                arena.enqueue_bulk(bad, sorted_by_group=True)
+            assert e.value.status == B.ERR_INVALID
+        arena.close()
+
+
 def test_mci_and_properties_at_full_size():
     """1M x 7 joint: maximal_committed_index for every group vs the oracle, plus
     size-independent properties: idempotence, monotone commit, joint = min of halves."""

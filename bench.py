@@ -364,6 +364,13 @@ def main():
             kernels.append({"kernel": name, "avg_us": 1e3 * ms / K, "share": ms / ms_total,
                             "alg_bytes_per_launch": units * b_alg / K, "achieved": gbs,
                             "frac": gbs / peak_gbs})
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f)
+        except Exception:
+            traffic = {}
+        for k in kernels:
+            k["traffic"] = traffic.get(k["kernel"])   # ncu dram bytes per launch (profiles/)
         dom = max(kernels, key=lambda k: k["avg_us"])
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -378,7 +385,7 @@ def main():
                 "parallelism": f"groups sharded over {world} GPU(s), no data-path collective",
             },
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"],
-                         "peak": peak_gbs, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                         "peak": peak_gbs, "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],
                          "peak_source": peak_src},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,

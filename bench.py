@@ -344,17 +344,16 @@ def main():
 
     # ---- aggregate over ranks (NCCL: counters and times only) -----------------------------------
     cnt = [a.counters() for a in arenas]
-    local = torch.tensor([ms_total, e2e_s, float(n * K), float(n * e2e_timed),
-                          float(sum(c["recomputes"] for c in cnt)),
-                          float(sum(c["advanced"] for c in cnt)),
-                          float(sum(c["records"] for c in cnt))], dtype=torch.float64, device="cuda")
-    mx, sm = local.clone(), local.clone()
-    if world > 1:
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-    ms_max, e2e_max = mx[0].item(), mx[1].item()
-    value = sm[2].item() / (ms_max * 1e-3)
-    e2e_value = sm[3].item() / e2e_max if e2e_max > 0 else None
+    S = importlib.import_module("raft-rs_b200.shard")
+    sums, maxes = S.aggregate(
+        dist if world > 1 else None, torch,
+        {"groups_device": n * K, "groups_e2e": n * e2e_timed,
+         "recomputes": sum(c["recomputes"] for c in cnt), "advanced": sum(c["advanced"] for c in cnt),
+         "records": sum(c["records"] for c in cnt)},
+        {"ms_total": ms_total, "e2e_s": e2e_s}, device="cuda")
+    ms_max, e2e_max = maxes["ms_total"], maxes["e2e_s"]
+    value = sums["groups_device"] / (ms_max * 1e-3)
+    e2e_value = sums["groups_e2e"] / e2e_max if e2e_max > 0 else None
 
     if rank == 0:
         kernels = []
@@ -399,7 +398,7 @@ def main():
                     "api": "raftgpu_enqueue_bulk(SORTED) + raftgpu_step_begin/_wait (READ_COMMITTED)"},
             "gpu_launches": 2 * K,
             "clocks": clocks,
-            "counters": {"recomputes": sm[4].item(), "advanced": sm[5].item(), "records": sm[6].item()},
+            "counters": {"recomputes": sums["recomputes"], "advanced": sums["advanced"], "records": sums["records"]},
         }
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core

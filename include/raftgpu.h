@@ -250,6 +250,40 @@ int32_t raftgpu_progress_get(raftgpu_arena *arena, uint32_t group, uint32_t peer
 int32_t raftgpu_progress_set(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot,
                              const raftgpu_progress *in);
 
+/* Any single method of Progress (src/tracker/progress.rs:75-243) on one peer, executed on the
+ * device columns; a0..a2 are the method's arguments, *out_result its bool (or -1 where the
+ * reference panics: update_state in Snapshot).  This is what the host mirror's ProgressRef
+ * calls; batches of maybe_update / maybe_decr_to go through raftgpu_enqueue_* instead. */
+enum {
+    RAFTGPU_POP_MAYBE_UPDATE = 0,         /* (n)                                  progress.rs:138-150 */
+    RAFTGPU_POP_MAYBE_DECR_TO = 1,        /* (rejected, match_hint, request_snapshot)     :168-206 */
+    RAFTGPU_POP_UPDATE_COMMITTED = 2,     /* (committed_index)                            :153-157 */
+    RAFTGPU_POP_OPTIMISTIC_UPDATE = 3,    /* (n)                                          :160-163 */
+    RAFTGPU_POP_BECOME_PROBE = 4,         /*                                              :95-107  */
+    RAFTGPU_POP_BECOME_REPLICATE = 5,     /*                                              :110-114 */
+    RAFTGPU_POP_BECOME_SNAPSHOT = 6,      /* (snapshot_idx)                               :117-121 */
+    RAFTGPU_POP_SNAPSHOT_FAILURE = 7,     /*                                              :124-127 */
+    RAFTGPU_POP_MAYBE_SNAPSHOT_ABORT = 8, /*                                              :131-134 */
+    RAFTGPU_POP_IS_PAUSED = 9,            /*                                              :210-216 */
+    RAFTGPU_POP_RESUME = 10,              /*                                              :219-222 */
+    RAFTGPU_POP_PAUSE = 11,               /*                                              :225-228 */
+    RAFTGPU_POP_UPDATE_STATE = 12,        /* (last)                                       :231-243 */
+    RAFTGPU_POP_RESET = 13                /* (next_idx)                                   :82-92   */
+};
+int32_t raftgpu_progress_op(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot, int32_t op,
+                            uint64_t a0, uint64_t a1, uint64_t a2, int32_t *out_result);
+
+/* ProgressTracker::has_quorum (tracker.rs:367-372) for a set of peer slots, and
+ * quorum_recently_active (tracker.rs:346-361; clears recent_active like the reference). */
+int32_t raftgpu_has_quorum(raftgpu_arena *arena, uint32_t group, uint32_t slot_mask, int32_t *out);
+int32_t raftgpu_quorum_recently_active(raftgpu_arena *arena, uint32_t group, uint32_t perspective_of_slot,
+                                       int32_t *out);
+
+/* RaftLog::maybe_commit(max_index, term) (raft_log.rs:487-499) for term == the leader's
+ * current term, i.e. the range test on [term_start, last_index]. */
+int32_t raftgpu_group_maybe_commit_to(raftgpu_arena *arena, uint32_t group, uint64_t max_index,
+                                      int32_t *out_advanced);
+
 /* ProgressTracker::enable_group_commit (tracker.rs:238-241) and
  * Raft::assign_commit_groups / clear_commit_group (raft.rs:531-552). */
 int32_t raftgpu_set_group_commit(raftgpu_arena *arena, uint32_t group, int32_t enable);

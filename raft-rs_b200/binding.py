@@ -33,6 +33,9 @@ REC_REJECT, REC_LOCAL, REC_EXT = 0x01, 0x02, 0x80
 RES_OK, RES_OLD_PAUSED, RES_NO_PROGRESS, RES_SEND = 0x01, 0x02, 0x04, 0x08
 STEP_READ_COMMITTED, STEP_READ_RESULTS = 0x1, 0x2
 BULK_SORTED = 0x1
+(POP_MAYBE_UPDATE, POP_MAYBE_DECR_TO, POP_UPDATE_COMMITTED, POP_OPTIMISTIC_UPDATE, POP_BECOME_PROBE,
+ POP_BECOME_REPLICATE, POP_BECOME_SNAPSHOT, POP_SNAPSHOT_FAILURE, POP_MAYBE_SNAPSHOT_ABORT, POP_IS_PAUSED,
+ POP_RESUME, POP_PAUSE, POP_UPDATE_STATE, POP_RESET) = range(14)
 
 (COL_MATCHED, COL_NEXT_IDX, COL_PEER_COMMITTED, COL_PENDING_SNAPSHOT, COL_PENDING_REQ_SNAPSHOT,
  COL_COMMIT_GROUP_ID, COL_PFLAGS, COL_VOTES, COL_META, COL_COMMITTED, COL_TERM_START,
@@ -143,6 +146,10 @@ def lib() -> C.CDLL:
             "raftgpu_group_get": ([vp, u32, C.POINTER(GroupState)], i32),
             "raftgpu_progress_get": ([vp, u32, u32, C.POINTER(Progress)], i32),
             "raftgpu_progress_set": ([vp, u32, u32, C.POINTER(Progress)], i32),
+            "raftgpu_progress_op": ([vp, u32, u32, i32, u64, u64, u64, C.POINTER(i32)], i32),
+            "raftgpu_has_quorum": ([vp, u32, u32, C.POINTER(i32)], i32),
+            "raftgpu_quorum_recently_active": ([vp, u32, u32, C.POINTER(i32)], i32),
+            "raftgpu_group_maybe_commit_to": ([vp, u32, u64, C.POINTER(i32)], i32),
             "raftgpu_set_group_commit": ([vp, u32, i32], i32),
             "raftgpu_assign_commit_group": ([vp, u32, u32, u64], i32),
             "raftgpu_column_write": ([vp, i32, u32, u32, u32, vp], i32),
@@ -371,6 +378,28 @@ class Arena:
 
     def progress_set(self, g, slot, p: Progress):
         self._ck(self._L.raftgpu_progress_set(self._h, g, slot, C.byref(p)), "progress_set")
+
+    def progress_op(self, g, slot, op: int, a0=0, a1=0, a2=0) -> int:
+        r = C.c_int32()
+        self._ck(self._L.raftgpu_progress_op(self._h, g, slot, op, a0, a1, a2, C.byref(r)), "progress_op")
+        return r.value
+
+    def has_quorum(self, g, slot_mask: int) -> bool:
+        r = C.c_int32()
+        self._ck(self._L.raftgpu_has_quorum(self._h, g, slot_mask, C.byref(r)), "has_quorum")
+        return bool(r.value)
+
+    def quorum_recently_active(self, g, perspective_of_slot: int) -> bool:
+        r = C.c_int32()
+        self._ck(self._L.raftgpu_quorum_recently_active(self._h, g, perspective_of_slot, C.byref(r)),
+                 "quorum_recently_active")
+        return bool(r.value)
+
+    def group_maybe_commit_to(self, g, max_index: int) -> bool:
+        r = C.c_int32()
+        self._ck(self._L.raftgpu_group_maybe_commit_to(self._h, g, max_index, C.byref(r)),
+                 "group_maybe_commit_to")
+        return bool(r.value)
 
     def set_group_commit(self, g, enable: bool):
         self._ck(self._L.raftgpu_set_group_commit(self._h, g, int(enable)), "set_group_commit")

@@ -786,6 +786,58 @@ int32_t raftgpu_progress_set(raftgpu_arena *a, uint32_t g, uint32_t peer_slot,
     });
 }
 
+static int32_t scratch_i32_op(raftgpu_arena *a, int32_t *out, const std::function<void(cudaStream_t, int32_t *)> &launch) {
+    int32_t *d = static_cast<int32_t *>(a->d_scratch) + 24;  // offset 96
+    uint8_t *hs = static_cast<uint8_t *>(a->h_scratch);
+    CK(a, cudaSetDevice(a->device));
+    launch(a->s_compute, d);
+    CKL(a);
+    CK(a, cudaMemcpyAsync(hs + 96, d, 4, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    if (out) *out = *reinterpret_cast<int32_t *>(hs + 96);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_progress_op(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, int32_t op, uint64_t a0,
+                            uint64_t a1, uint64_t a2, int32_t *out_result) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    if (!group_ok(a, g) || peer_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
+    if (!((present_mask(a->h_meta[g]) >> peer_slot) & 1u)) return RAFTGPU_ERR_PEER_NOT_FOUND;
+    if (op < 0 || op > RAFTGPU_POP_RESET) return RAFTGPU_ERR_INVALID;
+    return scratch_i32_op(a, out_result, [&](cudaStream_t st, int32_t *d) {
+        progress_op_kernel<<<1, 1, 0, st>>>(a->cols, g, peer_slot, op, a0, a1, a2, d);
+    });
+}
+
+int32_t raftgpu_has_quorum(raftgpu_arena *a, uint32_t g, uint32_t slot_mask, int32_t *out) {
+    if (!a || !out) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    return scratch_i32_op(a, out, [&](cudaStream_t st, int32_t *d) {
+        quorum_kernel<<<1, 1, 0, st>>>(a->cols, g, 0, slot_mask & 0xffu, d);
+    });
+}
+
+int32_t raftgpu_quorum_recently_active(raftgpu_arena *a, uint32_t g, uint32_t perspective_of_slot,
+                                       int32_t *out) {
+    if (!a || !out) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    if (!group_ok(a, g) || perspective_of_slot >= RAFTGPU_SLOTS) return RAFTGPU_ERR_RANGE;
+    return scratch_i32_op(a, out, [&](cudaStream_t st, int32_t *d) {
+        quorum_kernel<<<1, 1, 0, st>>>(a->cols, g, 1, perspective_of_slot, d);
+    });
+}
+
+int32_t raftgpu_group_maybe_commit_to(raftgpu_arena *a, uint32_t g, uint64_t max_index, int32_t *out_advanced) {
+    if (!a) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    if (!group_ok(a, g)) return RAFTGPU_ERR_RANGE;
+    return scratch_i32_op(a, out_advanced, [&](cudaStream_t st, int32_t *d) {
+        group_op_kernel<<<1, 1, 0, st>>>(a->cols, g, 6, max_index, 0, reinterpret_cast<uint32_t *>(d));
+    });
+}
+
 int32_t raftgpu_set_group_commit(raftgpu_arena *a, uint32_t g, int32_t enable) {
     if (!a) return RAFTGPU_ERR_INVALID;
     std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);

@@ -881,6 +881,141 @@ __global__ void progress_set_kernel(Columns c, uint32_t g, uint32_t s, raftgpu_p
                                           (p.ins_full ? RAFTGPU_PF_INS_FULL : 0));
 }
 
+__device__ __forceinline__ uint32_t majority_vote(uint32_t mask, uint32_t yes, uint32_t no);
+
+// Every method of Progress (src/tracker/progress.rs:75-243) on one cell, literally, for the
+// host mirror's ProgressRef: op codes are RAFTGPU_POP_*.  *out gets the bool / status result.
+__global__ void progress_op_kernel(Columns c, uint32_t g, uint32_t s, int op, uint64_t a0, uint64_t a1,
+                                   uint64_t a2, int32_t *out) {
+    const size_t cell = static_cast<size_t>(s) * c.cap + g;
+    uint64_t matched = c.matched[cell], next = c.next_idx[cell];
+    uint32_t f = c.pflags[cell];
+    const uint32_t state = f & RAFTGPU_PF_STATE_MASK;
+    int32_t ret = 0;
+    auto reset_st = [&](uint32_t st) {  // progress.rs:75-80
+        f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | st;
+        c.pending_snapshot[cell] = 0;
+    };
+    switch (op) {
+    case RAFTGPU_POP_MAYBE_UPDATE:  // progress.rs:138-150
+        if (matched < a0) {
+            matched = a0;
+            f &= ~RAFTGPU_PF_PAUSED;
+            ret = 1;
+        }
+        if (next < a0 + 1) next = a0 + 1;
+        break;
+    case RAFTGPU_POP_MAYBE_DECR_TO: {  // progress.rs:168-206 (a0 rejected, a1 match_hint, a2 request_snapshot)
+        if (state == RAFTGPU_STATE_REPLICATE) {
+            if (a0 < matched || (a0 == matched && a2 == RAFTGPU_INVALID_INDEX)) break;
+            if (a2 == RAFTGPU_INVALID_INDEX)
+                next = matched + 1;
+            else
+                c.pending_req_snapshot[cell] = a2;
+            ret = 1;
+            break;
+        }
+        if ((next == 0 || next - 1 != a0) && a2 == RAFTGPU_INVALID_INDEX) break;
+        if (a2 == RAFTGPU_INVALID_INDEX) {
+            next = umin64(a0, a1 + 1);
+            if (next < 1) next = 1;
+        } else if (c.pending_req_snapshot[cell] == RAFTGPU_INVALID_INDEX) {
+            c.pending_req_snapshot[cell] = a2;
+        }
+        f &= ~RAFTGPU_PF_PAUSED;
+        ret = 1;
+        break;
+    }
+    case RAFTGPU_POP_UPDATE_COMMITTED:  // progress.rs:153-157
+        if (a0 > c.peer_committed[cell]) c.peer_committed[cell] = a0;
+        break;
+    case RAFTGPU_POP_OPTIMISTIC_UPDATE:  // progress.rs:160-163
+        next = a0 + 1;
+        break;
+    case RAFTGPU_POP_BECOME_PROBE:  // progress.rs:95-107
+        if (state == RAFTGPU_STATE_SNAPSHOT) {
+            const uint64_t pending = c.pending_snapshot[cell];
+            reset_st(RAFTGPU_STATE_PROBE);
+            next = umax64(matched + 1, pending + 1);
+        } else {
+            reset_st(RAFTGPU_STATE_PROBE);
+            next = matched + 1;
+        }
+        break;
+    case RAFTGPU_POP_BECOME_REPLICATE:  // progress.rs:110-114
+        reset_st(RAFTGPU_STATE_REPLICATE);
+        next = matched + 1;
+        break;
+    case RAFTGPU_POP_BECOME_SNAPSHOT:  // progress.rs:117-121
+        reset_st(RAFTGPU_STATE_SNAPSHOT);
+        c.pending_snapshot[cell] = a0;
+        break;
+    case RAFTGPU_POP_SNAPSHOT_FAILURE:  // progress.rs:124-127
+        c.pending_snapshot[cell] = 0;
+        break;
+    case RAFTGPU_POP_MAYBE_SNAPSHOT_ABORT:  // progress.rs:131-134
+        ret = state == RAFTGPU_STATE_SNAPSHOT && matched >= c.pending_snapshot[cell];
+        break;
+    case RAFTGPU_POP_IS_PAUSED:  // progress.rs:210-216
+        ret = state == RAFTGPU_STATE_PROBE ? (f & RAFTGPU_PF_PAUSED) != 0
+              : state == RAFTGPU_STATE_REPLICATE ? (f & RAFTGPU_PF_INS_FULL) != 0 : 1;
+        break;
+    case RAFTGPU_POP_RESUME:  // progress.rs:219-222
+        f &= ~RAFTGPU_PF_PAUSED;
+        break;
+    case RAFTGPU_POP_PAUSE:  // progress.rs:225-228
+        f |= RAFTGPU_PF_PAUSED;
+        break;
+    case RAFTGPU_POP_UPDATE_STATE:  // progress.rs:231-243 (a0 = last); -1 where the reference panics
+        if (state == RAFTGPU_STATE_REPLICATE)
+            next = a0 + 1;  // optimistic_update; ins.add(last) is the host's
+        else if (state == RAFTGPU_STATE_PROBE)
+            f |= RAFTGPU_PF_PAUSED;
+        else
+            ret = -1;
+        break;
+    case RAFTGPU_POP_RESET:  // progress.rs:82-92 (a0 = next_idx)
+        matched = 0;
+        next = a0;
+        f = RAFTGPU_STATE_PROBE;
+        c.pending_snapshot[cell] = 0;
+        c.pending_req_snapshot[cell] = RAFTGPU_INVALID_INDEX;
+        break;
+    default:
+        ret = -2;
+    }
+    c.matched[cell] = matched;
+    c.next_idx[cell] = next;
+    c.pflags[cell] = static_cast<uint8_t>(f);
+    *out = ret;
+}
+
+// ProgressTracker::has_quorum (tracker.rs:367-372): vote_result(|id| set.get(id).map(|_| true)) == Won,
+// and quorum_recently_active (tracker.rs:346-361), which also clears recent_active.
+__global__ void quorum_kernel(Columns c, uint32_t g, int op, uint32_t arg, int32_t *out) {
+    const uint32_t meta = c.meta[g];
+    const uint32_t in = RAFTGPU_META_IN(meta), outm = RAFTGPU_META_OUT(meta);
+    uint32_t active = arg;
+    if (op == 1) {  // quorum_recently_active(perspective_of = slot arg)
+        const uint32_t present = in | outm | RAFTGPU_META_LEARN(meta);
+        active = 0;
+        for (int s = 0; s < kSlots; s++) {
+            if (!((present >> s) & 1u)) continue;
+            uint8_t *f = &c.pflags[static_cast<size_t>(s) * c.cap + g];
+            if (static_cast<uint32_t>(s) == arg) {
+                *f |= RAFTGPU_PF_RECENT_ACTIVE;  // tracker.rs:350-352
+                active |= 1u << s;
+            } else if (*f & RAFTGPU_PF_RECENT_ACTIVE) {
+                active |= 1u << s;  // tracker.rs:353-358
+                *f &= ~RAFTGPU_PF_RECENT_ACTIVE;
+            }
+        }
+    }
+    // members of the set vote yes, everyone else is missing (None)
+    const uint32_t i = majority_vote(in, active, 0), o = majority_vote(outm, active, 0);
+    *out = (i == RAFTGPU_VOTE_WON && o == RAFTGPU_VOTE_WON) ? 1 : 0;
+}
+
 __global__ void group_get_kernel(Columns c, uint32_t g, raftgpu_group_state *out) {
     raftgpu_group_state s{};
     s.meta = c.meta[g];
@@ -924,6 +1059,14 @@ __global__ void group_op_kernel(Columns c, uint32_t g, int op, uint64_t a, uint6
         if (*v == 0) *v = static_cast<uint8_t>(b);  // entry(id).or_insert(vote)
         break;
     }
+    case 6:  // RaftLog::maybe_commit(max_index = a, term = the leader's), raft_log.rs:487-499, range form
+        if (a > c.committed[g] && a >= c.term_start[g] && a <= c.last_index[g]) {
+            c.committed[g] = a;
+            *out = 1;
+        } else {
+            *out = 0;
+        }
+        break;
     }
 }
 

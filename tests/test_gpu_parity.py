@@ -238,6 +238,85 @@ def test_group_commit_random_vs_oracle(small):
     small.group_free(g)
 
 
+def test_progress_ops_vs_oracle(small):
+    """raftgpu_progress_op: every Progress method (progress.rs:75-243) on the device cell vs the
+    oracle's restatement, on random states and arguments."""
+    L = O.lib()
+    rng = random.Random(77)
+    g = small.group_alloc()
+    small.group_set_conf(g, 0b11, 0, 0, 0, 1)
+    ops = [
+        (B.POP_MAYBE_UPDATE, lambda p, a: L.ro_progress_maybe_update(p, a[0]), 1),
+        (B.POP_MAYBE_DECR_TO, lambda p, a: L.ro_progress_maybe_decr_to(p, a[0], a[1], a[2]), 3),
+        (B.POP_UPDATE_COMMITTED, lambda p, a: L.ro_progress_update_committed(p, a[0]) or 0, 1),
+        (B.POP_OPTIMISTIC_UPDATE, lambda p, a: L.ro_progress_optimistic_update(p, a[0]) or 0, 1),
+        (B.POP_BECOME_PROBE, lambda p, a: L.ro_progress_become_probe(p) or 0, 0),
+        (B.POP_BECOME_REPLICATE, lambda p, a: L.ro_progress_become_replicate(p) or 0, 0),
+        (B.POP_BECOME_SNAPSHOT, lambda p, a: L.ro_progress_become_snapshot(p, a[0]) or 0, 1),
+        (B.POP_SNAPSHOT_FAILURE, lambda p, a: L.ro_progress_snapshot_failure(p) or 0, 0),
+        (B.POP_MAYBE_SNAPSHOT_ABORT, lambda p, a: L.ro_progress_maybe_snapshot_abort(p), 0),
+        (B.POP_IS_PAUSED, lambda p, a: L.ro_progress_is_paused(p), 0),
+        (B.POP_RESUME, lambda p, a: L.ro_progress_resume(p) or 0, 0),
+        (B.POP_PAUSE, lambda p, a: L.ro_progress_pause(p) or 0, 0),
+        (B.POP_UPDATE_STATE, lambda p, a: L.ro_progress_update_state(p, a[0]), 1),
+        (B.POP_RESET, lambda p, a: L.ro_progress_reset(p, a[0]) or 0, 1),
+    ]
+    fields = ("matched", "next_idx", "pending_snapshot", "pending_request_snapshot", "commit_group_id",
+              "committed_index", "state", "paused", "recent_active", "ins_full")
+    for _ in range(400):
+        want = O.Progress()
+        want.matched, want.next_idx = rng.randrange(0, 12), rng.randrange(0, 14)
+        want.pending_snapshot = rng.choice([0, 0, rng.randrange(1, 14)])
+        want.pending_request_snapshot = rng.choice([0, 0, rng.randrange(1, 14)])
+        want.commit_group_id, want.committed_index = rng.randrange(0, 3), rng.randrange(0, 12)
+        want.state, want.paused = rng.randrange(0, 3), rng.randrange(0, 2)
+        want.recent_active, want.ins_full = rng.randrange(0, 2), rng.randrange(0, 2)
+        got = small.progress_get(g, 1)
+        for f in fields:
+            setattr(got, f, getattr(want, f))
+        small.progress_set(g, 1, got)
+        code, fn, nargs = rng.choice(ops)
+        args = [rng.choice([0, rng.randrange(0, 14)]) for _ in range(3)]
+        want_ret = fn(C.byref(want), args)
+        got_ret = small.progress_op(g, 1, code, *args)
+        after = small.progress_get(g, 1)
+        assert got_ret == want_ret, (code, args)
+        for f in fields:
+            assert getattr(after, f) == getattr(want, f), (code, args, f)
+    small.group_free(g)
+
+
+def test_has_quorum_and_recently_active_vs_oracle(small):
+    rng = random.Random(3)
+    g = small.group_alloc()
+    for _ in range(100):
+        inc, out = rng.randrange(0, 256), rng.choice([0, rng.randrange(0, 256)])
+        learners = rng.randrange(0, 256) & ~(inc | out)
+        small.group_set_conf(g, 0, 0, 0, None, 1)
+        small.group_set_conf(g, inc, out, learners, None, 1)
+        active = rng.randrange(0, 256)
+        a = [s + 1 for s in range(8) if inc >> s & 1]
+        b = [s + 1 for s in range(8) if out >> s & 1]
+        want = O.joint_vote_result(a, b, {s + 1: True for s in range(8) if active >> s & 1}) == O.VOTE_WON
+        assert small.has_quorum(g, active) == want           # tracker.rs:367-372
+        present = inc | out | learners
+        if present:
+            me = rng.choice([s for s in range(8) if present >> s & 1])
+            flags = {}
+            for s in range(8):
+                if present >> s & 1:
+                    p = small.progress_get(g, s)
+                    p.recent_active = rng.randrange(0, 2)
+                    flags[s] = p.recent_active
+                    small.progress_set(g, s, p)
+            act = {s + 1: True for s, f in flags.items() if f or s == me}
+            want = O.joint_vote_result(a, b, act) == O.VOTE_WON
+            assert small.quorum_recently_active(g, me) == want  # tracker.rs:346-361
+            for s in flags:
+                assert small.progress_get(g, s).recent_active == (1 if s == me else 0)
+    small.group_free(g)
+
+
 # --------------------------------------------------------------------------- lifecycle
 
 def test_group_lifecycle_mirrors_raft_new_reset_become_leader(small):

@@ -191,6 +191,8 @@ typedef struct {
     uint32_t n_waves;    /* kernel waves the records were split into (see raftgpu_enqueue_append_resp) */
     uint32_t n_groups;   /* groups recomputed */
     uint64_t n_advanced; /* groups whose committed index advanced */
+    uint64_t h2d_bytes;  /* bytes DMAed host -> device for this step (packed staging records) */
+    uint64_t d2h_bytes;  /* bytes DMAed device -> host (advanced bitmap, commit indexes, results) */
 } raftgpu_step_result;
 
 /* ---- arena lifecycle ---------------------------------------------------- */
@@ -351,8 +353,9 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *arena, const raftgpu_append_resp *re
 /* One batched step over everything enqueued: H2D of the staged records, the
  * apply kernel per wave, ONE recompute pass over all allocated groups, D2H of
  * the results.  raftgpu_step = raftgpu_step_begin + raftgpu_step_wait.  Between
- * begin and wait the caller may already enqueue the NEXT step's records (double
- * buffered). */
+ * begin and wait the caller may already enqueue the NEXT step's records, and may even
+ * begin it: up to TWO steps can be in flight (three staging sets), so the H2D of step
+ * j+1 overlaps the kernels and D2H of step j.  raftgpu_step_wait completes the oldest. */
 #define RAFTGPU_STEP_READ_COMMITTED 0x1u /* also copy back the new committed index of advanced groups */
 #define RAFTGPU_STEP_READ_RESULTS 0x2u   /* also copy back the per-record result bytes */
 int32_t raftgpu_step_begin(raftgpu_arena *arena, uint32_t flags);

@@ -99,7 +99,7 @@ class Counters(C.Structure):
 
 class StepResult(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_waves", C.c_uint32), ("n_groups", C.c_uint32),
-                ("n_advanced", C.c_uint64)]
+                ("n_advanced", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class SynthColumns(C.Structure):

@@ -6,6 +6,7 @@
 // RAFTGPU_ERR_NO_DEVICE and nothing else can be called.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <thread>
@@ -30,13 +31,15 @@ using namespace raftgpu;
 
 namespace {
 
-constexpr int kNumSets = 2;        // double-buffered staging
-constexpr uint32_t kChunk = 8192;  // records per staging chunk (192 KiB)
+constexpr int kNumSets = 3;        // staging sets: one filling, up to two steps in flight
+constexpr uint32_t kChunk = 2048;  // records per staging chunk (48 KiB)
 
+// A record moved to a later wave: its packed form (1..4 PackedRec) plus where its result goes.
 struct OverflowRec {
-    raftgpu_append_resp rec;
+    PackedRec pk[4];
+    int n_pk;
     uint32_t ring;
-    uint64_t seq;  // position in the ring's enqueue order
+    uint64_t seq;  // position of the (main) record in the ring's enqueue order
 };
 
 // One caller thread's staging ring: a list of chunks of the set's shared pinned
@@ -50,8 +53,8 @@ struct Ring {
 
 struct StagingSet {
     // host (pinned)
-    raftgpu_append_resp *h_recs = nullptr;      // [n_chunks][kChunk] wave-0 records, shared by all rings
-    raftgpu_append_resp *h_overflow = nullptr;  // later waves, packed at submit time
+    PackedRec *h_recs = nullptr;      // [n_chunks][kChunk] packed wave-0 records, shared by all rings
+    PackedRec *h_overflow = nullptr;  // later waves, laid out at submit time
     uint32_t *h_adv_bitmap = nullptr;
     uint64_t *h_committed = nullptr;
     uint8_t *h_results = nullptr;
@@ -63,9 +66,9 @@ struct StagingSet {
     std::mutex overflow_mu;
     std::unordered_map<uint64_t, uint32_t> overflow_depth;      // cell -> waves used beyond 0
     std::vector<std::vector<OverflowRec>> overflow_waves;       // wave w+1 records
-    std::vector<std::pair<uint32_t, uint64_t>> overflow_order;  // (ring, seq) per submitted overflow rec
+    std::vector<std::pair<uint32_t, uint64_t>> overflow_order;  // (ring, seq | UINT64_MAX for EXT) per packed rec
     // device
-    raftgpu_append_resp *d_recs = nullptr;
+    PackedRec *d_recs = nullptr;
     uint32_t *d_adv_bitmap = nullptr;
     uint64_t *d_commit_out = nullptr;
     uint8_t *d_results = nullptr;
@@ -99,7 +102,25 @@ struct HostPool {
         cv_done.wait(lk, [&] { return pending == 0; });
     }
     void worker(int idx, cpu_set_t cpus, bool pin) {
-        if (pin) sched_setaffinity(0, sizeof(cpus), &cpus);
+        if (pin) {
+            // one CPU per worker, taken in order from the GPU-local list (its first half are
+            // distinct physical cores on these hosts; SMT siblings come after)
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            int seen = 0, chosen = -1;
+            const int want = idx % std::max(1, CPU_COUNT(&cpus));
+            for (int c = 0; c < CPU_SETSIZE; c++)
+                if (CPU_ISSET(c, &cpus) && seen++ == want) {
+                    chosen = c;
+                    break;
+                }
+            if (chosen >= 0) {
+                CPU_SET(chosen, &one);
+                sched_setaffinity(0, sizeof(one), &one);
+            } else {
+                sched_setaffinity(0, sizeof(cpus), &cpus);
+            }
+        }
         uint64_t seen = 0;
         for (;;) {
             std::function<void(int)> fn;
@@ -150,7 +171,8 @@ struct raftgpu_arena {
     StagingSet sets[kNumSets];
     int fill = 0;        // set currently being filled by enqueue
     int last_done = -1;  // set whose results raftgpu_step_results exposes
-    int pending = -1;    // set submitted by step_begin and not yet waited for
+    int inflight[2] = {-1, -1};  // sets submitted by step_begin and not yet waited for, oldest first
+    int n_inflight = 0;
     // control plane: single-group calls share the scratch buffers and the meta mirror
     std::mutex ctl_mu;
     // group allocation
@@ -330,11 +352,14 @@ int32_t launch_recompute(raftgpu_arena *a, cudaStream_t st, uint32_t first, uint
     return RAFTGPU_OK;
 }
 
-int32_t launch_apply(raftgpu_arena *a, cudaStream_t st, const raftgpu_append_resp *d_recs, uint64_t n,
-                     uint8_t *d_results) {
+int32_t launch_apply(raftgpu_arena *a, cudaStream_t st, const void *d_recs, uint64_t n, uint8_t *d_results,
+                     bool packed) {
     if (n == 0) return RAFTGPU_OK;
     const uint32_t blocks = std::min<uint32_t>(div_up(n, 256), static_cast<uint32_t>(a->grid_apply));
-    apply_kernel<<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
+    if (packed)
+        apply_kernel<true><<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
+    else
+        apply_kernel<false><<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
     CKL(a);
     return RAFTGPU_OK;
 }
@@ -438,7 +463,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     a->grid_recompute = std::max(1, occ) * a->sm_count;
     TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, recompute_kernel<true>, 256, 0));
     a->grid_recompute5 = std::max(1, occ) * a->sm_count;
-    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel, 256, 0));
+    TRYC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, apply_kernel<true>, 256, 0));
     a->grid_apply = std::max(1, occ) * a->sm_count;
     a->tma_smem = 200u * 1024u;
     TRYC(cudaFuncSetAttribute(recompute_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -548,13 +573,17 @@ bool column_desc(raftgpu_arena *a, int32_t col, ColumnDesc *d) {
     }
 }
 
-// Move a duplicate-cell record (and the EXT record of a reject) to a later wave.
-void push_overflow(StagingSet &s, uint64_t cell, const raftgpu_append_resp *r, int n_recs, uint32_t ring,
-                   uint64_t seq) {
+// Move a duplicate-cell record (already packed) to a later wave.
+void push_overflow(StagingSet &s, uint64_t cell, const PackedRec *pk, int n_pk, uint32_t ring, uint64_t seq) {
     std::lock_guard<std::mutex> lk(s.overflow_mu);
     const uint32_t depth = s.overflow_depth[cell]++;  // 0 -> wave 1
     if (s.overflow_waves.size() <= depth) s.overflow_waves.resize(depth + 1);
-    for (int k = 0; k < n_recs; k++) s.overflow_waves[depth].push_back(OverflowRec{r[k], ring, seq + k});
+    OverflowRec o{};
+    for (int k = 0; k < n_pk; k++) o.pk[k] = pk[k];
+    o.n_pk = n_pk;
+    o.ring = ring;
+    o.seq = seq;
+    s.overflow_waves[depth].push_back(o);
 }
 
 // make a finished set reusable for filling
@@ -953,21 +982,51 @@ int32_t raftgpu_apply_device(raftgpu_arena *a, void *stream, const raftgpu_appen
                              uint64_t n, uint8_t *d_results) {
     if (!a || (!d_records && n)) return RAFTGPU_ERR_INVALID;
     CK(a, cudaSetDevice(a->device));
-    return launch_apply(a, pick_stream(a, stream), d_records, n, d_results);
+    return launch_apply(a, pick_stream(a, stream), d_records, n, d_results, /*packed=*/false);
 }
 
-// Streaming store of one record into the pinned ring: the destination is written once and
-// next read by the DMA engine, so bypass the cache (no read-for-ownership traffic).
-static inline void store_rec(raftgpu_append_resp *dst, const raftgpu_append_resp &r) {
+// Streaming store of one packed record into the pinned ring: the destination is written once
+// and next read by the DMA engine, so bypass the cache (no read-for-ownership traffic).
+static inline void store_rec(PackedRec *dst, const PackedRec &r) {
 #if defined(__x86_64__)
-    const long long *src = reinterpret_cast<const long long *>(&r);
-    long long *d = reinterpret_cast<long long *>(dst);
-    _mm_stream_si64(d, src[0]);
-    _mm_stream_si64(d + 1, src[1]);
-    _mm_stream_si64(d + 2, src[2]);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(dst),
+                     _mm_set_epi64x(static_cast<long long>(r.w1), static_cast<long long>(r.w0)));
 #else
     *dst = r;
 #endif
+}
+
+// Public 24-byte record (+ the EXT record of a REJECT) -> 1..4 packed 16-byte records
+// (layout: kernels.cuh PackedRec).
+static inline int pack_record(const raftgpu_append_resp &r, const raftgpu_append_resp *ext, PackedRec out[4]) {
+    uint64_t w0 = static_cast<uint64_t>(r.group) | (static_cast<uint64_t>(r.peer_slot & 7u) << 32);
+    if (r.peer_slot >= RAFTGPU_SLOTS) w0 = 0xffffffffull;  // no such slot: an out-of-range group says so
+    if (r.flags & RAFTGPU_REC_REJECT) w0 |= kPkReject;
+    if (r.flags & RAFTGPU_REC_LOCAL) w0 |= kPkLocal;
+    if (ext) w0 |= kPkHasExt;
+    bool wide = false;
+    uint64_t delta = 0;
+    if (r.flags & RAFTGPU_REC_LOCAL) {
+        if (r.commit == 0)
+            delta = kPkNoCommit;
+        else if (r.commit >= r.index && r.commit - r.index < kPkNoCommit)
+            delta = r.commit - r.index;
+        else
+            wide = true;
+    } else if (r.commit <= r.index && r.index - r.commit <= 0xFFFFFFull) {
+        delta = r.index - r.commit;
+    } else {
+        wide = true;
+    }
+    if (wide) w0 |= kPkWide;
+    int n = 0;
+    out[n++] = PackedRec{w0 | (delta << 40), r.index};
+    if (ext) {
+        out[n++] = PackedRec{kPkExt | (1ull << 40), ext->index};                  // next_probe_index
+        if (ext->commit != RAFTGPU_INVALID_INDEX) out[n++] = PackedRec{kPkExt | (2ull << 40), ext->commit};
+    }
+    if (wide) out[n++] = PackedRec{kPkExt | (3ull << 40), r.commit};
+    return n;
 }
 
 // Stage `n` records on one ring.  `sorted` = the caller promised non-decreasing group order
@@ -977,16 +1036,16 @@ static inline void store_rec(raftgpu_append_resp *dst, const raftgpu_append_resp
 static int32_t enqueue_ring(raftgpu_arena *a, StagingSet &s, uint32_t ring, const raftgpu_append_resp *recs,
                             uint64_t n, bool sorted, bool atomic_touch) {
     Ring &rg = s.rings[ring];
-    raftgpu_append_resp *dst =
-        rg.chunks.empty() ? nullptr : s.h_recs + static_cast<size_t>(rg.chunks.back()) * kChunk;
+    PackedRec *dst = rg.chunks.empty() ? nullptr : s.h_recs + static_cast<size_t>(rg.chunks.back()) * kChunk;
     uint32_t fill = rg.fill;
     uint64_t seq = rg.seq;
     int32_t rc = RAFTGPU_OK;
     uint32_t prev_group = 0;
-    const raftgpu_append_resp pad{0, 0, RAFTGPU_REC_EXT, 0, 0, 0};
+    const PackedRec pad{kPkExt, 0};
+    PackedRec pk[4];
     for (uint64_t i = 0; i < n; i++) {
         const raftgpu_append_resp &r = recs[i];
-        if (r.flags & RAFTGPU_REC_EXT) continue;  // copied together with its REJECT
+        if (r.flags & RAFTGPU_REC_EXT) continue;  // travels with its REJECT
         if (sorted) {
             if (r.group < prev_group) {
                 rc = RAFTGPU_ERR_INVALID;
@@ -994,8 +1053,20 @@ static int32_t enqueue_ring(raftgpu_arena *a, StagingSet &s, uint32_t ring, cons
             }
             prev_group = r.group;
         }
-        const int n_recs =
-            ((r.flags & RAFTGPU_REC_REJECT) && i + 1 < n && (recs[i + 1].flags & RAFTGPU_REC_EXT)) ? 2 : 1;
+        bool has_ext = false;
+        int n_pk;
+        if (__builtin_expect(r.flags == 0 && r.commit <= r.index && r.index - r.commit <= 0xFFFFFFull &&
+                                 r.peer_slot < RAFTGPU_SLOTS, 1)) {
+            // the common record: an accepted AppendResponse
+            pk[0] = PackedRec{static_cast<uint64_t>(r.group) | (static_cast<uint64_t>(r.peer_slot) << 32) |
+                                  ((r.index - r.commit) << 40),
+                              r.index};
+            n_pk = 1;
+        } else {
+            has_ext = (r.flags & RAFTGPU_REC_REJECT) && i + 1 < n && (recs[i + 1].flags & RAFTGPU_REC_EXT);
+            n_pk = pack_record(r, has_ext ? &recs[i + 1] : nullptr, pk);
+        }
+        const int n_orig = has_ext ? 2 : 1;
         bool dup = false;
         if (r.group < a->cap && r.peer_slot < RAFTGPU_SLOTS) {
             const uint8_t bit = static_cast<uint8_t>(1u << r.peer_slot);
@@ -1008,12 +1079,12 @@ static int32_t enqueue_ring(raftgpu_arena *a, StagingSet &s, uint32_t ring, cons
             }
         }
         if (dup) {
-            push_overflow(s, (static_cast<uint64_t>(r.group) << 3) | r.peer_slot, &r, n_recs, ring, seq);
-            for (int k = 0; k < n_recs; k++) rg.overflow_seq.push_back(seq + k);
-            seq += n_recs;
+            push_overflow(s, (static_cast<uint64_t>(r.group) << 3) | r.peer_slot, pk, n_pk, ring, seq);
+            for (int k = 0; k < n_orig; k++) rg.overflow_seq.push_back(seq + k);
+            seq += n_orig;
             continue;
         }
-        if (fill + n_recs > kChunk) {
+        if (fill + n_pk > kChunk) {
             // pad the tail of the chunk with no-op records (EXT records are skipped by the kernel)
             for (; dst && fill < kChunk; fill++) store_rec(&dst[fill], pad);
             const uint32_t ch = s.next_chunk.fetch_add(1);
@@ -1026,9 +1097,8 @@ static int32_t enqueue_ring(raftgpu_arena *a, StagingSet &s, uint32_t ring, cons
             dst = s.h_recs + static_cast<size_t>(ch) * kChunk;
             fill = 0;
         }
-        store_rec(&dst[fill++], r);
-        if (n_recs == 2) store_rec(&dst[fill++], recs[i + 1]);
-        seq += n_recs;
+        for (int k = 0; k < n_pk; k++) store_rec(&dst[fill++], pk[k]);
+        seq += n_orig;
     }
 #if defined(__x86_64__)
     _mm_sfence();
@@ -1083,10 +1153,21 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, 
         cut[t] = c;
     }
     std::vector<int32_t> rcs(T, RAFTGPU_OK);
+    static const bool trace = getenv("RAFTGPU_TRACE") != nullptr;
+    std::vector<double> wt(T, 0.0);
+    const auto t_all = std::chrono::steady_clock::now();
     a->pool->run([&](int t) {
+        const auto t0 = std::chrono::steady_clock::now();
         if (cut[t + 1] > cut[t])
             rcs[t] = enqueue_ring(a, s, static_cast<uint32_t>(t), recs + cut[t], cut[t + 1] - cut[t], sorted, !sorted);
+        wt[t] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     });
+    if (trace) {
+        const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_all).count();
+        fprintf(stderr, "[raftgpu] enqueue_bulk n=%llu T=%d total %.3f ms, workers min %.3f max %.3f ms\n",
+                static_cast<unsigned long long>(n), T, total, *std::min_element(wt.begin(), wt.end()),
+                *std::max_element(wt.begin(), wt.end()));
+    }
     bool order_ok = true;
     if (sorted)  // slices are internally ordered (checked by the workers); check the seams too
         for (int t = 1; t < T; t++)
@@ -1101,7 +1182,7 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, 
 
 int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     if (!a) return RAFTGPU_ERR_INVALID;
-    if (a->pending >= 0) return fail(a, RAFTGPU_ERR_BUSY, "previous step not waited for");
+    if (a->n_inflight >= 2) return fail(a, RAFTGPU_ERR_BUSY, "two steps already in flight: call raftgpu_step_wait");
     CK(a, cudaSetDevice(a->device));
     StagingSet &s = a->sets[a->fill];
     // pad every ring's last chunk, then ONE H2D of the used prefix of the shared buffer
@@ -1109,38 +1190,43 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     for (auto &rg : s.rings) {
         n_real += rg.seq - rg.overflow_seq.size();
         if (rg.chunks.empty()) continue;
-        raftgpu_append_resp *dst = s.h_recs + static_cast<size_t>(rg.chunks.back()) * kChunk;
-        for (; rg.fill < kChunk; rg.fill++) dst[rg.fill] = raftgpu_append_resp{0, 0, RAFTGPU_REC_EXT, 0, 0, 0};
+        PackedRec *dst = s.h_recs + static_cast<size_t>(rg.chunks.back()) * kChunk;
+        for (; rg.fill < kChunk; rg.fill++) dst[rg.fill] = PackedRec{kPkExt, 0};
     }
     const uint32_t used_chunks = std::min(s.next_chunk.load(), a->n_chunks);
     const uint64_t wave0 = static_cast<uint64_t>(used_chunks) * kChunk;
     if (wave0)
-        CK(a, cudaMemcpyAsync(s.d_recs, s.h_recs, wave0 * sizeof(raftgpu_append_resp),
+        CK(a, cudaMemcpyAsync(s.d_recs, s.h_recs, wave0 * sizeof(PackedRec),
                               cudaMemcpyHostToDevice, a->s_h2d));
     std::vector<uint64_t> wave_sizes;
     uint64_t ov = 0;
     s.overflow_order.clear();
+    uint64_t ov_orig = 0;
     for (auto &w : s.overflow_waves) {
-        if (ov + w.size() > a->overflow_records) return fail(a, RAFTGPU_ERR_FULL, "overflow staging full");
+        const uint64_t before = ov;
         for (const OverflowRec &o : w) {
-            s.h_overflow[ov++] = o.rec;
-            s.overflow_order.emplace_back(o.ring, o.seq);
+            if (ov + o.n_pk > a->overflow_records) return fail(a, RAFTGPU_ERR_FULL, "overflow staging full");
+            for (int k = 0; k < o.n_pk; k++) {
+                s.h_overflow[ov++] = o.pk[k];
+                s.overflow_order.emplace_back(o.ring, k == 0 ? o.seq : UINT64_MAX);
+            }
+            ov_orig += (o.pk[0].w0 & kPkHasExt) ? 2 : 1;
         }
-        wave_sizes.push_back(w.size());
+        wave_sizes.push_back(ov - before);
     }
     if (ov)
-        CK(a, cudaMemcpyAsync(s.d_recs + wave0, s.h_overflow, ov * sizeof(raftgpu_append_resp),
+        CK(a, cudaMemcpyAsync(s.d_recs + wave0, s.h_overflow, ov * sizeof(PackedRec),
                               cudaMemcpyHostToDevice, a->s_h2d));
     CK(a, cudaEventRecord(s.ev_h2d, a->s_h2d));
 
     // compute: apply per wave, then one recompute pass over [0, hi)
     CK(a, cudaStreamWaitEvent(a->s_compute, s.ev_h2d, 0));
     uint8_t *d_res = (flags & RAFTGPU_STEP_READ_RESULTS) ? s.d_results : nullptr;
-    int32_t rc = launch_apply(a, a->s_compute, s.d_recs, wave0, d_res);
+    int32_t rc = launch_apply(a, a->s_compute, s.d_recs, wave0, d_res, /*packed=*/true);
     if (rc != RAFTGPU_OK) return rc;
     uint64_t woff = wave0;
     for (uint64_t wsz : wave_sizes) {
-        rc = launch_apply(a, a->s_compute, s.d_recs + woff, wsz, d_res ? d_res + woff : nullptr);
+        rc = launch_apply(a, a->s_compute, s.d_recs + woff, wsz, d_res ? d_res + woff : nullptr, /*packed=*/true);
         if (rc != RAFTGPU_OK) return rc;
         woff += wsz;
     }
@@ -1167,12 +1253,22 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     s.in_flight = true;
     s.flags = flags;
     s.wave0_slots = wave0;
-    s.result.n_records = n_real + ov;
+    s.result.n_records = n_real + ov_orig;
+    s.result.h2d_bytes = (wave0 + ov) * sizeof(PackedRec);
+    s.result.d2h_bytes = 4 + (hi ? 4ull * ((hi + 31) / 32) : 0) +
+                         (((flags & RAFTGPU_STEP_READ_COMMITTED) && hi) ? 8ull * hi : 0) + ((d_res && woff) ? woff : 0);
     s.result.n_waves = static_cast<uint32_t>((n_real ? 1 : 0) + wave_sizes.size());
     s.result.n_groups = hi;
-    a->pending = a->fill;
-    // flip: the other set becomes the fill target (its step must have been waited for)
-    const int other = 1 - a->fill;
+    a->inflight[a->n_inflight++] = a->fill;
+    // flip: a set that is neither in flight nor holding the results of the last completed step
+    // becomes the fill target (with 3 sets and <= 2 in flight there is always one)
+    int other = -1;
+    for (int k = 0; k < kNumSets; k++) {
+        if (a->sets[k].in_flight) continue;
+        if (k == a->last_done && other >= 0) continue;  // prefer keeping the last results alive
+        if (other < 0 || k != a->last_done) other = k;
+    }
+    if (other < 0) return fail(a, RAFTGPU_ERR_BUSY, "no free staging set");
     rc = reclaim_set(a, a->sets[other]);
     if (rc != RAFTGPU_OK) return rc;
     if (a->last_done == other) a->last_done = -1;  // its results are gone
@@ -1182,14 +1278,17 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
 
 int32_t raftgpu_step_wait(raftgpu_arena *a, raftgpu_step_result *out) {
     if (!a) return RAFTGPU_ERR_INVALID;
-    if (a->pending < 0) return fail(a, RAFTGPU_ERR_INVALID, "no step in flight");
-    StagingSet &s = a->sets[a->pending];
+    if (a->n_inflight == 0) return fail(a, RAFTGPU_ERR_INVALID, "no step in flight");
+    const int cur = a->inflight[0];
+    StagingSet &s = a->sets[cur];
     CK(a, cudaEventSynchronize(s.ev_done));
     s.in_flight = false;
     s.result.n_advanced = *s.h_step_adv;
     if (out) *out = s.result;
-    a->last_done = a->pending;
-    a->pending = -1;
+    a->last_done = cur;
+    a->inflight[0] = a->inflight[1];
+    a->inflight[1] = -1;
+    a->n_inflight--;
     return RAFTGPU_OK;
 }
 
@@ -1220,24 +1319,27 @@ int32_t raftgpu_step_record_results(raftgpu_arena *a, uint32_t ring, uint8_t *ou
     *out_n = rg.seq;
     if (!out) return RAFTGPU_OK;
     if (cap < rg.seq) return RAFTGPU_ERR_INVALID;
+    memset(out, 0, rg.seq);
     // later-wave records of this ring, by seq
     for (size_t k = 0; k < s.overflow_order.size(); k++)
-        if (s.overflow_order[k].first == ring) out[s.overflow_order[k].second] = s.h_results[s.wave0_slots + k];
-    // wave-0 records fill the remaining seq positions in chunk order
+        if (s.overflow_order[k].first == ring && s.overflow_order[k].second != UINT64_MAX)
+            out[s.overflow_order[k].second] = s.h_results[s.wave0_slots + k];
+    // wave-0 records fill the remaining seq positions in chunk order: one result per main packed
+    // record, which stands for 1 public record (2 with its EXT)
     size_t ov = 0;
     uint64_t seq = 0;
     for (size_t ci = 0; ci < rg.chunks.size() && seq < rg.seq; ci++) {
         const uint8_t *res = s.h_results + static_cast<size_t>(rg.chunks[ci]) * kChunk;
-        const raftgpu_append_resp *src = s.h_recs + static_cast<size_t>(rg.chunks[ci]) * kChunk;
+        const PackedRec *src = s.h_recs + static_cast<size_t>(rg.chunks[ci]) * kChunk;
         for (uint32_t k = 0; k < kChunk && seq < rg.seq; k++) {
-            // padding: an EXT record that does not follow a REJECT of the same chunk
-            if ((src[k].flags & RAFTGPU_REC_EXT) && (k == 0 || !(src[k - 1].flags & RAFTGPU_REC_REJECT))) continue;
+            if (src[k].w0 & kPkExt) continue;  // EXT payloads and padding
             while (ov < rg.overflow_seq.size() && rg.overflow_seq[ov] == seq) {
                 ov++;
                 seq++;
             }
             if (seq >= rg.seq) break;
-            out[seq++] = res[k];
+            out[seq] = res[k];
+            seq += (src[k].w0 & kPkHasExt) ? 2 : 1;
         }
     }
     return RAFTGPU_OK;

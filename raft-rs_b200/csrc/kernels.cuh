@@ -560,19 +560,84 @@ struct CellRegs {
     uint64_t matched, next_idx, peer_committed;
 };
 
-__device__ __forceinline__ RecRegs load_rec(const raftgpu_append_resp *recs, uint64_t i, uint64_t n) {
+// Packed staging record, 16 bytes: what raftgpu_enqueue_* writes into the pinned rings and the
+// step path ships over PCIe (the public 24-byte raftgpu_append_resp stays the API; packing cuts
+// the H2D bytes -- the end-to-end bottleneck -- and the apply kernel's record traffic by a third).
+//   w0: [0,32) group  [32,35) slot  35 REJECT  36 LOCAL  37 EXT  38 WIDE  39 HAS_EXT  [40,64) delta
+//   w1: m.index   (EXT: the payload)
+// commit is carried as a 24-bit delta: index - commit for a message (a follower's commit never
+// exceeds what it acknowledges), commit - index for a LOCAL record (0xFFFFFF = "no new
+// last_index"); anything else sets WIDE and the exact value follows in an EXT record.
+// EXT kinds (in the delta field): 1 = next_probe_index, 2 = request_snapshot, 3 = wide commit,
+// 0 = padding.
+struct PackedRec {
+    uint64_t w0, w1;
+};
+constexpr uint64_t kPkReject = 1ull << 35, kPkLocal = 1ull << 36, kPkExt = 1ull << 37, kPkWide = 1ull << 38,
+                   kPkHasExt = 1ull << 39;
+constexpr uint32_t kPkNoCommit = 0xFFFFFFu;
+
+template <bool kPacked>
+__device__ __forceinline__ RecRegs load_rec(const void *recs_v, uint64_t i, uint64_t n) {
     RecRegs r;
-    if (i < n) {
-        const uint64_t *p = reinterpret_cast<const uint64_t *>(recs + i);
-        r.w0 = p[0];
-        r.index = p[1];
-        r.commit = p[2];
-    } else {  // past the end: a no-op (EXT) record
+    if (i >= n) {  // past the end: a no-op (EXT) record
         r.w0 = static_cast<uint64_t>(RAFTGPU_REC_EXT) << 40;
         r.index = 0;
         r.commit = 0;
+        return r;
+    }
+    if constexpr (!kPacked) {
+        const uint64_t *p = reinterpret_cast<const uint64_t *>(static_cast<const raftgpu_append_resp *>(recs_v) + i);
+        r.w0 = p[0];
+        r.index = p[1];
+        r.commit = p[2];
+    } else {
+        const ulonglong2 q = reinterpret_cast<const ulonglong2 *>(recs_v)[i];  // one 128-bit load
+        const uint64_t w0 = q.x;
+        const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
+        const uint32_t flags = ((w0 & kPkReject) ? RAFTGPU_REC_REJECT : 0u) | ((w0 & kPkLocal) ? RAFTGPU_REC_LOCAL : 0u) |
+                               ((w0 & kPkExt) ? RAFTGPU_REC_EXT : 0u);
+        // the public layout: group | slot << 32 | flags << 40
+        r.w0 = (w0 & 0xffffffffull) | (((w0 >> 32) & 7ull) << 32) | (static_cast<uint64_t>(flags) << 40);
+        r.index = q.y;
+        if (w0 & kPkLocal)
+            r.commit = delta == kPkNoCommit ? 0 : q.y + delta;
+        else
+            r.commit = q.y - delta;
+        if ((w0 & kPkWide) && !(w0 & kPkExt)) {  // rare: the exact commit follows in an EXT of kind 3
+            for (uint64_t j = i + 1; j < n && j <= i + 3; j++) {
+                const ulonglong2 e = reinterpret_cast<const ulonglong2 *>(recs_v)[j];
+                if (!(e.x & kPkExt)) break;
+                if ((e.x >> 40) == 3) r.commit = e.y;
+            }
+        }
     }
     return r;
+}
+
+// next_probe_index / request_snapshot of the REJECT at position i (raft.rs:1560-1661, 1709)
+template <bool kPacked>
+__device__ __forceinline__ void load_reject_ext(const void *recs_v, uint64_t i, uint64_t n, uint64_t &hint,
+                                                uint64_t &request_snapshot) {
+    hint = 0;
+    request_snapshot = RAFTGPU_INVALID_INDEX;
+    if constexpr (!kPacked) {
+        if (i + 1 < n) {
+            const uint64_t *e = reinterpret_cast<const uint64_t *>(static_cast<const raftgpu_append_resp *>(recs_v) + i + 1);
+            if ((e[0] >> 40) & RAFTGPU_REC_EXT) {
+                hint = e[1];
+                request_snapshot = e[2];
+            }
+        }
+    } else {
+        for (uint64_t j = i + 1; j < n && j <= i + 3; j++) {
+            const ulonglong2 e = reinterpret_cast<const ulonglong2 *>(recs_v)[j];
+            if (!(e.x & kPkExt)) break;
+            const uint32_t kind = static_cast<uint32_t>(e.x >> 40);
+            if (kind == 1) hint = e.y;
+            if (kind == 2) request_snapshot = e.y;
+        }
+    }
 }
 
 __device__ __forceinline__ CellRegs load_cell(const Columns &c, const RecRegs &r) {
@@ -592,9 +657,9 @@ __device__ __forceinline__ CellRegs load_cell(const Columns &c, const RecRegs &r
 }
 
 // One record against its cell: raft.rs:1663-1743.  Returns the result byte.
-__device__ __forceinline__ uint32_t apply_one(const Columns &c, const raftgpu_append_resp *recs, uint64_t n,
-                                              uint64_t i, const RecRegs &rec, const CellRegs &cd,
-                                              uint32_t (&local)[5]) {
+template <bool kPacked>
+__device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs, uint64_t n, uint64_t i,
+                                              const RecRegs &rec, const CellRegs &cd, uint32_t (&local)[5]) {
     const uint64_t index = rec.index, commit = rec.commit;
     const uint32_t g = static_cast<uint32_t>(rec.w0);
     const uint32_t slot = static_cast<uint32_t>(rec.w0 >> 32) & 0xffu;
@@ -635,14 +700,8 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const raftgpu_ap
 
         if (rflags & RAFTGPU_REC_REJECT) {
             local[2]++;
-            uint64_t hint = 0, request_snapshot = RAFTGPU_INVALID_INDEX;
-            if (i + 1 < n) {
-                const uint64_t *e = reinterpret_cast<const uint64_t *>(recs + i + 1);
-                if ((e[0] >> 40) & RAFTGPU_REC_EXT) {
-                    hint = e[1];
-                    request_snapshot = e[2];
-                }
-            }
+            uint64_t hint, request_snapshot;
+            load_reject_ext<kPacked>(recs, i, n, hint, request_snapshot);
             // Progress::maybe_decr_to, progress.rs:168-206
             bool ok;
             if (state == RAFTGPU_STATE_REPLICATE) {
@@ -715,20 +774,21 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const raftgpu_ap
     return res;
 }
 
+template <bool kPacked>
 __global__ void __launch_bounds__(256)
-apply_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n,
-             uint8_t *__restrict__ results, unsigned long long *__restrict__ counters) {
+apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__restrict__ results,
+             unsigned long long *__restrict__ counters) {
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t local[5] = {0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress
     uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     // prologue: fill the pipeline
-    RecRegs rec_a = load_rec(recs, i, n);
-    RecRegs rec_b = load_rec(recs, i + stride, n);
+    RecRegs rec_a = load_rec<kPacked>(recs, i, n);
+    RecRegs rec_b = load_rec<kPacked>(recs, i + stride, n);
     CellRegs cell_a = load_cell(c, rec_a);
     for (; i < n; i += stride) {
-        const RecRegs rec_c = load_rec(recs, i + 2 * stride, n);  // element k+2: record
+        const RecRegs rec_c = load_rec<kPacked>(recs, i + 2 * stride, n);  // element k+2: record
         const CellRegs cell_b = load_cell(c, rec_b);              // element k+1: its cell
-        const uint32_t res = apply_one(c, recs, n, i, rec_a, cell_a, local);  // element k
+        const uint32_t res = apply_one<kPacked>(c, recs, n, i, rec_a, cell_a, local);  // element k
         if (results) results[i] = static_cast<uint8_t>(res);
         rec_a = rec_b;
         cell_a = cell_b;

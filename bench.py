@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="pipelined e2e steps per timed chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--public-records", action="store_true",
+                    help="device-resident leg reads 24-byte public records instead of the packed 16-byte form")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no clock warm loop, no e2e, no CPU leg")
     args = ap.parse_args()
@@ -218,6 +220,7 @@ def main():
     # are slow on these VMs; HBM holds all K+W rounds.
     per_arena = [(W + K + N_ARENAS - 1 - a) // N_ARENAS for a in range(N_ARENAS)]
     arenas, round_len, d_recs = [], [], []
+    pack_buf = np.empty((5 * n + 64, 2), dtype=np.uint64)
     for a in range(N_ARENAS):
         seed = SEED + 0x100 * a + 0x10000 * rank
         s = B.Synth(n, seed, k_peers=K_PEERS)
@@ -227,10 +230,16 @@ def main():
         ptrs, lens = [], []
         for _ in range(per_arena[a]):
             recs = s.next_round()
-            p = ar.device_alloc(recs.nbytes)
-            ar.h2d(p, recs)
+            if args.public_records:       # the 24-byte public record layout in HBM
+                p = ar.device_alloc(recs.nbytes)
+                ar.h2d(p, recs)
+                lens.append((len(recs), len(recs)))
+            else:                         # the packed 16-byte wire form (what the staging path ships)
+                k = ar.pack_records(recs, pack_buf)
+                p = ar.device_alloc(16 * k)
+                ar.h2d(p, pack_buf[:k])
+                lens.append((k, len(recs)))
             ptrs.append(p)
-            lens.append(len(recs))
         arenas.append(ar)
         round_len.append(lens)
         d_recs.append(ptrs)
@@ -244,7 +253,10 @@ def main():
         a, r = schedule[i]
         if ev:
             ev[0].record(stream)
-        arenas[a].apply_device(d_recs[a][r], round_len[a][r], stream=sh)
+        if args.public_records:
+            arenas[a].apply_device(d_recs[a][r], round_len[a][r][0], stream=sh)
+        else:
+            arenas[a].apply_device_packed(d_recs[a][r], round_len[a][r][0], stream=sh)
         if ev:
             ev[1].record(stream)
         arenas[a].recompute(0, n, stream=sh)
@@ -279,7 +291,7 @@ def main():
     ms_total = e0.elapsed_time(e1)
     ms_apply = sum(e[0].elapsed_time(e[1]) for e in evs)
     ms_recompute = sum(e[1].elapsed_time(e[2]) for e in evs)
-    n_records = sum(round_len[a][r] for a, r in schedule[W:])
+    n_records = sum(round_len[a][r][1] for a, r in schedule[W:])
 
     # ---- e2e: host buffers -> enqueue -> step (H2D, kernels, D2H) on a fresh arena ------------
     # The caller's records sit in ordinary host memory; raftgpu_enqueue_append_resp stages them
@@ -346,6 +358,31 @@ def main():
         e2e_s += time.perf_counter() - t0
         e2e_timed += m
         h2d_bytes += sum(pj.nbytes for pj in parts)
+    # ---- e2e, zero-copy: the caller builds its batch (packed 16-byte records) directly in the
+    # arena's NUMA-local pinned memory (untimed, like the generation above); timed is
+    # raftgpu_step_begin_packed (H2D straight from that buffer, the GPU verifies the one-wave
+    # promise) + raftgpu_step_wait, two steps in flight.
+    zc = {"value": None}
+    if e2e_steps:
+        pk = [ea.host_alloc_packed(5 * n + 64) for _ in range(chunk)]
+        zc_s, zc_timed, zc_dma = 0.0, 0, [0, 0]
+        while zc_timed < e2e_steps:
+            m = min(chunk, e2e_steps - zc_timed)
+            ks = [ea.pack_records(es.next_round(bufs[j]), pk[j]) for j in range(m)]   # untimed
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            ea.step_begin_packed(pk[0], ks[0], flags)
+            for j in range(m):
+                if j + 1 < m:
+                    ea.step_begin_packed(pk[j + 1], ks[j + 1], flags)
+                sr = ea.step_wait()
+                zc_dma[0] += sr.h2d_bytes
+                zc_dma[1] += sr.d2h_bytes
+            zc_s += time.perf_counter() - t0
+            zc_timed += m
+        zc = {"seconds": zc_s, "steps": zc_timed, "h2d": zc_dma[0] / zc_timed, "d2h": zc_dma[1] / zc_timed}
     h2d = dma[0] / max(1, e2e_timed)
     d2h = dma[1] / max(1, e2e_timed)
     caller_bytes = h2d_bytes / max(1, e2e_timed)
@@ -359,7 +396,7 @@ def main():
         {"groups_device": n * K, "groups_e2e": n * e2e_timed,
          "recomputes": sum(c["recomputes"] for c in cnt), "advanced": sum(c["advanced"] for c in cnt),
          "records": sum(c["records"] for c in cnt)},
-        {"ms_total": ms_total, "e2e_s": e2e_s}, device="cuda")
+        {"ms_total": ms_total, "e2e_s": e2e_s, "zc_s": zc.get("seconds", 0.0)}, device="cuda")
     ms_max, e2e_max = maxes["ms_total"], maxes["e2e_s"]
     value = sums["groups_device"] / (ms_max * 1e-3)
     e2e_value = sums["groups_e2e"] / e2e_max if e2e_max > 0 else None
@@ -389,6 +426,7 @@ def main():
                             "round per step (apply + recompute)",
                 "groups_per_gpu": n, "peers": K_PEERS, "seed": hex(SEED),
                 "records_per_step": n_records / K,
+                "record_format": "24 B public" if args.public_records else "16 B packed (raftgpu_pack_records)",
                 "l2": f"inputs larger than L2: {N_ARENAS} arenas rotated, fresh records every step",
                 "parallelism": f"groups sharded over {world} GPU(s), no data-path collective",
             },
@@ -406,6 +444,12 @@ def main():
                                          "step_begin": 1e3 * phase[1] / max(1, e2e_timed),
                                          "step_wait": 1e3 * phase[2] / max(1, e2e_timed)},
                     "api": "raftgpu_enqueue_bulk(SORTED) + raftgpu_step_begin/_wait (READ_COMMITTED)"},
+            "e2e_zero_copy": None if not zc.get("steps") else {
+                "value": world * n * zc["steps"] / maxes["zc_s"], "unit": UNIT,
+                "ms_per_step": 1e3 * maxes["zc_s"] / zc["steps"], "steps": zc["steps"],
+                "h2d_bytes_per_step": zc["h2d"], "d2h_bytes_per_step": zc["d2h"],
+                "api": "raftgpu_step_begin_packed (caller-built packed records in raftgpu_host_alloc "
+                       "memory, no staging copy, device-side one-wave check) + raftgpu_step_wait"},
             "gpu_launches": 2 * K,
             "clocks": clocks,
             "counters": {"recomputes": sums["recomputes"], "advanced": sums["advanced"], "records": sums["records"]},

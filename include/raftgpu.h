@@ -193,6 +193,7 @@ typedef struct {
     uint64_t n_advanced; /* groups whose committed index advanced */
     uint64_t h2d_bytes;  /* bytes DMAed host -> device for this step (packed staging records) */
     uint64_t d2h_bytes;  /* bytes DMAed device -> host (advanced bitmap, commit indexes, results) */
+    uint64_t n_duplicates; /* zero-copy steps: records dropped because their cell already had one */
 } raftgpu_step_result;
 
 /* ---- arena lifecycle ---------------------------------------------------- */
@@ -331,6 +332,11 @@ int32_t raftgpu_recompute(raftgpu_arena *arena, void *stream, uint32_t first, ui
 int32_t raftgpu_apply_device(raftgpu_arena *arena, void *stream,
                              const raftgpu_append_resp *d_records, uint64_t n, uint8_t *d_results);
 
+/* Same, for records that are already in the packed 16-byte wire form (raftgpu_pack_records,
+ * the format the staging path ships over PCIe) in HBM: a third less record traffic. */
+int32_t raftgpu_apply_device_packed(raftgpu_arena *arena, void *stream, const void *d_packed_records,
+                                    uint64_t n_packed, uint8_t *d_results);
+
 /* Stage host records for the next step (RawNode::step -> Raft::step ->
  * handle_append_response, raw_node.rs:402-411 / raft.rs:1559).  Records for one
  * (group, peer) keep their arrival order: a second record for a cell that
@@ -349,6 +355,26 @@ int32_t raftgpu_enqueue_append_resp(raftgpu_arena *arena, uint32_t ring,
 #define RAFTGPU_BULK_SORTED 0x1u
 int32_t raftgpu_enqueue_bulk(raftgpu_arena *arena, const raftgpu_append_resp *records, uint64_t n,
                              uint32_t flags);
+
+/* ---- zero-copy submission ---------------------------------------------------
+ * For callers that build their batch directly in DMA-able memory: raftgpu_host_alloc returns
+ * pinned memory on the GPU-local NUMA node, raftgpu_pack_records converts public records to
+ * the 16-byte packed wire form (a REJECT and its EXT become 2-3 packed records; returns the
+ * packed count), and raftgpu_step_begin_packed ships such a buffer with no staging copy:
+ * H2D straight from the caller's buffer, ONE apply wave, the recompute pass, D2H of the
+ * results.  The one-record-per-(group, peer) precondition cannot be checked on the host
+ * without reading the batch, so the GPU checks it: a duplicate is not applied, counted in
+ * raftgpu_step_result.n_duplicates, and raftgpu_step_wait returns RAFTGPU_ERR_INVALID.
+ * The buffer must stay untouched until that step's raftgpu_step_wait returns. */
+typedef struct {
+    uint64_t w0, w1;
+} raftgpu_packed_rec;
+int32_t raftgpu_host_alloc(raftgpu_arena *arena, uint64_t bytes, void **out_pinned);
+int32_t raftgpu_host_free(raftgpu_arena *arena, void *pinned);
+int32_t raftgpu_pack_records(const raftgpu_append_resp *records, uint64_t n, raftgpu_packed_rec *out,
+                             uint64_t out_capacity, uint64_t *out_n);
+int32_t raftgpu_step_begin_packed(raftgpu_arena *arena, const raftgpu_packed_rec *pinned_records,
+                                  uint64_t n_packed, uint32_t flags);
 
 /* One batched step over everything enqueued: H2D of the staged records, the
  * apply kernel per wave, ONE recompute pass over all allocated groups, D2H of

@@ -99,7 +99,8 @@ class Counters(C.Structure):
 
 class StepResult(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_waves", C.c_uint32), ("n_groups", C.c_uint32),
-                ("n_advanced", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("n_advanced", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("n_duplicates", C.c_uint64)]
 
 
 class SynthColumns(C.Structure):
@@ -158,9 +159,14 @@ def lib() -> C.CDLL:
             "raftgpu_maybe_commit": ([vp, u32, C.POINTER(i32), C.POINTER(u64)], i32),
             "raftgpu_recompute": ([vp, vp, u32, u32, vp, vp, vp, vp], i32),
             "raftgpu_apply_device": ([vp, vp, vp, u64, vp], i32),
+            "raftgpu_apply_device_packed": ([vp, vp, vp, u64, vp], i32),
             "raftgpu_enqueue_append_resp": ([vp, u32, vp, u64], i32),
             "raftgpu_enqueue_bulk": ([vp, vp, u64, u32], i32),
             "raftgpu_step_begin": ([vp, u32], i32),
+            "raftgpu_step_begin_packed": ([vp, vp, u64, u32], i32),
+            "raftgpu_pack_records": ([vp, u64, vp, u64, C.POINTER(u64)], i32),
+            "raftgpu_host_alloc": ([vp, u64, C.POINTER(vp)], i32),
+            "raftgpu_host_free": ([vp, vp], i32),
             "raftgpu_step_wait": ([vp, C.POINTER(StepResult)], i32),
             "raftgpu_step": ([vp, u32, C.POINTER(StepResult)], i32),
             "raftgpu_step_results": ([vp, C.POINTER(vp), C.POINTER(vp)], i32),
@@ -459,6 +465,10 @@ class Arena:
     def apply_device(self, d_recs, n, stream=None, d_results=None):
         self._ck(self._L.raftgpu_apply_device(self._h, stream, d_recs, n, d_results), "apply_device")
 
+    def apply_device_packed(self, d_packed, n_packed, stream=None, d_results=None):
+        self._ck(self._L.raftgpu_apply_device_packed(self._h, stream, d_packed, n_packed, d_results),
+                 "apply_device_packed")
+
     def enqueue(self, recs: np.ndarray, ring: int = 0):
         assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous
         self._ck(self._L.raftgpu_enqueue_append_resp(self._h, ring, recs.ctypes.data, len(recs)),
@@ -469,12 +479,32 @@ class Arena:
         self._ck(self._L.raftgpu_enqueue_bulk(self._h, recs.ctypes.data, len(recs),
                                               BULK_SORTED if sorted_by_group else 0), "enqueue_bulk")
 
+    def host_alloc_packed(self, n_records: int) -> np.ndarray:
+        """NUMA-local pinned buffer of packed 16-byte records (u64 pairs), owned by the arena."""
+        p = C.c_void_p()
+        self._ck(self._L.raftgpu_host_alloc(self._h, 16 * n_records, C.byref(p)), "host_alloc")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n_records, 2))
+
+    def pack_records(self, recs: np.ndarray, out: np.ndarray) -> int:
+        assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous and out.dtype == np.uint64
+        n = C.c_uint64()
+        self._ck(self._L.raftgpu_pack_records(recs.ctypes.data, len(recs), out.ctypes.data, out.shape[0],
+                                              C.byref(n)), "pack_records")
+        return n.value
+
+    def step_begin_packed(self, packed: np.ndarray, n_packed: int, flags=0):
+        self._ck(self._L.raftgpu_step_begin_packed(self._h, packed.ctypes.data, n_packed, flags),
+                 "step_begin_packed")
+
     def step_begin(self, flags=0):
         self._ck(self._L.raftgpu_step_begin(self._h, flags), "step_begin")
 
-    def step_wait(self) -> StepResult:
+    def step_wait(self, check: bool = True) -> StepResult:
         r = StepResult()
-        self._ck(self._L.raftgpu_step_wait(self._h, C.byref(r)), "step_wait")
+        rc = self._L.raftgpu_step_wait(self._h, C.byref(r))
+        if check:
+            self._ck(rc, "step_wait")
+        r.status = rc
         return r
 
     def step(self, flags=0) -> StepResult:

@@ -72,7 +72,8 @@ struct StagingSet {
     uint32_t *d_adv_bitmap = nullptr;
     uint64_t *d_commit_out = nullptr;
     uint8_t *d_results = nullptr;
-    uint32_t *d_step_adv = nullptr;
+    uint32_t *d_step_adv = nullptr;  // [0] advanced groups of the step, [1] duplicate records (zero-copy)
+    uint32_t *d_touched = nullptr;   // [cap/4] zero-copy steps: one bit per (group, slot)
     // sync
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
     bool in_flight = false;
@@ -186,6 +187,7 @@ struct raftgpu_arena {
     uint64_t l2_bytes = 0, device_bytes = 0, pinned_bytes = 0;
     std::string last_error;
     std::vector<void *> user_allocs;
+    std::vector<void *> host_allocs;  // raftgpu_host_alloc
     HostPool *pool = nullptr;  // created on first raftgpu_enqueue_bulk
     cpu_set_t local_cpus;      // GPU-local CPUs (empty when unknown)
     bool have_local_cpus = false;
@@ -377,6 +379,7 @@ void free_set(StagingSet &s) {
     cudaFree(s.d_commit_out);
     cudaFree(s.d_results);
     cudaFree(s.d_step_adv);
+    cudaFree(s.d_touched);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_compute) cudaEventDestroy(s.ev_compute);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -403,6 +406,7 @@ void destroy(raftgpu_arena *a) {
     cudaFree(a->d_scratch);
     cudaFreeHost(a->h_scratch);
     for (void *p : a->user_allocs) cudaFree(p);
+    for (void *p : a->host_allocs) cudaFreeHost(p);
     delete a->pool;
     for (auto &s : a->sets) free_set(s);
     if (a->s_compute) cudaStreamDestroy(a->s_compute);
@@ -525,6 +529,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
         TRY(dev_alloc(a, &s.d_commit_out, a->cap));
         TRY(dev_alloc(a, &s.d_results, rec_total));
         TRY(dev_alloc(a, &s.d_step_adv, 4));
+        TRY(dev_alloc(a, &s.d_touched, a->cap / 4));
         TRYC(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         TRYC(cudaEventCreateWithFlags(&s.ev_compute, cudaEventDisableTiming));
         TRYC(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
@@ -985,6 +990,13 @@ int32_t raftgpu_apply_device(raftgpu_arena *a, void *stream, const raftgpu_appen
     return launch_apply(a, pick_stream(a, stream), d_records, n, d_results, /*packed=*/false);
 }
 
+int32_t raftgpu_apply_device_packed(raftgpu_arena *a, void *stream, const void *d_packed_records, uint64_t n,
+                                    uint8_t *d_results) {
+    if (!a || (!d_packed_records && n)) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    return launch_apply(a, pick_stream(a, stream), d_packed_records, n, d_results, /*packed=*/true);
+}
+
 // Streaming store of one packed record into the pinned ring: the destination is written once
 // and next read by the DMA engine, so bypass the cache (no read-for-ownership traffic).
 static inline void store_rec(PackedRec *dst, const PackedRec &r) {
@@ -1180,11 +1192,19 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, 
     return RAFTGPU_OK;
 }
 
-int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
+// Submit one step.  ext != nullptr: zero-copy -- wave 0 is the caller's pinned packed buffer and the
+// GPU verifies the one-record-per-cell promise; otherwise wave 0 is what the rings staged.
+static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ext, uint64_t ext_n) {
     if (!a) return RAFTGPU_ERR_INVALID;
     if (a->n_inflight >= 2) return fail(a, RAFTGPU_ERR_BUSY, "two steps already in flight: call raftgpu_step_wait");
     CK(a, cudaSetDevice(a->device));
     StagingSet &s = a->sets[a->fill];
+    if (ext) {
+        if (s.next_chunk.load() != 0 || !s.overflow_waves.empty())
+            return fail(a, RAFTGPU_ERR_INVALID, "records were enqueued for this step: cannot mix with a zero-copy batch");
+        if (ext_n > static_cast<uint64_t>(a->n_chunks) * kChunk)
+            return fail(a, RAFTGPU_ERR_FULL, "zero-copy batch larger than the device staging buffer");
+    }
     // pad every ring's last chunk, then ONE H2D of the used prefix of the shared buffer
     uint64_t n_real = 0;
     for (auto &rg : s.rings) {
@@ -1194,9 +1214,10 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
         for (; rg.fill < kChunk; rg.fill++) dst[rg.fill] = PackedRec{kPkExt, 0};
     }
     const uint32_t used_chunks = std::min(s.next_chunk.load(), a->n_chunks);
-    const uint64_t wave0 = static_cast<uint64_t>(used_chunks) * kChunk;
+    const uint64_t wave0 = ext ? ext_n : static_cast<uint64_t>(used_chunks) * kChunk;
+    if (ext) n_real = ext_n;
     if (wave0)
-        CK(a, cudaMemcpyAsync(s.d_recs, s.h_recs, wave0 * sizeof(PackedRec),
+        CK(a, cudaMemcpyAsync(s.d_recs, ext ? ext : s.h_recs, wave0 * sizeof(PackedRec),
                               cudaMemcpyHostToDevice, a->s_h2d));
     std::vector<uint64_t> wave_sizes;
     uint64_t ov = 0;
@@ -1222,7 +1243,19 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     // compute: apply per wave, then one recompute pass over [0, hi)
     CK(a, cudaStreamWaitEvent(a->s_compute, s.ev_h2d, 0));
     uint8_t *d_res = (flags & RAFTGPU_STEP_READ_RESULTS) ? s.d_results : nullptr;
-    int32_t rc = launch_apply(a, a->s_compute, s.d_recs, wave0, d_res, /*packed=*/true);
+    CK(a, cudaMemsetAsync(s.d_step_adv, 0, 8, a->s_compute));
+    int32_t rc = RAFTGPU_OK;
+    if (ext) {
+        CK(a, cudaMemsetAsync(s.d_touched, 0, a->cap, a->s_compute));
+        if (wave0) {
+            const uint32_t blocks = std::min<uint32_t>(div_up(wave0, 256), static_cast<uint32_t>(a->grid_apply));
+            apply_kernel<true, true><<<blocks, 256, 0, a->s_compute>>>(a->cols, s.d_recs, wave0, d_res, a->d_counters,
+                                                                     s.d_touched, s.d_step_adv + 1);
+            CKL(a);
+        }
+    } else {
+        rc = launch_apply(a, a->s_compute, s.d_recs, wave0, d_res, /*packed=*/true);
+    }
     if (rc != RAFTGPU_OK) return rc;
     uint64_t woff = wave0;
     for (uint64_t wsz : wave_sizes) {
@@ -1230,7 +1263,6 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
         if (rc != RAFTGPU_OK) return rc;
         woff += wsz;
     }
-    CK(a, cudaMemsetAsync(s.d_step_adv, 0, 4, a->s_compute));
     const uint32_t hi = a->hi;
     rc = launch_recompute(a, a->s_compute, 0, hi, a->voter_hint, s.d_adv_bitmap,
                           (flags & RAFTGPU_STEP_READ_COMMITTED) ? s.d_commit_out : nullptr, nullptr, nullptr,
@@ -1240,7 +1272,7 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
 
     // D2H of the results
     CK(a, cudaStreamWaitEvent(a->s_d2h, s.ev_compute, 0));
-    CK(a, cudaMemcpyAsync(s.h_step_adv, s.d_step_adv, 4, cudaMemcpyDeviceToHost, a->s_d2h));
+    CK(a, cudaMemcpyAsync(s.h_step_adv, s.d_step_adv, 8, cudaMemcpyDeviceToHost, a->s_d2h));
     if (hi)
         CK(a, cudaMemcpyAsync(s.h_adv_bitmap, s.d_adv_bitmap, 4ull * ((hi + 31) / 32),
                               cudaMemcpyDeviceToHost, a->s_d2h));
@@ -1255,7 +1287,7 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     s.wave0_slots = wave0;
     s.result.n_records = n_real + ov_orig;
     s.result.h2d_bytes = (wave0 + ov) * sizeof(PackedRec);
-    s.result.d2h_bytes = 4 + (hi ? 4ull * ((hi + 31) / 32) : 0) +
+    s.result.d2h_bytes = 8 + (hi ? 4ull * ((hi + 31) / 32) : 0) +
                          (((flags & RAFTGPU_STEP_READ_COMMITTED) && hi) ? 8ull * hi : 0) + ((d_res && woff) ? woff : 0);
     s.result.n_waves = static_cast<uint32_t>((n_real ? 1 : 0) + wave_sizes.size());
     s.result.n_groups = hi;
@@ -1276,6 +1308,59 @@ int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) {
     return RAFTGPU_OK;
 }
 
+int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) { return step_submit(a, flags, nullptr, 0); }
+
+int32_t raftgpu_step_begin_packed(raftgpu_arena *a, const raftgpu_packed_rec *pinned_records, uint64_t n_packed,
+                                  uint32_t flags) {
+    if (!a || (!pinned_records && n_packed)) return RAFTGPU_ERR_INVALID;
+    static_assert(sizeof(raftgpu_packed_rec) == sizeof(PackedRec), "packed record layout");
+    static const PackedRec kNone{kPkExt, 0};
+    return step_submit(a, flags, n_packed ? reinterpret_cast<const PackedRec *>(pinned_records) : &kNone,
+                       n_packed);
+}
+
+int32_t raftgpu_pack_records(const raftgpu_append_resp *records, uint64_t n, raftgpu_packed_rec *out,
+                             uint64_t out_capacity, uint64_t *out_n) {
+    if ((!records && n) || !out || !out_n) return RAFTGPU_ERR_INVALID;
+    uint64_t k = 0;
+    PackedRec pk[4];
+    for (uint64_t i = 0; i < n; i++) {
+        const raftgpu_append_resp &r = records[i];
+        if (r.flags & RAFTGPU_REC_EXT) continue;
+        const bool has_ext = (r.flags & RAFTGPU_REC_REJECT) && i + 1 < n && (records[i + 1].flags & RAFTGPU_REC_EXT);
+        const int n_pk = pack_record(r, has_ext ? &records[i + 1] : nullptr, pk);
+        if (k + n_pk > out_capacity) return RAFTGPU_ERR_FULL;
+        for (int j = 0; j < n_pk; j++) out[k++] = raftgpu_packed_rec{pk[j].w0, pk[j].w1};
+    }
+    *out_n = k;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_host_alloc(raftgpu_arena *a, uint64_t bytes, void **out_pinned) {
+    if (!a || !out_pinned) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    CK(a, cudaSetDevice(a->device));
+    LocalCpuGuard numa_guard(a->device);  // first touch on the GPU-local NUMA node
+    uint8_t *p = nullptr;
+    int32_t rc = pin_alloc(a, &p, bytes);
+    if (rc != RAFTGPU_OK) return rc;
+    a->host_allocs.push_back(p);
+    *out_pinned = p;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_host_free(raftgpu_arena *a, void *pinned) {
+    if (!a || !pinned) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    for (size_t i = 0; i < a->host_allocs.size(); i++)
+        if (a->host_allocs[i] == pinned) {
+            a->host_allocs.erase(a->host_allocs.begin() + i);
+            CK(a, cudaFreeHost(pinned));
+            return RAFTGPU_OK;
+        }
+    return RAFTGPU_ERR_INVALID;
+}
+
 int32_t raftgpu_step_wait(raftgpu_arena *a, raftgpu_step_result *out) {
     if (!a) return RAFTGPU_ERR_INVALID;
     if (a->n_inflight == 0) return fail(a, RAFTGPU_ERR_INVALID, "no step in flight");
@@ -1283,12 +1368,15 @@ int32_t raftgpu_step_wait(raftgpu_arena *a, raftgpu_step_result *out) {
     StagingSet &s = a->sets[cur];
     CK(a, cudaEventSynchronize(s.ev_done));
     s.in_flight = false;
-    s.result.n_advanced = *s.h_step_adv;
+    s.result.n_advanced = s.h_step_adv[0];
+    s.result.n_duplicates = s.h_step_adv[1];
     if (out) *out = s.result;
     a->last_done = cur;
     a->inflight[0] = a->inflight[1];
     a->inflight[1] = -1;
     a->n_inflight--;
+    if (s.result.n_duplicates)
+        return fail(a, RAFTGPU_ERR_INVALID, "zero-copy batch had more than one record for a (group, peer) cell");
     return RAFTGPU_OK;
 }
 

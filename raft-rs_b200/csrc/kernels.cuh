@@ -44,6 +44,12 @@ enum Counter : int {
     kCntCount
 };
 
+// Fire-and-forget L2 prefetch: costs no destination register, so it deepens the memory pipeline
+// beyond what registers x occupancy allow (the kernels here are long-scoreboard bound).
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
 
@@ -329,6 +335,23 @@ recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint_arg,
         const uint64_t g64 = static_cast<uint64_t>(base) + (static_cast<uint64_t>(tile) << 5) + lane;
         const bool active = g64 >= first && g64 < end;
         const uint32_t g = static_cast<uint32_t>(g64);
+        // pull this warp's NEXT tile into L2 while the current one is processed; each row of a tile
+        // is 256 contiguous bytes = two 128-byte lines, so lanes 0..1 cover it (slots by lane / 2)
+        if (tile + n_warps < n_tiles) {
+            const uint64_t gn = static_cast<uint64_t>(base) + (static_cast<uint64_t>(tile + n_warps) << 5);
+            const uint32_t row = lane >> 1, half = (lane & 1u) * 16u;
+            if (row < kSlots) {
+                if ((hint >> row) & 1u) prefetch_l2(c.matched + static_cast<size_t>(row) * c.cap + gn + half);
+            } else if (row == kSlots) {
+                prefetch_l2(c.committed + gn + half);
+            } else if (row == kSlots + 1) {
+                prefetch_l2(c.term_start + gn + half);
+            } else if (row == kSlots + 2) {
+                prefetch_l2(c.last_index + gn + half);
+            } else if (row == kSlots + 3 && half == 0) {
+                prefetch_l2(c.meta + gn);
+            }
+        }
         bool advanced = false;
         if (active) {
             // one batch of independent loads
@@ -541,14 +564,16 @@ __device__ __forceinline__ void reset_state(Cell &p, uint32_t state, uint64_t *p
 // one record, so threads never race on a cell and no atomics are needed on the
 // columns.
 //
-// The loop is software-pipelined three deep, because the work is two dependent
+// The loop is software-pipelined four deep, because the work is two dependent
 // HBM round trips (the record names the cell; the cell decides the update):
-//   iteration k issues   the record load of element k+2,
+//   iteration k issues   the record load of element k+3,
+//                        L2 prefetches (no destination registers) of the cell of
+//                        element k+2,
 //                        the cell loads (meta, matched, next_idx, pflags,
-//                        committed_index) of element k+1,
+//                        committed_index) of element k+1 -- by now L2 hits,
 //   and computes / stores element k,
-// so every load has a whole iteration to land and each thread keeps ~53 B in
-// flight all the time instead of alternating between the two phases.
+// so every access has at least a whole iteration to land and the DRAM latency of
+// the scattered cell accesses is paid by prefetches, not by register-holding loads.
 // Algorithmic bytes per record: 24 (record) + RMW of matched, next_idx,
 // committed_index (48) + flag byte and meta (~4) = 76.
 struct RecRegs {
@@ -638,6 +663,19 @@ __device__ __forceinline__ void load_reject_ext(const void *recs_v, uint64_t i, 
             if (kind == 2) request_snapshot = e.y;
         }
     }
+}
+
+// Stage 2 of the apply pipeline: pull the record's cell (and its group's meta word) into L2.
+__device__ __forceinline__ void prefetch_cell(const Columns &c, const RecRegs &r) {
+    const uint32_t g = static_cast<uint32_t>(r.w0);
+    const uint32_t slot = static_cast<uint32_t>(r.w0 >> 32) & 0xffu;
+    if (((r.w0 >> 40) & RAFTGPU_REC_EXT) || g >= c.cap || slot >= kSlots) return;
+    const size_t cell = static_cast<size_t>(slot) * c.cap + g;
+    prefetch_l2(c.matched + cell);
+    prefetch_l2(c.next_idx + cell);
+    prefetch_l2(c.peer_committed + cell);
+    prefetch_l2(c.pflags + cell);
+    prefetch_l2(c.meta + g);
 }
 
 __device__ __forceinline__ CellRegs load_cell(const Columns &c, const RecRegs &r) {
@@ -774,25 +812,49 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs
     return res;
 }
 
-template <bool kPacked>
-__global__ void __launch_bounds__(256)
+// kCheckDup (zero-copy submissions, where no host code has seen the records): every record marks
+// its cell in `touched` ([cap] bytes, one bit per peer slot, cleared by the caller beforehand)
+// with an L2 atomic; a cell marked twice breaks the one-wave precondition -- the record is NOT
+// applied and *dup_count is bumped so the step can fail loudly.
+template <bool kPacked, bool kCheckDup = false>
+__global__ void __launch_bounds__(256, 4)
 apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__restrict__ results,
-             unsigned long long *__restrict__ counters) {
+             unsigned long long *__restrict__ counters, uint32_t *__restrict__ touched = nullptr,
+             uint32_t *__restrict__ dup_count = nullptr) {
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t local[5] = {0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress
     uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     // prologue: fill the pipeline
     RecRegs rec_a = load_rec<kPacked>(recs, i, n);
     RecRegs rec_b = load_rec<kPacked>(recs, i + stride, n);
+    RecRegs rec_c = load_rec<kPacked>(recs, i + 2 * stride, n);
     CellRegs cell_a = load_cell(c, rec_a);
+    prefetch_cell(c, rec_b);
     for (; i < n; i += stride) {
-        const RecRegs rec_c = load_rec<kPacked>(recs, i + 2 * stride, n);  // element k+2: record
-        const CellRegs cell_b = load_cell(c, rec_b);              // element k+1: its cell
+        const RecRegs rec_d = load_rec<kPacked>(recs, i + 3 * stride, n);  // element k+3: record
+        prefetch_cell(c, rec_c);                                   // element k+2: cell -> L2
+        const CellRegs cell_b = load_cell(c, rec_b);               // element k+1: cell -> registers
+        if constexpr (kCheckDup) {
+            const uint32_t g = static_cast<uint32_t>(rec_a.w0), slot = static_cast<uint32_t>(rec_a.w0 >> 32) & 0xffu;
+            if (!((rec_a.w0 >> 40) & RAFTGPU_REC_EXT) && g < c.cap && slot < kSlots) {
+                const uint32_t bit = 1u << (8 * (g & 3u) + slot);
+                if (atomicOr(&touched[g >> 2], bit) & bit) {  // second record for this cell in one wave
+                    atomicAdd(dup_count, 1u);
+                    if (results) results[i] = 0;
+                    rec_a = rec_b;
+                    cell_a = cell_b;
+                    rec_b = rec_c;
+                    rec_c = rec_d;
+                    continue;
+                }
+            }
+        }
         const uint32_t res = apply_one<kPacked>(c, recs, n, i, rec_a, cell_a, local);  // element k
         if (results) results[i] = static_cast<uint8_t>(res);
         rec_a = rec_b;
         cell_a = cell_b;
         rec_b = rec_c;
+        rec_c = rec_d;
     }
     const int which[5] = {kCntRecords, kCntUpdates, kCntRejects, kCntDecrements, kCntNoProgress};
     block_flush_counts<5>(local, which, counters, nullptr);

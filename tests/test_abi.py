@@ -30,7 +30,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(B.Progress) == 56
     assert C.sizeof(B.GroupState) == 32
     assert C.sizeof(B.Counters) == 64
-    assert C.sizeof(B.StepResult) == 40
+    assert C.sizeof(B.StepResult) == 48
     assert B.APPEND_RESP_DTYPE.itemsize == 24
 
 

@@ -463,6 +463,54 @@ def test_enqueue_bulk_sorted_unsorted_and_order_check():
         arena.close()
 
 
+def test_zero_copy_packed_submission_and_duplicate_detection():
+    """raftgpu_step_begin_packed: the caller's pinned packed buffer goes to the GPU with no staging
+    copy; results equal the oracle; a batch that breaks the one-record-per-cell promise is
+    detected ON THE DEVICE and the step fails loudly."""
+    n = 100_000
+    synth = B.Synth(n, 0x5EED0002)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    bufs = [arena.host_alloc_packed(5 * n + 64) for _ in range(2)]
+    for rnd in range(4):
+        recs = synth.next_round().copy()
+        k = arena.pack_records(recs, bufs[rnd % 2])
+        assert len(recs) <= k <= len(recs) + np.count_nonzero(recs["flags"] & B.REC_REJECT)
+        arena.step_begin_packed(bufs[rnd % 2], k, B.STEP_READ_COMMITTED)
+        r = arena.step_wait()
+        O.arena_apply(ref, recs, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        assert r.n_advanced == want_adv and r.n_duplicates == 0 and r.h2d_bytes == 16 * k
+        bm, com = arena.step_results(n)
+        assert np.array_equal(bm, want_bm[: len(bm)])
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+        assert_columns_equal(arena.read_columns(n), ref, n, f"zero-copy round {rnd}")
+    # wide commits (commit > index, huge deltas) survive packing
+    wide = np.zeros(3, dtype=B.APPEND_RESP_DTYPE)
+    wide[0] = (5, 1, 0, 0, 10, 1 << 40)                 # commit far above index
+    wide[1] = (6, 2, 0, 0, (1 << 50) + 7, 3)            # delta does not fit 24 bits
+    wide[2] = (7, 0, B.REC_LOCAL, 0, 9, 4)              # LOCAL with commit < index
+    k = arena.pack_records(wide, bufs[0])
+    assert k == 6
+    arena.step_begin_packed(bufs[0], k, 0)
+    arena.step_wait()
+    O.arena_apply(ref, wide, mode=0)
+    O.arena_recompute(ref)
+    assert_columns_equal(arena.read_columns(n), ref, n, "wide commits")
+    # two records for one cell in one zero-copy batch: detected by the kernel
+    dup = np.zeros(2, dtype=B.APPEND_RESP_DTYPE)
+    dup[0] = (11, 1, 0, 0, int(ref.matched[1, 11]) + 5, 0)
+    dup[1] = (11, 1, 0, 0, int(ref.matched[1, 11]) + 9, 0)
+    k = arena.pack_records(dup, bufs[1])
+    arena.step_begin_packed(bufs[1], k, 0)
+    r = arena.step_wait(check=False)
+    assert r.status == B.ERR_INVALID and r.n_duplicates == 1
+    arena.close()
+
+
 def test_mci_and_properties_at_full_size():
     """1M x 7 joint: maximal_committed_index for every group vs the oracle, plus
     size-independent properties: idempotence, monotone commit, joint = min of halves."""

@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="pipelined e2e steps per timed chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scatter", action="store_true",
+                    help="device-resident leg uses the general two-kernel path (scatter apply + recompute) "
+                         "instead of the fused tile kernel for group-ordered batches")
     ap.add_argument("--public-records", action="store_true",
                     help="device-resident leg reads 24-byte public records instead of the packed 16-byte form")
     ap.add_argument("--profile", action="store_true",
@@ -219,7 +222,8 @@ def main():
     # Host memory is kept small and reused (one record buffer per generator): fresh host pages
     # are slow on these VMs; HBM holds all K+W rounds.
     per_arena = [(W + K + N_ARENAS - 1 - a) // N_ARENAS for a in range(N_ARENAS)]
-    arenas, round_len, d_recs = [], [], []
+    arenas, round_len, d_recs, d_offs = [], [], [], []
+    fused = not (args.scatter or args.public_records)
     pack_buf = np.empty((5 * n + 64, 2), dtype=np.uint64)
     for a in range(N_ARENAS):
         seed = SEED + 0x100 * a + 0x10000 * rank
@@ -227,7 +231,7 @@ def main():
         ar = B.Arena(n, device=local_rank, n_rings=1, ring_records=4096)
         assert ar.group_alloc_range(n) == 0
         ar.load_columns(s.initial)
-        ptrs, lens = [], []
+        ptrs, lens, offs = [], [], []
         for _ in range(per_arena[a]):
             recs = s.next_round()
             if args.public_records:       # the 24-byte public record layout in HBM
@@ -239,10 +243,16 @@ def main():
                 p = ar.device_alloc(16 * k)
                 ar.h2d(p, pack_buf[:k])
                 lens.append((k, len(recs)))
+                if fused:                 # the batch is in group order: its 256-group tile index
+                    off = B.tile_index(pack_buf, k, n)
+                    po = ar.device_alloc(off.nbytes)
+                    ar.h2d(po, off)
+                    offs.append(po)
             ptrs.append(p)
         arenas.append(ar)
         round_len.append(lens)
         d_recs.append(ptrs)
+        d_offs.append(offs)
         del s
     schedule = [(i % N_ARENAS, i // N_ARENAS) for i in range(W + K)]  # (arena, round) per step
 
@@ -253,6 +263,12 @@ def main():
         a, r = schedule[i]
         if ev:
             ev[0].record(stream)
+        if fused:   # ONE kernel: apply + recompute on shared-memory tiles (group-ordered batch)
+            arenas[a].step_sorted_device(d_recs[a][r], round_len[a][r][0], d_offs[a][r], stream=sh)
+            if ev:
+                ev[1].record(stream)
+                ev[2].record(stream)
+            return
         if args.public_records:
             arenas[a].apply_device(d_recs[a][r], round_len[a][r][0], stream=sh)
         else:
@@ -403,11 +419,15 @@ def main():
 
     if rank == 0:
         kernels = []
-        for name, ms, units, b_alg in (("apply_kernel", ms_apply, n_records, B_ALG_APPLY),
-                                       ("recompute_kernel", ms_recompute, n * K, B_ALG_RECOMPUTE)):
-            gbs = units * b_alg / (ms * 1e-3) / 1e9
+        if fused:
+            klist = (("step_tile_kernel", ms_apply, n_records * B_ALG_APPLY + n * K * B_ALG_RECOMPUTE),)
+        else:
+            klist = (("apply_kernel", ms_apply, n_records * B_ALG_APPLY),
+                     ("recompute_kernel", ms_recompute, n * K * B_ALG_RECOMPUTE))
+        for name, ms, alg_bytes in klist:
+            gbs = alg_bytes / (ms * 1e-3) / 1e9
             kernels.append({"kernel": name, "avg_us": 1e3 * ms / K, "share": ms / ms_total,
-                            "alg_bytes_per_launch": units * b_alg / K, "achieved": gbs,
+                            "alg_bytes_per_launch": alg_bytes / K, "achieved": gbs,
                             "frac": gbs / peak_gbs})
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -427,6 +447,8 @@ def main():
                 "groups_per_gpu": n, "peers": K_PEERS, "seed": hex(SEED),
                 "records_per_step": n_records / K,
                 "record_format": "24 B public" if args.public_records else "16 B packed (raftgpu_pack_records)",
+                "device_path": "fused tile kernel (raftgpu_step_sorted_device, group-ordered batch + tile index)"
+                               if fused else "scatter apply + recompute (raftgpu_apply_device[_packed] + raftgpu_recompute)",
                 "l2": f"inputs larger than L2: {N_ARENAS} arenas rotated, fresh records every step",
                 "parallelism": f"groups sharded over {world} GPU(s), no data-path collective",
             },
@@ -450,7 +472,7 @@ def main():
                 "h2d_bytes_per_step": zc["h2d"], "d2h_bytes_per_step": zc["d2h"],
                 "api": "raftgpu_step_begin_packed (caller-built packed records in raftgpu_host_alloc "
                        "memory, no staging copy, device-side one-wave check) + raftgpu_step_wait"},
-            "gpu_launches": 2 * K,
+            "gpu_launches": (1 if fused else 2) * K,
             "clocks": clocks,
             "counters": {"recomputes": sums["recomputes"], "advanced": sums["advanced"], "records": sums["records"]},
         }

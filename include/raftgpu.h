@@ -137,6 +137,11 @@ typedef struct {
 #define RAFTGPU_REC_LOCAL 0x02u
 #define RAFTGPU_REC_EXT 0x80u    /* extension record of the preceding REJECT */
 
+/* The packed 16-byte wire form of a record (raftgpu_pack_records); layout in DESIGN.md 2. */
+typedef struct {
+    uint64_t w0, w1;
+} raftgpu_packed_rec;
+
 /* per-record result byte */
 #define RAFTGPU_RES_OK 0x01u          /* maybe_update / maybe_decr_to returned true */
 #define RAFTGPU_RES_OLD_PAUSED 0x02u  /* pr.is_paused() before maybe_update, raft.rs:1724 */
@@ -337,6 +342,22 @@ int32_t raftgpu_apply_device(raftgpu_arena *arena, void *stream,
 int32_t raftgpu_apply_device_packed(raftgpu_arena *arena, void *stream, const void *d_packed_records,
                                     uint64_t n_packed, uint8_t *d_results);
 
+/* The FUSED step for batches in group order: apply + recompute in one kernel whose HBM traffic is
+ * all dense bulk transfers.  d_packed_records are packed records in
+ * non-decreasing group order (EXT payloads directly behind their record); d_tile_off[t] is the
+ * index of the first record whose group is >= t * RAFTGPU_TILE_GROUPS, for t = 0..n_tiles
+ * (raftgpu_tile_index builds and validates it on the host).  One wave per call, like
+ * raftgpu_apply_device; processes all allocated groups [0, hi).  A record found outside its tile
+ * is not applied and reported as RAFTGPU_RES_NO_PROGRESS.  Asynchronous on `stream`. */
+#define RAFTGPU_TILE_GROUPS 256
+int32_t raftgpu_step_sorted_device(raftgpu_arena *arena, void *stream, const void *d_packed_records,
+                                   uint64_t n_packed, const uint32_t *d_tile_off, uint8_t *d_results,
+                                   uint32_t *d_adv_bitmap, uint64_t *d_commit_out);
+/* Host helper: out[t] for t = 0..n_tiles where n_tiles = ceil(n_groups / RAFTGPU_TILE_GROUPS)
+ * (out has n_tiles + 1 entries).  RAFTGPU_ERR_INVALID if the records are not in group order. */
+int32_t raftgpu_tile_index(const raftgpu_packed_rec *packed, uint64_t n_packed, uint32_t n_groups,
+                           uint32_t *out, uint64_t out_capacity);
+
 /* Stage host records for the next step (RawNode::step -> Raft::step ->
  * handle_append_response, raw_node.rs:402-411 / raft.rs:1559).  Records for one
  * (group, peer) keep their arrival order: a second record for a cell that
@@ -366,9 +387,6 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *arena, const raftgpu_append_resp *re
  * without reading the batch, so the GPU checks it: a duplicate is not applied, counted in
  * raftgpu_step_result.n_duplicates, and raftgpu_step_wait returns RAFTGPU_ERR_INVALID.
  * The buffer must stay untouched until that step's raftgpu_step_wait returns. */
-typedef struct {
-    uint64_t w0, w1;
-} raftgpu_packed_rec;
 int32_t raftgpu_host_alloc(raftgpu_arena *arena, uint64_t bytes, void **out_pinned);
 int32_t raftgpu_host_free(raftgpu_arena *arena, void *pinned);
 int32_t raftgpu_pack_records(const raftgpu_append_resp *records, uint64_t n, raftgpu_packed_rec *out,

@@ -160,6 +160,8 @@ def lib() -> C.CDLL:
             "raftgpu_recompute": ([vp, vp, u32, u32, vp, vp, vp, vp], i32),
             "raftgpu_apply_device": ([vp, vp, vp, u64, vp], i32),
             "raftgpu_apply_device_packed": ([vp, vp, vp, u64, vp], i32),
+            "raftgpu_step_sorted_device": ([vp, vp, vp, u64, vp, vp, vp, vp], i32),
+            "raftgpu_tile_index": ([vp, u64, u32, vp, u64], i32),
             "raftgpu_enqueue_append_resp": ([vp, u32, vp, u64], i32),
             "raftgpu_enqueue_bulk": ([vp, vp, u64, u32], i32),
             "raftgpu_step_begin": ([vp, u32], i32),
@@ -195,6 +197,19 @@ def lib() -> C.CDLL:
 
 def strerror(status: int) -> str:
     return lib().raftgpu_strerror(status).decode()
+
+
+TILE_GROUPS = 256
+
+
+def tile_index(packed: np.ndarray, n_packed: int, n_groups: int) -> np.ndarray:
+    """raftgpu_tile_index: first packed record of every 256-group tile (+ the end)."""
+    n_tiles = (n_groups + TILE_GROUPS - 1) // TILE_GROUPS
+    out = np.zeros(n_tiles + 1, dtype=np.uint32)
+    rc = lib().raftgpu_tile_index(packed.ctypes.data, n_packed, n_groups, out.ctypes.data, len(out))
+    if rc != OK:
+        raise RaftGpuError(rc, "raftgpu_tile_index")
+    return out
 
 
 # --------------------------------------------------------------------------- host columns
@@ -468,6 +483,11 @@ class Arena:
     def apply_device_packed(self, d_packed, n_packed, stream=None, d_results=None):
         self._ck(self._L.raftgpu_apply_device_packed(self._h, stream, d_packed, n_packed, d_results),
                  "apply_device_packed")
+
+    def step_sorted_device(self, d_packed, n_packed, d_tile_off, stream=None, d_results=None, d_adv=None,
+                           d_commit=None):
+        self._ck(self._L.raftgpu_step_sorted_device(self._h, stream, d_packed, n_packed, d_tile_off, d_results,
+                                                    d_adv, d_commit), "step_sorted_device")
 
     def enqueue(self, recs: np.ndarray, ring: int = 0):
         assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous

@@ -161,8 +161,10 @@ struct raftgpu_arena {
     int grid_recompute = 0, grid_recompute5 = 0, grid_apply = 0;  // persistent grid sizes (blocks)
     uint32_t n_simple5 = 0;                  // groups whose meta is the plain 5-voter configuration
     bool force_general = false;              // RAFTGPU_FORCE_GENERAL=1: never take the simple5 kernels
+    bool prefetch = false;                   // RAFTGPU_PREFETCH=1: kernels with the L2 prefetch stage
     bool use_tma = false;                    // RAFTGPU_TMA=1 selects the TMA-fed recompute kernel
     uint32_t tma_smem = 0;                   // dynamic shared memory for the TMA stage ring
+    uint32_t tile_smem = 0;                  // dynamic shared memory for the fused tile kernel
     int tma_stages_cap = 0;                  // RAFTGPU_TMA_STAGES (tuning knob)
     Columns cols{};
     unsigned long long *d_counters = nullptr;
@@ -341,7 +343,11 @@ int32_t launch_recompute(raftgpu_arena *a, cudaStream_t st, uint32_t first, uint
     }
     const uint32_t base = first & ~31u;
     const uint64_t threads = static_cast<uint64_t>(first - base) + n;
-    if (simple5) {
+    if (simple5 && a->prefetch) {
+        const uint32_t blocks = std::min<uint32_t>(div_up(threads, 256), static_cast<uint32_t>(a->grid_recompute5));
+        recompute_kernel<true, true><<<blocks, 256, 0, st>>>(a->cols, first, n, hint, d_adv, d_commit, d_mci, d_gc,
+                                                            d_step_adv, a->d_counters);
+    } else if (simple5) {
         const uint32_t blocks = std::min<uint32_t>(div_up(threads, 256), static_cast<uint32_t>(a->grid_recompute5));
         recompute_kernel<true><<<blocks, 256, 0, st>>>(a->cols, first, n, hint, d_adv, d_commit, d_mci, d_gc,
                                                       d_step_adv, a->d_counters);
@@ -358,8 +364,12 @@ int32_t launch_apply(raftgpu_arena *a, cudaStream_t st, const void *d_recs, uint
                      bool packed) {
     if (n == 0) return RAFTGPU_OK;
     const uint32_t blocks = std::min<uint32_t>(div_up(n, 256), static_cast<uint32_t>(a->grid_apply));
-    if (packed)
+    if (packed && a->prefetch)
+        apply_kernel<true, false, true><<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
+    else if (packed)
         apply_kernel<true><<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
+    else if (a->prefetch)
+        apply_kernel<false, false, true><<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
     else
         apply_kernel<false><<<blocks, 256, 0, st>>>(a->cols, d_recs, n, d_results, a->d_counters);
     CKL(a);
@@ -474,11 +484,25 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
                               static_cast<int>(a->tma_smem)));
     TRYC(cudaFuncSetAttribute(recompute_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               static_cast<int>(a->tma_smem)));
+    a->tile_smem = 226u * 1024u;
+#define RAFTGPU_TILE_ATTR(CT, NG)                                                                             \
+    TRYC(cudaFuncSetAttribute(step_tile_kernel<false, CT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                              static_cast<int>(a->tile_smem)));                                              \
+    TRYC(cudaFuncSetAttribute(step_tile_kernel<true, CT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                              static_cast<int>(a->tile_smem)))
+    RAFTGPU_TILE_ATTR(256, 1);
+    RAFTGPU_TILE_ATTR(256, 2);
+    RAFTGPU_TILE_ATTR(256, 3);
+    RAFTGPU_TILE_ATTR(512, 1);
+    RAFTGPU_TILE_ATTR(512, 2);
+#undef RAFTGPU_TILE_ATTR
     {
         const char *e = getenv("RAFTGPU_TMA");
         a->use_tma = e && e[0] == '1';
         const char *f = getenv("RAFTGPU_FORCE_GENERAL");
         a->force_general = f && f[0] == '1';
+        const char *pf = getenv("RAFTGPU_PREFETCH");
+        a->prefetch = pf && pf[0] == '1';
         const char *t = getenv("RAFTGPU_TMA_STAGES");
         if (t) a->tma_stages_cap = atoi(t);
     }
@@ -988,6 +1012,77 @@ int32_t raftgpu_apply_device(raftgpu_arena *a, void *stream, const raftgpu_appen
     if (!a || (!d_records && n)) return RAFTGPU_ERR_INVALID;
     CK(a, cudaSetDevice(a->device));
     return launch_apply(a, pick_stream(a, stream), d_records, n, d_results, /*packed=*/false);
+}
+
+int32_t raftgpu_step_sorted_device(raftgpu_arena *a, void *stream, const void *d_packed_records, uint64_t n_packed,
+                                   const uint32_t *d_tile_off, uint8_t *d_results, uint32_t *d_adv_bitmap,
+                                   uint64_t *d_commit_out) {
+    if (!a || !d_tile_off || (!d_packed_records && n_packed)) return RAFTGPU_ERR_INVALID;
+    CK(a, cudaSetDevice(a->device));
+    const uint32_t hi = a->hi;
+    if (hi == 0) return RAFTGPU_OK;
+    const bool simple5 = range_simple5(a, 0, hi) && !a->force_general;
+    const uint32_t hint = simple5 ? 0x1fu : (a->voter_hint & 0xffu);
+    const uint32_t H = static_cast<uint32_t>(__builtin_popcount(hint));
+    // variant knobs (tuning): RAFTGPU_TILE_VARIANT = <threads per consumer group><groups>, e.g. 2562, 5122, 2563
+    static const int variant = getenv("RAFTGPU_TILE_VARIANT") ? atoi(getenv("RAFTGPU_TILE_VARIANT")) : 2562;
+    static const int cap_env = getenv("RAFTGPU_TILE_RECCAP") ? atoi(getenv("RAFTGPU_TILE_RECCAP")) : 1536;
+    const uint32_t rec_cap = static_cast<uint32_t>(cap_env) & ~3u;
+    const uint32_t stage_bytes = tile_stage_bytes(H, rec_cap);
+    int stages = std::min<int>(kFMaxStages, static_cast<int>(a->tile_smem / stage_bytes));
+    if (stages < 2 || H == 0) return fail(a, RAFTGPU_ERR_INVALID, "configuration too wide for the fused tile kernel");
+    TileArgs t{};
+    t.recs = static_cast<const PackedRec *>(d_packed_records);
+    t.tile_off = d_tile_off;
+    t.n_groups = hi;
+    t.hint = hint;
+    t.n_stages = stages;
+    t.rec_cap = rec_cap;
+    t.results = d_results;
+    t.adv_bitmap = d_adv_bitmap;
+    t.commit_out = d_commit_out;
+    t.step_advanced = nullptr;
+    t.counters = a->d_counters;
+    const uint32_t n_tiles = div_up(hi, kFTile);
+    const uint32_t blocks = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(a->sm_count));
+    const size_t smem = static_cast<size_t>(stages) * stage_bytes;
+    cudaStream_t st = pick_stream(a, stream);
+#define RAFTGPU_LAUNCH_TILE(CT, NG)                                                        \
+    do {                                                                                   \
+        if (simple5)                                                                       \
+            step_tile_kernel<true, CT, NG><<<blocks, CT * NG + 32, smem, st>>>(a->cols, t); \
+        else                                                                               \
+            step_tile_kernel<false, CT, NG><<<blocks, CT * NG + 32, smem, st>>>(a->cols, t); \
+    } while (0)
+    switch (variant) {
+    case 2561: RAFTGPU_LAUNCH_TILE(256, 1); break;
+    case 2563: RAFTGPU_LAUNCH_TILE(256, 3); break;
+    case 5121: RAFTGPU_LAUNCH_TILE(512, 1); break;
+    case 5122: RAFTGPU_LAUNCH_TILE(512, 2); break;
+    default: RAFTGPU_LAUNCH_TILE(256, 2); break;
+    }
+#undef RAFTGPU_LAUNCH_TILE
+    CKL(a);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_tile_index(const raftgpu_packed_rec *packed, uint64_t n_packed, uint32_t n_groups, uint32_t *out,
+                           uint64_t out_capacity) {
+    if ((!packed && n_packed) || !out) return RAFTGPU_ERR_INVALID;
+    const uint32_t n_tiles = div_up(n_groups, kFTile);
+    if (out_capacity < static_cast<uint64_t>(n_tiles) + 1 || n_packed > UINT32_MAX) return RAFTGPU_ERR_INVALID;
+    uint32_t t = 0;  // next tile whose start is still unknown
+    uint32_t prev_group = 0;
+    for (uint64_t i = 0; i < n_packed; i++) {
+        if (packed[i].w0 & kPkExt) continue;  // payloads / padding ride behind their record
+        const uint32_t g = static_cast<uint32_t>(packed[i].w0);
+        if (g < prev_group) return RAFTGPU_ERR_INVALID;  // not in group order
+        prev_group = g;
+        const uint32_t tile = g / kFTile;
+        while (t <= tile && t <= n_tiles) out[t++] = static_cast<uint32_t>(i);
+    }
+    while (t <= n_tiles) out[t++] = static_cast<uint32_t>(n_packed);
+    return RAFTGPU_OK;
 }
 
 int32_t raftgpu_apply_device_packed(raftgpu_arena *a, void *stream, const void *d_packed_records, uint64_t n,

@@ -316,7 +316,7 @@ __device__ __forceinline__ void publish_tile(uint32_t *adv_bitmap, uint64_t g64,
 }
 
 // ---- LDG feed: persistent grid, each warp walks 32-group tiles with a grid stride.
-template <bool kSimple5>
+template <bool kSimple5, bool kPrefetch = false>
 __global__ void __launch_bounds__(256, kSimple5 ? 6 : 4)
 recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint_arg,
                  uint32_t *__restrict__ adv_bitmap, uint64_t *__restrict__ commit_out,
@@ -337,7 +337,7 @@ recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint_arg,
         const uint32_t g = static_cast<uint32_t>(g64);
         // pull this warp's NEXT tile into L2 while the current one is processed; each row of a tile
         // is 256 contiguous bytes = two 128-byte lines, so lanes 0..1 cover it (slots by lane / 2)
-        if (tile + n_warps < n_tiles) {
+        if (kPrefetch && tile + n_warps < n_tiles) {
             const uint64_t gn = static_cast<uint64_t>(base) + (static_cast<uint64_t>(tile + n_warps) << 5);
             const uint32_t row = lane >> 1, half = (lane & 1u) * 16u;
             if (row < kSlots) {
@@ -564,16 +564,15 @@ __device__ __forceinline__ void reset_state(Cell &p, uint32_t state, uint64_t *p
 // one record, so threads never race on a cell and no atomics are needed on the
 // columns.
 //
-// The loop is software-pipelined four deep, because the work is two dependent
+// The loop is software-pipelined three deep, because the work is two dependent
 // HBM round trips (the record names the cell; the cell decides the update):
-//   iteration k issues   the record load of element k+3,
-//                        L2 prefetches (no destination registers) of the cell of
-//                        element k+2,
+//   iteration k issues   the record load of element k+2,
 //                        the cell loads (meta, matched, next_idx, pflags,
-//                        committed_index) of element k+1 -- by now L2 hits,
+//                        committed_index) of element k+1,
 //   and computes / stores element k,
-// so every access has at least a whole iteration to land and the DRAM latency of
-// the scattered cell accesses is paid by prefetches, not by register-holding loads.
+// so every load has a whole iteration to land.  (An extra L2-prefetch stage, kPrefetch, was
+// measured and does not help: at ~12 MB in flight the kernel is limited by the DRAM
+// efficiency of sector-granular scattered accesses, not by latency -- profiles/.)
 // Algorithmic bytes per record: 24 (record) + RMW of matched, next_idx,
 // committed_index (48) + flag byte and meta (~4) = 76.
 struct RecRegs {
@@ -583,6 +582,12 @@ struct CellRegs {
     uint32_t meta;
     uint32_t flags;
     uint64_t matched, next_idx, peer_committed;
+};
+// Where one cell's hot fields live: HBM (scatter kernel) or a shared-memory tile (fused kernel).
+// The cold columns (pending_snapshot, pending_request_snapshot) are always addressed in HBM.
+struct CellPtrs {
+    uint64_t *matched, *next_idx, *peer_committed, *last_index;
+    uint8_t *pflags;
 };
 
 // Packed staging record, 16 bytes: what raftgpu_enqueue_* writes into the pinned rings and the
@@ -665,6 +670,15 @@ __device__ __forceinline__ void load_reject_ext(const void *recs_v, uint64_t i, 
     }
 }
 
+__device__ __forceinline__ CellPtrs global_cell_ptrs(const Columns &c, const RecRegs &r) {
+    const uint32_t g = static_cast<uint32_t>(r.w0);
+    const uint32_t slot = static_cast<uint32_t>(r.w0 >> 32) & 0xffu;
+    const bool ok = g < c.cap && slot < kSlots;
+    const size_t cell = ok ? static_cast<size_t>(slot) * c.cap + g : 0;
+    return CellPtrs{c.matched + cell, c.next_idx + cell, c.peer_committed + cell, c.last_index + (ok ? g : 0),
+                    c.pflags + cell};
+}
+
 // Stage 2 of the apply pipeline: pull the record's cell (and its group's meta word) into L2.
 __device__ __forceinline__ void prefetch_cell(const Columns &c, const RecRegs &r) {
     const uint32_t g = static_cast<uint32_t>(r.w0);
@@ -697,7 +711,8 @@ __device__ __forceinline__ CellRegs load_cell(const Columns &c, const RecRegs &r
 // One record against its cell: raft.rs:1663-1743.  Returns the result byte.
 template <bool kPacked>
 __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs, uint64_t n, uint64_t i,
-                                              const RecRegs &rec, const CellRegs &cd, uint32_t (&local)[5]) {
+                                              const RecRegs &rec, const CellRegs &cd, const CellPtrs &ptr,
+                                              uint32_t *local) {
     const uint64_t index = rec.index, commit = rec.commit;
     const uint32_t g = static_cast<uint32_t>(rec.w0);
     const uint32_t slot = static_cast<uint32_t>(rec.w0 >> 32) & 0xffu;
@@ -722,7 +737,7 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs
 
     if (rflags & RAFTGPU_REC_LOCAL) {
         // raft.rs:974-991 append_entry: last_index grew
-        if (commit != 0) c.last_index[g] = commit;
+        if (commit != 0) *ptr.last_index = commit;
         // raft.rs:1010-1014 on_persist_entries: prs[self].maybe_update(index)
         if (pr.matched < index) {  // progress.rs:138-150
             pr.matched = index;
@@ -734,7 +749,7 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs
     } else {
         pr.flags |= RAFTGPU_PF_RECENT_ACTIVE;  // raft.rs:1674
         // raft.rs:1677 pr.update_committed(m.commit), progress.rs:153-157
-        if (commit > cd.peer_committed) c.peer_committed[cell] = commit;
+        if (commit > cd.peer_committed) *ptr.peer_committed = commit;
 
         if (rflags & RAFTGPU_REC_REJECT) {
             local[2]++;
@@ -806,9 +821,9 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs
             }
         }
     }
-    if (pr.matched != cd.matched) c.matched[cell] = pr.matched;
-    if (pr.next_idx != cd.next_idx) c.next_idx[cell] = pr.next_idx;
-    if (pr.flags != cd.flags) c.pflags[cell] = static_cast<uint8_t>(pr.flags);
+    if (pr.matched != cd.matched) *ptr.matched = pr.matched;
+    if (pr.next_idx != cd.next_idx) *ptr.next_idx = pr.next_idx;
+    if (pr.flags != cd.flags) *ptr.pflags = static_cast<uint8_t>(pr.flags);
     return res;
 }
 
@@ -816,7 +831,7 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs
 // its cell in `touched` ([cap] bytes, one bit per peer slot, cleared by the caller beforehand)
 // with an L2 atomic; a cell marked twice breaks the one-wave precondition -- the record is NOT
 // applied and *dup_count is bumped so the step can fail loudly.
-template <bool kPacked, bool kCheckDup = false>
+template <bool kPacked, bool kCheckDup = false, bool kPrefetch = false>
 __global__ void __launch_bounds__(256, 4)
 apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__restrict__ results,
              unsigned long long *__restrict__ counters, uint32_t *__restrict__ touched = nullptr,
@@ -827,12 +842,10 @@ apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__re
     // prologue: fill the pipeline
     RecRegs rec_a = load_rec<kPacked>(recs, i, n);
     RecRegs rec_b = load_rec<kPacked>(recs, i + stride, n);
-    RecRegs rec_c = load_rec<kPacked>(recs, i + 2 * stride, n);
     CellRegs cell_a = load_cell(c, rec_a);
-    prefetch_cell(c, rec_b);
     for (; i < n; i += stride) {
-        const RecRegs rec_d = load_rec<kPacked>(recs, i + 3 * stride, n);  // element k+3: record
-        prefetch_cell(c, rec_c);                                   // element k+2: cell -> L2
+        const RecRegs rec_c = load_rec<kPacked>(recs, i + 2 * stride, n);  // element k+2: record
+        if (kPrefetch) prefetch_cell(c, rec_c);                    // (optional) its cell -> L2
         const CellRegs cell_b = load_cell(c, rec_b);               // element k+1: cell -> registers
         if constexpr (kCheckDup) {
             const uint32_t g = static_cast<uint32_t>(rec_a.w0), slot = static_cast<uint32_t>(rec_a.w0 >> 32) & 0xffu;
@@ -844,20 +857,339 @@ apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__re
                     rec_a = rec_b;
                     cell_a = cell_b;
                     rec_b = rec_c;
-                    rec_c = rec_d;
                     continue;
                 }
             }
         }
-        const uint32_t res = apply_one<kPacked>(c, recs, n, i, rec_a, cell_a, local);  // element k
+        const CellPtrs gp = global_cell_ptrs(c, rec_a);
+        const uint32_t res = apply_one<kPacked>(c, recs, n, i, rec_a, cell_a, gp, local);  // element k
         if (results) results[i] = static_cast<uint8_t>(res);
         rec_a = rec_b;
         cell_a = cell_b;
         rec_b = rec_c;
-        rec_c = rec_d;
     }
     const int which[5] = {kCntRecords, kCntUpdates, kCntRejects, kCntDecrements, kCntNoProgress};
     block_flush_counts<5>(local, which, counters, nullptr);
+}
+
+// ---------------------------------------------------------------------------
+// step_tile_kernel: apply + recompute FUSED, for batches whose records are in group order.
+//
+// The scatter apply kernel above moves ~12 MB in flight but tops out near 3.7 TB/s: its cell
+// accesses are sector-granular (8 useful bytes per 32-byte sector request, several rows per
+// record), which HBM serves at roughly half the efficiency of dense bursts.  When the batch is
+// ordered by group, a tile of kFTile consecutive groups owns a CONTIGUOUS record range, so the
+// whole step becomes dense traffic: per tile the producer warp bulk-loads (TMA, cp.async.bulk)
+// the tile's rows of matched / next_idx / committed_index / pflags / meta / committed /
+// term_start / last_index and its record range into one shared-memory stage; the consumers
+//   A. apply every record of the tile to the shared-memory rows (one thread per record;
+//      distinct cells per wave, so no conflicts),
+//   B. recompute the commit index of the tile's groups from the same shared-memory rows
+//      (matched is read from HBM once per step instead of twice),
+//   C. bulk-store the rows back (cp.async.bulk.global.shared::cta).
+// Peer slots outside `hint` (learners) and the cold columns are handled through HBM directly.
+// tile_off[t] = index of the first packed record of tile t (raftgpu_tile_index builds it).
+constexpr int kFTile = 256;                  // groups per tile
+// consumer groups: tile i of a CTA is handled by group i % kNG, so the phases of kNG tiles overlap
+// inside one CTA; each group has kCT threads (kCT >= kFTile).  Template parameters of the kernel.
+constexpr int kFMaxStages = 4;
+// Row strides inside a stage.  Records arrive in group order, so the ~3.5 records of one group sit
+// in neighbouring lanes and touch the SAME column index of DIFFERENT rows: with a 256-element row
+// stride they would all fall on the same shared-memory banks (4-way conflicts on every access).
+// 258 u64 (= 2064 B, still 16-byte aligned for TMA) shifts consecutive rows by 4 banks.
+constexpr uint32_t kFRow64 = (kFTile + 2) * 8;   // bytes per u64 row
+constexpr uint32_t kFRow8 = kFTile + 16;         // bytes per u8 (pflags) row
+
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+// 1-D TMA store: shared -> global, tracked by the per-thread bulk async-group
+__device__ __forceinline__ void tma_store_1d(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+struct TileArgs {
+    const PackedRec *recs;     // packed records in group order
+    const uint32_t *tile_off;  // [n_tiles + 1]
+    uint32_t n_groups;         // groups [0, n_groups)
+    uint32_t hint;
+    int n_stages;
+    uint32_t rec_cap;          // packed records staged per tile (multiple of 4); the rest is read from HBM
+    uint8_t *results;          // nullable, one byte per packed record
+    uint32_t *adv_bitmap;      // nullable
+    uint64_t *commit_out;      // nullable
+    uint32_t *step_advanced;   // nullable
+    unsigned long long *counters;
+};
+
+// bytes of one stage for H hinted slots (shared by host and device)
+__host__ __device__ constexpr uint32_t tile_stage_bytes(uint32_t H, uint32_t rec_cap) {
+    return 3u * H * kFRow64 + 3u * kFRow64 + kFTile * 4u + H * kFRow8 + rec_cap * 16u;
+}
+
+template <bool kSimple5, int kCT, int kNG>
+__global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, TileArgs a) {
+    static_assert(kCT >= kFTile && kCT % 32 == 0, "a consumer group covers a tile");
+    const uint32_t kFRecCap = a.rec_cap;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[kFMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];
+
+    const uint32_t hint = kSimple5 ? 0x1fu : (a.hint & 0xffu);
+    const uint32_t H = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint));
+    // stage layout (bytes)
+    const uint32_t o_matched = 0, o_next = H * kFRow64, o_pc = 2u * H * kFRow64, o_committed = 3u * H * kFRow64,
+                   o_ts = o_committed + kFRow64, o_li = o_ts + kFRow64, o_meta = o_li + kFRow64,
+                   o_flags = o_meta + kFTile * 4u, o_recs = o_flags + H * kFRow8, stage_bytes = tile_stage_bytes(H, a.rec_cap);
+    const uint32_t n_tiles = (a.n_groups + kFTile - 1) / kFTile;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.n_stages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t local[7] = {0, 0, 0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress | recomputes, advanced
+    if (warp == kNG * kCT / 32) {
+        // ===================== producer warp =====================
+        const uint32_t n_copies = 4u * H + 5u;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int st = it % a.n_stages;
+            const uint32_t ph = (it / a.n_stages) & 1u;
+            const uint32_t g0 = tile * kFTile;
+            const uint32_t ng = a.n_groups - g0 < kFTile ? a.n_groups - g0 : kFTile;
+            const uint32_t ng16 = (ng + 15u) & ~15u;  // 16-byte multiples for every row; inside the padded stride
+            const uint32_t rbeg = a.tile_off[tile], rend = a.tile_off[tile + 1];
+            const uint32_t staged = rend - rbeg < kFRecCap ? rend - rbeg : kFRecCap;
+            if (lane == 0) {
+                mbar_wait(&empty_bar[st], ph ^ 1u);
+                mbar_expect_tx(&full_bar[st], 3u * H * ng16 * 8u + H * ng16 + 3u * ng16 * 8u + ng16 * 4u + staged * 16u);
+            }
+            __syncwarp();
+            uint8_t *sb = smem + static_cast<size_t>(st) * stage_bytes;
+            for (uint32_t j = lane; j < n_copies; j += 32) {
+                if (j < 4u * H) {
+                    const uint32_t col = j / H, r = j % H;  // col: 0 matched, 1 next_idx, 2 committed_index, 3 pflags
+                    uint32_t slot = 0, seen = 0;
+                    for (uint32_t s2 = 0; s2 < kSlots; s2++)
+                        if ((hint >> s2) & 1u) {
+                            if (seen == r) slot = s2;
+                            seen++;
+                        }
+                    const size_t cell = static_cast<size_t>(slot) * c.cap + g0;
+                    if (col == 0) tma_load_1d(sb + o_matched + r * kFRow64, c.matched + cell, ng16 * 8u, &full_bar[st]);
+                    if (col == 1) tma_load_1d(sb + o_next + r * kFRow64, c.next_idx + cell, ng16 * 8u, &full_bar[st]);
+                    if (col == 2) tma_load_1d(sb + o_pc + r * kFRow64, c.peer_committed + cell, ng16 * 8u, &full_bar[st]);
+                    if (col == 3) tma_load_1d(sb + o_flags + r * kFRow8, c.pflags + cell, ng16, &full_bar[st]);
+                } else if (j == 4u * H) {
+                    tma_load_1d(sb + o_committed, c.committed + g0, ng16 * 8u, &full_bar[st]);
+                } else if (j == 4u * H + 1) {
+                    tma_load_1d(sb + o_ts, c.term_start + g0, ng16 * 8u, &full_bar[st]);
+                } else if (j == 4u * H + 2) {
+                    tma_load_1d(sb + o_li, c.last_index + g0, ng16 * 8u, &full_bar[st]);
+                } else if (j == 4u * H + 3) {
+                    tma_load_1d(sb + o_meta, c.meta + g0, ng16 * 4u, &full_bar[st]);
+                } else if (staged) {
+                    tma_load_1d(sb + o_recs, a.recs + rbeg, staged * 16u, &full_bar[st]);
+                }
+            }
+        }
+    } else {
+        // ===================== consumers: group cg takes every kFGroups-th tile of this CTA =====================
+        const uint32_t cg = warp / (kCT / 32);
+        const uint32_t tid = threadIdx.x - cg * kCT;
+        const int bar_id = 1 + static_cast<int>(cg);
+        constexpr uint32_t R64 = kFRow64 / 8;  // row stride in u64 elements
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            if (it % kNG != cg) continue;
+            const int st = it % a.n_stages;
+            const uint32_t ph = (it / a.n_stages) & 1u;
+            const uint32_t g0 = tile * kFTile;
+            const uint32_t ng = a.n_groups - g0 < kFTile ? a.n_groups - g0 : kFTile;
+            const uint32_t ng16 = (ng + 15u) & ~15u;
+            const uint32_t rbeg = a.tile_off[tile], rend = a.tile_off[tile + 1];
+            const uint32_t cnt = rend - rbeg, staged = cnt < kFRecCap ? cnt : kFRecCap;
+            uint8_t *sb = smem + static_cast<size_t>(st) * stage_bytes;
+            uint64_t *s_matched = reinterpret_cast<uint64_t *>(sb + o_matched);
+            uint64_t *s_next = reinterpret_cast<uint64_t *>(sb + o_next);
+            uint64_t *s_pc = reinterpret_cast<uint64_t *>(sb + o_pc);
+            uint64_t *s_committed = reinterpret_cast<uint64_t *>(sb + o_committed);
+            uint64_t *s_ts = reinterpret_cast<uint64_t *>(sb + o_ts);
+            uint64_t *s_li = reinterpret_cast<uint64_t *>(sb + o_li);
+            uint32_t *s_meta = reinterpret_cast<uint32_t *>(sb + o_meta);
+            uint8_t *s_flags = sb + o_flags;
+            const PackedRec *s_recs = reinterpret_cast<const PackedRec *>(sb + o_recs);
+            mbar_wait(&full_bar[st], ph);
+
+            // ---- A: the tile's records against the shared-memory rows (raft.rs:1663-1743)
+            for (uint32_t k = tid; k < cnt; k += kCT) {
+                // Fast path: the common records -- an accepted AppendResponse or a leader-local
+                // record for a peer in Replicate state whose cell is staged -- straight on the packed
+                // words and the shared-memory cell; same statements as apply_one's accept / LOCAL
+                // branches (raft.rs:1674-1677, 1724-1727, 1010-1014; progress.rs:138-157).
+                if (k + 4u <= staged) {
+                    const ulonglong2 q = reinterpret_cast<const ulonglong2 *>(s_recs)[k];
+                    const uint64_t w0 = q.x;
+                    if (w0 & kPkExt) {
+                        if (a.results) a.results[rbeg + k] = 0;
+                        continue;
+                    }
+                    const uint32_t slot = static_cast<uint32_t>(w0 >> 32) & 7u;
+                    const uint32_t gl = static_cast<uint32_t>(w0) - g0;
+                    if (!(w0 & (kPkReject | kPkWide)) && gl < ng && ((hint >> slot) & 1u)) {
+                        const uint32_t r = __popc(hint & ((1u << slot) - 1u));
+                        const uint32_t ci = r * R64 + gl;
+                        const uint32_t f0 = s_flags[r * kFRow8 + gl];
+                        const bool present = kSimple5 || (((RAFTGPU_META_IN(s_meta[gl]) | RAFTGPU_META_OUT(s_meta[gl]) |
+                                                            RAFTGPU_META_LEARN(s_meta[gl])) >> slot) & 1u);
+                        if (present && (f0 & RAFTGPU_PF_STATE_MASK) == RAFTGPU_STATE_REPLICATE) {
+                            const uint64_t index = q.y;
+                            const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
+                            uint64_t m = s_matched[ci], nx = s_next[ci];
+                            uint32_t f = f0, res = 0;
+                            local[0]++;
+                            if (w0 & kPkLocal) {
+                                if (delta != kPkNoCommit) s_li[gl] = index + delta;  // raft.rs:974-991
+                            } else {
+                                f |= RAFTGPU_PF_RECENT_ACTIVE;                         // raft.rs:1674
+                                const uint64_t commit = index - delta;
+                                if (commit > s_pc[ci]) s_pc[ci] = commit;             // raft.rs:1677
+                            }
+                            if (m < index) {                                           // progress.rs:138-150
+                                res = RAFTGPU_RES_OK |
+                                      ((!(w0 & kPkLocal) && (f0 & RAFTGPU_PF_INS_FULL)) ? RAFTGPU_RES_OLD_PAUSED : 0u);
+                                s_matched[ci] = index;
+                                f &= ~RAFTGPU_PF_PAUSED;
+                                local[1]++;
+                            }
+                            if (nx < index + 1) s_next[ci] = index + 1;
+                            if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
+                            if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
+                            continue;
+                        }
+                    }
+                }
+                // General path.  A record whose EXT payloads might straddle the staged prefix is read from HBM.
+                const bool from_smem = k + 4u <= staged;
+                const void *base = from_smem ? static_cast<const void *>(s_recs) : static_cast<const void *>(a.recs + rbeg);
+                const uint64_t nn = from_smem ? staged : cnt;
+                const RecRegs rec = load_rec<true>(base, k, nn);
+                uint32_t res = 0;
+                if (!((rec.w0 >> 40) & RAFTGPU_REC_EXT)) {
+                    const uint32_t g = static_cast<uint32_t>(rec.w0), slot = static_cast<uint32_t>(rec.w0 >> 32) & 0xffu;
+                    const uint32_t gl = g - g0;
+                    if (gl >= ng) {  // not this tile's group: the batch is not in group order / bad index
+                        local[0]++;
+                        local[4]++;
+                        res = RAFTGPU_RES_NO_PROGRESS;
+                    } else if (slot < kSlots && ((hint >> slot) & 1u)) {
+                        const uint32_t r = __popc(hint & ((1u << slot) - 1u));
+                        CellRegs cd;
+                        cd.meta = s_meta[gl];
+                        cd.matched = s_matched[r * R64 + gl];
+                        cd.next_idx = s_next[r * R64 + gl];
+                        cd.flags = s_flags[r * kFRow8 + gl];
+                        cd.peer_committed = s_pc[r * R64 + gl];
+                        const CellPtrs sp{&s_matched[r * R64 + gl], &s_next[r * R64 + gl], &s_pc[r * R64 + gl], &s_li[gl],
+                                          &s_flags[r * kFRow8 + gl]};
+                        res = apply_one<true>(c, base, nn, k, rec, cd, sp, local);
+                    } else {  // a peer slot outside the hint (a learner): its cell lives in HBM
+                        CellRegs cd = load_cell(c, rec);
+                        cd.meta = s_meta[gl];
+                        CellPtrs gp = global_cell_ptrs(c, rec);
+                        gp.last_index = &s_li[gl];
+                        res = apply_one<true>(c, base, nn, k, rec, cd, gp, local);
+                    }
+                }
+                if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
+            }
+            named_bar_sync(bar_id, kCT);
+
+            // ---- B: Raft::maybe_commit for the tile's groups (raft.rs:893-904)
+            if (tid < kFTile) {  // warp-uniform: kFTile is a multiple of 32
+                const uint32_t gl = tid;
+                const bool active = gl < ng;
+                const uint32_t g = g0 + gl;
+                bool advanced = false;
+                if (active) {
+                    const uint32_t meta = s_meta[gl];
+                    uint64_t v[kSlots];
+                    uint32_t r = 0;
+#pragma unroll
+                    for (int s2 = 0; s2 < kSlots; s2++) {
+                        v[s2] = 0;
+                        if ((hint >> s2) & 1u) {
+                            v[s2] = s_matched[r * R64 + gl];
+                            r++;
+                        }
+                    }
+                    uint64_t mci;
+                    bool use_gc;
+                    eval_mci<kSimple5>(c, g, meta, v, hint, mci, use_gc);
+                    advanced = mci > s_committed[gl] && mci >= s_ts[gl] && mci <= s_li[gl];  // raft_log.rs:488
+                    if (advanced) {
+                        s_committed[gl] = mci;
+                        if (a.commit_out) a.commit_out[g] = mci;
+                        if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
+                            const uint32_t self = RAFTGPU_META_SELF(meta);
+                            uint64_t *pc = ((hint >> self) & 1u)
+                                               ? &s_pc[__popc(hint & ((1u << self) - 1u)) * R64 + gl]
+                                               : &c.peer_committed[static_cast<size_t>(self) * c.cap + g];
+                            if (mci > *pc) *pc = mci;
+                        }
+                    }
+                }
+                uint32_t lc[2] = {0, 0};
+                publish_tile(a.adv_bitmap, static_cast<uint64_t>(g0) + gl, lane, active, advanced, lc);
+                local[5] += lc[0];
+                local[6] += lc[1];
+            }
+
+            // ---- C: rows back to HBM
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(bar_id, kCT);
+            const uint32_t n_out = 4u * H + 2u;
+            if (tid < n_out) {
+                if (tid < 4u * H) {
+                    const uint32_t col = tid / H, r = tid % H;
+                    uint32_t slot = 0, seen = 0;
+                    for (uint32_t s2 = 0; s2 < kSlots; s2++)
+                        if ((hint >> s2) & 1u) {
+                            if (seen == r) slot = s2;
+                            seen++;
+                        }
+                    const size_t cell = static_cast<size_t>(slot) * c.cap + g0;
+                    if (col == 0) tma_store_1d(c.matched + cell, s_matched + r * R64, ng16 * 8u);
+                    if (col == 1) tma_store_1d(c.next_idx + cell, s_next + r * R64, ng16 * 8u);
+                    if (col == 2) tma_store_1d(c.peer_committed + cell, s_pc + r * R64, ng16 * 8u);
+                    if (col == 3) tma_store_1d(c.pflags + cell, s_flags + r * kFRow8, ng16);
+                } else if (tid == 4u * H) {
+                    tma_store_1d(c.committed + g0, s_committed, ng16 * 8u);
+                } else {
+                    tma_store_1d(c.last_index + g0, s_li, ng16 * 8u);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage may be refilled
+            }
+            named_bar_sync(bar_id, kCT);
+            if (tid == 0) mbar_arrive(&empty_bar[st]);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have landed
+    }
+    const int which[7] = {kCntRecords, kCntUpdates, kCntRejects, kCntDecrements, kCntNoProgress, kCntRecomputes, kCntAdvanced};
+    block_flush_counts<7>(local, which, a.counters, nullptr);
+    if (a.step_advanced) {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, local[6]);
+        if (lane == 0 && w) atomicAdd(a.step_advanced, w);
+    }
 }
 
 // ---------------------------------------------------------------------------

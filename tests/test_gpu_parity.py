@@ -511,6 +511,111 @@ def test_zero_copy_packed_submission_and_duplicate_detection():
     arena.close()
 
 
+def _fused_round(arena, n, recs, ref, pk, d_bufs):
+    """One fused step (raftgpu_step_sorted_device) on `recs` (group order) checked against the oracle."""
+    k = arena.pack_records(recs, pk)
+    off = B.tile_index(pk, k, n)
+    d_pk, d_off, d_res, d_bm, d_com = d_bufs
+    arena.h2d(d_pk, pk[:k])
+    arena.h2d(d_off, off)
+    arena.step_sorted_device(d_pk, k, d_off, d_results=d_res, d_adv=d_bm, d_commit=d_com)
+    res = np.zeros(k, dtype=np.uint8)
+    bm = np.zeros(arena.cap // 32, dtype=np.uint32)
+    arena.d2h(res, d_res)
+    arena.d2h(bm, d_bm)
+    want_res = O.arena_apply(ref, recs, mode=0)
+    want_adv, want_bm, _, _ = O.arena_recompute(ref)
+    main_pk = (pk[:k, 0] & np.uint64(1 << 37)) == 0           # packed records that are not EXT payloads
+    main_orig = (recs["flags"] & B.REC_EXT) == 0
+    assert np.array_equal(res[main_pk], want_res[main_orig]), "per-record results differ"
+    assert not res[~main_pk].any()
+    words = (n + 31) // 32
+    assert np.array_equal(bm[:words], want_bm[:words])
+    assert_columns_equal(arena.read_columns(n), ref, n, "fused step")
+    return want_adv
+
+
+@pytest.mark.parametrize("n,joint", [(100_003, False), (70_001, True), (1_000_000, False)])
+def test_fused_tile_step_vs_oracle(n, joint):
+    """raftgpu_step_sorted_device: the fused apply + recompute kernel on group-ordered batches,
+    including a ragged last tile, the general (joint, hint 0x7f) instantiation and 1M groups."""
+    synth = B.Synth(n, 0x5EED0007, joint=joint)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    pk = np.zeros((9 * n + 64, 2), dtype=np.uint64)
+    d_bufs = (arena.device_alloc(pk.nbytes), arena.device_alloc(4 * (n // 256 + 2)),
+              arena.device_alloc(9 * n + 64), arena.device_alloc(arena.cap // 8), arena.device_alloc(8 * arena.cap))
+    total = 0
+    for _ in range(3 if n >= 1_000_000 else 6):
+        total += _fused_round(arena, n, synth.next_round().copy(), ref, pk, d_bufs)
+    assert total > n // 2
+    cnt = arena.counters()
+    assert cnt["recomputes"] % n == 0 and cnt["advanced"] == total
+    arena.close()
+
+
+def test_fused_tile_step_learners_group_commit_and_crowded_tiles():
+    """Fused kernel corner cases: peers outside the voter hint (learners -> HBM path), group commit
+    groups (general kernel), a tile with more records than the shared-memory staging holds, records
+    whose EXT payloads straddle that boundary, and a record that is not in its tile."""
+    n = 2000
+    synth = B.Synth(n, 0x5EED0009)
+    cols = synth.initial
+    rng = np.random.default_rng(5)
+    learners = rng.random(n) < 0.3                      # slot 6 is a learner in 30 % of the groups
+    cols.meta[:n] |= (learners.astype(np.uint32) << np.uint32(16 + 6))
+    cols.next_idx[6, :n] = np.where(learners, cols.matched[0, :n] - 5, 0)
+    cols.pflags[6, :n] = np.where(learners, O.STATE_PROBE, 0)
+    gc = rng.random(n) < 0.2                            # 20 % of the groups use group commit
+    cols.meta[:n] |= np.where(gc, O.META_GROUP_COMMIT, 0).astype(np.uint32)
+    cols.commit_group_id[:5, :n] = rng.integers(0, 3, (5, n))
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(cols)
+    ref = O.copy_columns(cols)
+    pk = np.zeros((20 * n, 2), dtype=np.uint64)
+    d_bufs = (arena.device_alloc(pk.nbytes), arena.device_alloc(4 * (n // 256 + 2)),
+              arena.device_alloc(20 * n), arena.device_alloc(arena.cap // 8), arena.device_alloc(8 * arena.cap))
+    for rnd in range(3):
+        base = synth.next_round().copy()
+        # add learner responses (slot 6) and make tile 1 (groups 256..511) crowded with rejects:
+        extra = []
+        for g in np.nonzero(learners)[0]:
+            extra.append((g, 6, 0, 0, int(ref.matched[0, g]) - 3 + rnd, 0))
+        recs = np.concatenate([base, np.array(extra, dtype=B.APPEND_RESP_DTYPE)])
+        if rnd == 1:   # every follower of tile 1 rejects: 3 packed records each (reject, hint, snapshot)
+            keep = ~((recs["group"] >= 256) & (recs["group"] < 512) & (recs["peer_slot"] >= 1) & (recs["peer_slot"] <= 4))
+            recs = recs[keep]
+            crowd = []
+            for g in range(256, 512):
+                for s in range(1, 5):
+                    crowd.append((g, s, B.REC_REJECT, 0, int(ref.next_idx[s, g]) - 1, 0))
+                    crowd.append((g, s, B.REC_EXT, 0, int(ref.matched[s, g]), 77))
+            recs = np.concatenate([recs, np.array(crowd, dtype=B.APPEND_RESP_DTYPE)])
+        order = np.argsort(recs["group"], kind="stable")   # group order, arrival order kept inside a group
+        recs = np.ascontiguousarray(recs[order])
+        adv = _fused_round(arena, n, recs, ref, pk, d_bufs)
+    # a record filed under the wrong tile is not applied
+    bad = np.zeros(2, dtype=B.APPEND_RESP_DTYPE)
+    bad[0] = (10, 1, 0, 0, int(ref.matched[1, 10]) + 1, int(ref.matched[1, 10]))
+    bad[1] = (900, 1, 0, 0, int(ref.matched[1, 900]) + 1, int(ref.matched[1, 900]))
+    k = arena.pack_records(bad, pk)
+    assert k == 2
+    off = B.tile_index(pk, k, n)
+    off[1:4] = 2                                            # claim both records belong to tile 0
+    arena.h2d(d_bufs[0], pk[:k])
+    arena.h2d(d_bufs[1], off)
+    arena.step_sorted_device(d_bufs[0], k, d_bufs[1], d_results=d_bufs[2])
+    res = np.zeros(k, dtype=np.uint8)
+    arena.d2h(res, d_bufs[2])
+    assert res[1] == B.RES_NO_PROGRESS and res[0] & B.RES_OK
+    with pytest.raises(B.RaftGpuError):
+        B.tile_index(np.ascontiguousarray(pk[:k][::-1]), k, n)   # not in group order
+    arena.close()
+
+
 def test_mci_and_properties_at_full_size():
     """1M x 7 joint: maximal_committed_index for every group vs the oracle, plus
     size-independent properties: idempotence, monotone commit, joint = min of halves."""

@@ -405,6 +405,11 @@ def main():
     clocks = sampler.stop()
 
     # ---- aggregate over ranks (NCCL: counters and times only) -----------------------------------
+    if os.environ.get("RAFTGPU_TILE_DEBUG") and rank == 0:
+        d = sum(a.debug_read().astype(np.float64) for a in arenas)
+        if d[4]:
+            print("[tile debug] cycles per tile: wait_loads %.0f  records %.0f  recompute %.0f  stores %.0f  (tiles %d)"
+                  % (d[0] / d[4], d[1] / d[4], d[2] / d[4], d[3] / d[4], d[4]), file=sys.stderr)
     cnt = [a.counters() for a in arenas]
     S = importlib.import_module("raft-rs_b200.shard")
     sums, maxes = S.aggregate(

@@ -435,6 +435,9 @@ int32_t raftgpu_vote_result(raftgpu_arena *arena, uint32_t group, int32_t *out_r
 /* ---- plumbing ------------------------------------------------------------ */
 int32_t raftgpu_counters_read(raftgpu_arena *arena, raftgpu_counters *out);
 int32_t raftgpu_synchronize(raftgpu_arena *arena);
+/* Diagnostics: 8 u64 slots the fused kernel fills when RAFTGPU_TILE_DEBUG is set (cycle totals
+ * of its phases: wait for loads, records, recompute, stores; [4] = tiles). */
+int32_t raftgpu_debug_read(raftgpu_arena *arena, uint64_t *out8);
 /* Device scratch owned by the arena (for callers that keep record batches in
  * HBM, e.g. the bench's device-resident leg). */
 int32_t raftgpu_device_alloc(raftgpu_arena *arena, uint64_t bytes, void **out_device_ptr);

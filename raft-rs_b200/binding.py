@@ -179,6 +179,7 @@ def lib() -> C.CDLL:
             "raftgpu_vote_result": ([vp, u32, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)], i32),
             "raftgpu_counters_read": ([vp, C.POINTER(Counters)], i32),
             "raftgpu_synchronize": ([vp], i32),
+            "raftgpu_debug_read": ([vp, vp], i32),
             "raftgpu_device_alloc": ([vp, u64, C.POINTER(vp)], i32),
             "raftgpu_device_free": ([vp, vp], i32),
             "raftgpu_memcpy_h2d": ([vp, vp, vp, u64], i32),
@@ -329,6 +330,11 @@ class Arena:
         i = Info()
         self._ck(self._L.raftgpu_arena_info(self._h, C.byref(i)), "arena_info")
         return i
+
+    def debug_read(self) -> np.ndarray:
+        out = np.zeros(8, dtype=np.uint64)
+        self._ck(self._L.raftgpu_debug_read(self._h, out.ctypes.data), "debug_read")
+        return out
 
     def synchronize(self):
         self._ck(self._L.raftgpu_synchronize(self._h), "synchronize")

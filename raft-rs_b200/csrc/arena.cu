@@ -494,7 +494,6 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     RAFTGPU_TILE_ATTR(256, 2);
     RAFTGPU_TILE_ATTR(256, 3);
     RAFTGPU_TILE_ATTR(512, 1);
-    RAFTGPU_TILE_ATTR(512, 2);
 #undef RAFTGPU_TILE_ATTR
     {
         const char *e = getenv("RAFTGPU_TMA");
@@ -526,7 +525,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     TRY(dev_alloc(a, &c.term_start, a->cap));
     TRY(dev_alloc(a, &c.last_index, a->cap));
     TRYC(cudaMemset(c.term_start, 0xff, sizeof(uint64_t) * a->cap));  // RAFTGPU_NO_TERM_START
-    TRY(dev_alloc(a, &a->d_counters, kCntCount));
+    TRY(dev_alloc(a, &a->d_counters, kCntCount + 8));  // + 8 diagnostic slots (fused kernel phase cycles)
     TRY(dev_alloc(a, reinterpret_cast<uint8_t **>(&a->d_scratch), 256));
     TRY(pin_alloc(a, reinterpret_cast<uint8_t **>(&a->h_scratch), 256));
 
@@ -1026,7 +1025,7 @@ int32_t raftgpu_step_sorted_device(raftgpu_arena *a, void *stream, const void *d
     const uint32_t H = static_cast<uint32_t>(__builtin_popcount(hint));
     // variant knobs (tuning): RAFTGPU_TILE_VARIANT = <threads per consumer group><groups>, e.g. 2562, 5122, 2563
     static const int variant = getenv("RAFTGPU_TILE_VARIANT") ? atoi(getenv("RAFTGPU_TILE_VARIANT")) : 2562;
-    static const int cap_env = getenv("RAFTGPU_TILE_RECCAP") ? atoi(getenv("RAFTGPU_TILE_RECCAP")) : 1536;
+    static const int cap_env = getenv("RAFTGPU_TILE_RECCAP") ? atoi(getenv("RAFTGPU_TILE_RECCAP")) : 1024;
     const uint32_t rec_cap = static_cast<uint32_t>(cap_env) & ~3u;
     const uint32_t stage_bytes = tile_stage_bytes(H, rec_cap);
     int stages = std::min<int>(kFMaxStages, static_cast<int>(a->tile_smem / stage_bytes));
@@ -1043,6 +1042,8 @@ int32_t raftgpu_step_sorted_device(raftgpu_arena *a, void *stream, const void *d
     t.commit_out = d_commit_out;
     t.step_advanced = nullptr;
     t.counters = a->d_counters;
+    static const bool tile_debug = getenv("RAFTGPU_TILE_DEBUG") != nullptr;
+    t.dbg = tile_debug ? a->d_counters + kCntCount : nullptr;  // 8 spare u64 behind the counters
     const uint32_t n_tiles = div_up(hi, kFTile);
     const uint32_t blocks = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(a->sm_count));
     const size_t smem = static_cast<size_t>(stages) * stage_bytes;
@@ -1050,15 +1051,14 @@ int32_t raftgpu_step_sorted_device(raftgpu_arena *a, void *stream, const void *d
 #define RAFTGPU_LAUNCH_TILE(CT, NG)                                                        \
     do {                                                                                   \
         if (simple5)                                                                       \
-            step_tile_kernel<true, CT, NG><<<blocks, CT * NG + 32, smem, st>>>(a->cols, t); \
+            step_tile_kernel<true, CT, NG><<<blocks, CT * NG + 64, smem, st>>>(a->cols, t); \
         else                                                                               \
-            step_tile_kernel<false, CT, NG><<<blocks, CT * NG + 32, smem, st>>>(a->cols, t); \
+            step_tile_kernel<false, CT, NG><<<blocks, CT * NG + 64, smem, st>>>(a->cols, t); \
     } while (0)
     switch (variant) {
     case 2561: RAFTGPU_LAUNCH_TILE(256, 1); break;
     case 2563: RAFTGPU_LAUNCH_TILE(256, 3); break;
     case 5121: RAFTGPU_LAUNCH_TILE(512, 1); break;
-    case 5122: RAFTGPU_LAUNCH_TILE(512, 2); break;
     default: RAFTGPU_LAUNCH_TILE(256, 2); break;
     }
 #undef RAFTGPU_LAUNCH_TILE
@@ -1585,6 +1585,16 @@ int32_t raftgpu_counters_read(raftgpu_arena *a, raftgpu_counters *out) {
     CK(a, cudaMemcpyAsync(a->h_scratch, a->d_counters, sizeof(*out), cudaMemcpyDeviceToHost, a->s_compute));
     CK(a, cudaStreamSynchronize(a->s_compute));
     memcpy(out, a->h_scratch, sizeof(*out));
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_debug_read(raftgpu_arena *a, uint64_t *out8) {
+    if (!a || !out8) return RAFTGPU_ERR_INVALID;
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    CK(a, cudaSetDevice(a->device));
+    CK(a, cudaMemcpyAsync(a->h_scratch, a->d_counters + kCntCount, 64, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    memcpy(out8, a->h_scratch, 64);
     return RAFTGPU_OK;
 }
 

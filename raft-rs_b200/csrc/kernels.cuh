@@ -555,7 +555,9 @@ struct Cell {
 __device__ __forceinline__ void reset_state(Cell &p, uint32_t state, uint64_t *pending_snapshot) {
     p.flags &= ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK);
     p.flags |= state;
-    if (*pending_snapshot != 0) *pending_snapshot = 0;
+    // a plain store, not "if non-zero then clear": the cold column would otherwise cost a dependent
+    // HBM read on every state transition (and, in the fused kernel, stall the tile's barrier)
+    *pending_snapshot = 0;
 }
 
 // apply_kernel: the per-message prefix of Raft::handle_append_response
@@ -922,6 +924,7 @@ struct TileArgs {
     uint64_t *commit_out;      // nullable
     uint32_t *step_advanced;   // nullable
     unsigned long long *counters;
+    unsigned long long *dbg;   // nullable: [8] cycle totals per phase (diagnostics, RAFTGPU_TILE_DEBUG=1)
 };
 
 // bytes of one stage for H hinted slots (shared by host and device)
@@ -930,12 +933,13 @@ __host__ __device__ constexpr uint32_t tile_stage_bytes(uint32_t H, uint32_t rec
 }
 
 template <bool kSimple5, int kCT, int kNG>
-__global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, TileArgs a) {
+__global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, TileArgs a) {
     static_assert(kCT >= kFTile && kCT % 32 == 0, "a consumer group covers a tile");
     const uint32_t kFRecCap = a.rec_cap;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[kFMaxStages];
-    __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];
+    __shared__ __align__(8) uint64_t full_bar[kFMaxStages];   // loads landed            (load warp -> consumers)
+    __shared__ __align__(8) uint64_t done_bar[kFMaxStages];   // rows final in smem      (consumers -> store warp)
+    __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];  // rows read by the stores (store warp -> load warp)
 
     const uint32_t hint = kSimple5 ? 0x1fu : (a.hint & 0xffu);
     const uint32_t H = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint));
@@ -949,6 +953,7 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.n_stages; s++) {
             mbar_init(&full_bar[s], 1);
+            mbar_init(&done_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -956,8 +961,46 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
     __syncthreads();
 
     uint32_t local[7] = {0, 0, 0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress | recomputes, advanced
-    if (warp == kNG * kCT / 32) {
-        // ===================== producer warp =====================
+    if (warp == kNG * kCT / 32 + 1) {
+        // ===================== store warp: rows back to HBM, then the stage is free =====================
+        const uint32_t n_out = 4u * H + 2u;
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int st = it % a.n_stages;
+            const uint32_t ph = (it / a.n_stages) & 1u;
+            const uint32_t g0 = tile * kFTile;
+            const uint32_t ng = a.n_groups - g0 < kFTile ? a.n_groups - g0 : kFTile;
+            const uint32_t ng16 = (ng + 15u) & ~15u;
+            uint8_t *sb = smem + static_cast<size_t>(st) * stage_bytes;
+            mbar_wait(&done_bar[st], ph);  // every lane waits: the barrier's completion orders the consumers' writes
+            for (uint32_t j = lane; j < n_out; j += 32) {
+                if (j < 4u * H) {
+                    const uint32_t col = j / H, r = j % H;
+                    uint32_t slot = 0, seen = 0;
+                    for (uint32_t s2 = 0; s2 < kSlots; s2++)
+                        if ((hint >> s2) & 1u) {
+                            if (seen == r) slot = s2;
+                            seen++;
+                        }
+                    const size_t cell = static_cast<size_t>(slot) * c.cap + g0;
+                    if (col == 0) tma_store_1d(c.matched + cell, sb + o_matched + r * kFRow64, ng16 * 8u);
+                    if (col == 1) tma_store_1d(c.next_idx + cell, sb + o_next + r * kFRow64, ng16 * 8u);
+                    if (col == 2) tma_store_1d(c.peer_committed + cell, sb + o_pc + r * kFRow64, ng16 * 8u);
+                    if (col == 3) tma_store_1d(c.pflags + cell, sb + o_flags + r * kFRow8, ng16);
+                } else if (j == 4u * H) {
+                    tma_store_1d(c.committed + g0, sb + o_committed, ng16 * 8u);
+                } else {
+                    tma_store_1d(c.last_index + g0, sb + o_li, ng16 * 8u);
+                }
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory has been read
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have landed
+    } else if (warp == kNG * kCT / 32) {
+        // ===================== load warp =====================
         const uint32_t n_copies = 4u * H + 5u;
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
@@ -1014,7 +1057,6 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
             const uint32_t ph = (it / a.n_stages) & 1u;
             const uint32_t g0 = tile * kFTile;
             const uint32_t ng = a.n_groups - g0 < kFTile ? a.n_groups - g0 : kFTile;
-            const uint32_t ng16 = (ng + 15u) & ~15u;
             const uint32_t rbeg = a.tile_off[tile], rend = a.tile_off[tile + 1];
             const uint32_t cnt = rend - rbeg, staged = cnt < kFRecCap ? cnt : kFRecCap;
             uint8_t *sb = smem + static_cast<size_t>(st) * stage_bytes;
@@ -1027,15 +1069,21 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
             uint32_t *s_meta = reinterpret_cast<uint32_t *>(sb + o_meta);
             uint8_t *s_flags = sb + o_flags;
             const PackedRec *s_recs = reinterpret_cast<const PackedRec *>(sb + o_recs);
+            long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+            if (a.dbg && tid == 0) t0 = clock64();
             mbar_wait(&full_bar[st], ph);
+            if (a.dbg && tid == 0) t1 = clock64();
 
             // ---- A: the tile's records against the shared-memory rows (raft.rs:1663-1743)
             for (uint32_t k = tid; k < cnt; k += kCT) {
-                // Fast path: the common records -- an accepted AppendResponse or a leader-local
-                // record for a peer in Replicate state whose cell is staged -- straight on the packed
-                // words and the shared-memory cell; same statements as apply_one's accept / LOCAL
-                // branches (raft.rs:1674-1677, 1724-1727, 1010-1014; progress.rs:138-157).
-                if (k + 4u <= staged) {
+                // Fast path: a record for a staged cell of a peer in Replicate or Probe state -- accept,
+                // leader-local, or a rejection without a snapshot request -- straight on the packed
+                // words and the shared-memory cell.  Statement for statement the branches of apply_one
+                // (raft.rs:1674-1743, 1010-1014; progress.rs:95-114, 138-206); everything else (Snapshot
+                // state, request_snapshot, WIDE commits, learners, records near the staging boundary)
+                // takes the general path below.
+                const bool in_smem = staged == cnt || k + 4u <= staged;  // whole tile staged, or far from the cut
+                if (in_smem) {
                     const ulonglong2 q = reinterpret_cast<const ulonglong2 *>(s_recs)[k];
                     const uint64_t w0 = q.x;
                     if (w0 & kPkExt) {
@@ -1043,34 +1091,87 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
                         continue;
                     }
                     const uint32_t slot = static_cast<uint32_t>(w0 >> 32) & 7u;
-                    const uint32_t gl = static_cast<uint32_t>(w0) - g0;
-                    if (!(w0 & (kPkReject | kPkWide)) && gl < ng && ((hint >> slot) & 1u)) {
+                    const uint32_t g = static_cast<uint32_t>(w0);
+                    const uint32_t gl = g - g0;
+                    if (!(w0 & kPkWide) && gl < ng && ((hint >> slot) & 1u)) {
                         const uint32_t r = __popc(hint & ((1u << slot) - 1u));
                         const uint32_t ci = r * R64 + gl;
                         const uint32_t f0 = s_flags[r * kFRow8 + gl];
+                        const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
                         const bool present = kSimple5 || (((RAFTGPU_META_IN(s_meta[gl]) | RAFTGPU_META_OUT(s_meta[gl]) |
                                                             RAFTGPU_META_LEARN(s_meta[gl])) >> slot) & 1u);
-                        if (present && (f0 & RAFTGPU_PF_STATE_MASK) == RAFTGPU_STATE_REPLICATE) {
+                        bool simple = present && state != RAFTGPU_STATE_SNAPSHOT;
+                        uint64_t hint_idx = 0;
+                        if (simple && (w0 & kPkReject) && k + 2u >= staged) simple = false;  // payloads at the very end
+                        if (simple && (w0 & kPkReject)) {  // look at the EXT payloads: [kind 1 hint] [kind 2 snapshot request]
+                            const ulonglong2 e1 = reinterpret_cast<const ulonglong2 *>(s_recs)[k + 1];
+                            const ulonglong2 e2 = reinterpret_cast<const ulonglong2 *>(s_recs)[k + 2];
+                            const bool x1 = (e1.x & kPkExt) != 0, x2 = x1 && (e2.x & kPkExt) != 0;
+                            if (x1 && (e1.x >> 40) == 1) hint_idx = e1.y;
+                            if ((x1 && (e1.x >> 40) == 2) || (x2 && (e2.x >> 40) == 2)) simple = false;
+                        }
+                        if (simple) {
                             const uint64_t index = q.y;
                             const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
                             uint64_t m = s_matched[ci], nx = s_next[ci];
+                            const uint64_t m0 = m, nx0 = nx;
                             uint32_t f = f0, res = 0;
                             local[0]++;
-                            if (w0 & kPkLocal) {
+                            const bool is_local = (w0 & kPkLocal) != 0;
+                            if (is_local) {
                                 if (delta != kPkNoCommit) s_li[gl] = index + delta;  // raft.rs:974-991
                             } else {
-                                f |= RAFTGPU_PF_RECENT_ACTIVE;                         // raft.rs:1674
+                                f |= RAFTGPU_PF_RECENT_ACTIVE;                       // raft.rs:1674
                                 const uint64_t commit = index - delta;
-                                if (commit > s_pc[ci]) s_pc[ci] = commit;             // raft.rs:1677
+                                if (commit > s_pc[ci]) s_pc[ci] = commit;           // raft.rs:1677
                             }
-                            if (m < index) {                                           // progress.rs:138-150
-                                res = RAFTGPU_RES_OK |
-                                      ((!(w0 & kPkLocal) && (f0 & RAFTGPU_PF_INS_FULL)) ? RAFTGPU_RES_OLD_PAUSED : 0u);
-                                s_matched[ci] = index;
-                                f &= ~RAFTGPU_PF_PAUSED;
-                                local[1]++;
+                            if (w0 & kPkReject) {                                    // progress.rs:168-206, no snapshot request
+                                local[2]++;
+                                bool ok;
+                                if (state == RAFTGPU_STATE_REPLICATE) {
+                                    ok = index > m;                                  // :173-177 stale otherwise
+                                    if (ok) nx = m + 1;                              // :178-179
+                                } else if (nx == 0 || nx - 1 != index) {
+                                    ok = false;                                      // :188-192 stale
+                                } else {
+                                    nx = umin64(index, hint_idx + 1);                // :195-199
+                                    if (nx < 1) nx = 1;
+                                    f &= ~RAFTGPU_PF_PAUSED;                         // :204
+                                    ok = true;
+                                }
+                                if (ok) {
+                                    local[3]++;
+                                    res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
+                                    if (state == RAFTGPU_STATE_REPLICATE) {          // raft.rs:1716-1718 become_probe
+                                        f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) |
+                                            RAFTGPU_STATE_PROBE;
+                                        c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
+                                        nx = m + 1;
+                                    }
+                                }
+                            } else {
+                                // maybe_update (progress.rs:138-150): shared by the accept path (raft.rs:1724-1730)
+                                // and the leader-local path (raft.rs:1010-1014); only an accept looks at
+                                // is_paused() and may move a probing peer to Replicate
+                                const bool old_paused = !is_local && (state == RAFTGPU_STATE_PROBE ? (f & RAFTGPU_PF_PAUSED) != 0
+                                                                                                   : (f & RAFTGPU_PF_INS_FULL) != 0);
+                                const bool need = m < index;
+                                if (need) {
+                                    m = index;
+                                    f &= ~RAFTGPU_PF_PAUSED;
+                                    local[1]++;
+                                    res = RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u);
+                                }
+                                if (nx < index + 1) nx = index + 1;
+                                if (need && !is_local && state == RAFTGPU_STATE_PROBE) {  // raft.rs:1730 become_replicate
+                                    f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) |
+                                        RAFTGPU_STATE_REPLICATE;
+                                    c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
+                                    nx = m + 1;
+                                }
                             }
-                            if (nx < index + 1) s_next[ci] = index + 1;
+                            if (m != m0) s_matched[ci] = m;
+                            if (nx != nx0) s_next[ci] = nx;
                             if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
                             if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
                             continue;
@@ -1078,7 +1179,7 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
                     }
                 }
                 // General path.  A record whose EXT payloads might straddle the staged prefix is read from HBM.
-                const bool from_smem = k + 4u <= staged;
+                const bool from_smem = in_smem;
                 const void *base = from_smem ? static_cast<const void *>(s_recs) : static_cast<const void *>(a.recs + rbeg);
                 const uint64_t nn = from_smem ? staged : cnt;
                 const RecRegs rec = load_rec<true>(base, k, nn);
@@ -1112,6 +1213,7 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
                 if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
             }
             named_bar_sync(bar_id, kCT);
+            if (a.dbg && tid == 0) t2 = clock64();
 
             // ---- B: Raft::maybe_commit for the tile's groups (raft.rs:893-904)
             if (tid < kFTile) {  // warp-uniform: kFTile is a multiple of 32
@@ -1153,36 +1255,20 @@ __global__ void __launch_bounds__(kCT *kNG + 32, 1) step_tile_kernel(Columns c, 
                 local[6] += lc[1];
             }
 
-            // ---- C: rows back to HBM
+            // ---- C: hand the stage to the store warp (generic writes -> async proxy: fence, then signal)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             named_bar_sync(bar_id, kCT);
-            const uint32_t n_out = 4u * H + 2u;
-            if (tid < n_out) {
-                if (tid < 4u * H) {
-                    const uint32_t col = tid / H, r = tid % H;
-                    uint32_t slot = 0, seen = 0;
-                    for (uint32_t s2 = 0; s2 < kSlots; s2++)
-                        if ((hint >> s2) & 1u) {
-                            if (seen == r) slot = s2;
-                            seen++;
-                        }
-                    const size_t cell = static_cast<size_t>(slot) * c.cap + g0;
-                    if (col == 0) tma_store_1d(c.matched + cell, s_matched + r * R64, ng16 * 8u);
-                    if (col == 1) tma_store_1d(c.next_idx + cell, s_next + r * R64, ng16 * 8u);
-                    if (col == 2) tma_store_1d(c.peer_committed + cell, s_pc + r * R64, ng16 * 8u);
-                    if (col == 3) tma_store_1d(c.pflags + cell, s_flags + r * kFRow8, ng16);
-                } else if (tid == 4u * H) {
-                    tma_store_1d(c.committed + g0, s_committed, ng16 * 8u);
-                } else {
-                    tma_store_1d(c.last_index + g0, s_li, ng16 * 8u);
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage may be refilled
+            if (a.dbg && tid == 0) t3 = clock64();
+            if (tid == 0) mbar_arrive(&done_bar[st]);
+            if (a.dbg && tid == 0) {
+                t4 = clock64();
+                atomicAdd(&a.dbg[0], static_cast<unsigned long long>(t1 - t0));  // waiting for the TMA loads
+                atomicAdd(&a.dbg[1], static_cast<unsigned long long>(t2 - t1));  // A: records
+                atomicAdd(&a.dbg[2], static_cast<unsigned long long>(t3 - t2));  // B: recompute (+ fence, barrier)
+                atomicAdd(&a.dbg[3], static_cast<unsigned long long>(t4 - t3));  // C: stores + drain
+                atomicAdd(&a.dbg[4], 1ull);                                       // tiles
             }
-            named_bar_sync(bar_id, kCT);
-            if (tid == 0) mbar_arrive(&empty_bar[st]);
         }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have landed
     }
     const int which[7] = {kCntRecords, kCntUpdates, kCntRejects, kCntDecrements, kCntNoProgress, kCntRecomputes, kCntAdvanced};
     block_flush_counts<7>(local, which, a.counters, nullptr);

@@ -518,6 +518,7 @@ def _fused_round(arena, n, recs, ref, pk, d_bufs):
     d_pk, d_off, d_res, d_bm, d_com = d_bufs
     arena.h2d(d_pk, pk[:k])
     arena.h2d(d_off, off)
+    arena.h2d(d_bm, np.zeros(arena.cap // 32, dtype=np.uint32))   # bits past n_groups are left untouched
     arena.step_sorted_device(d_pk, k, d_off, d_results=d_res, d_adv=d_bm, d_commit=d_com)
     res = np.zeros(k, dtype=np.uint8)
     bm = np.zeros(arena.cap // 32, dtype=np.uint32)

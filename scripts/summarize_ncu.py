@@ -10,22 +10,28 @@ L.append("Source: `scripts/gpu_round.sh` -> `ncu --set full --clock-control none
          "`--metrics gpu__time_duration.sum` launch list of the same command.  ncu serialises kernels and "
          "replays them, so absolute times are cold-cache; compare SHARES with the live CUDA-event numbers "
          "in bench.py.\n")
-# launch list
-rows = list(csv.reader(open(f"{d}/launches.csv", errors="ignore")))
-hdr, per = None, collections.defaultdict(list)
-for r in rows:
-    if "Kernel Name" in r:
-        hdr = r
-        continue
-    if hdr and len(r) == len(hdr):
-        x = dict(zip(hdr, r))
-        if x.get("Metric Name") == "gpu__time_duration.sum":
-            v = float(x["Metric Value"].replace(",", ""))
-            per[x["Kernel Name"].split("(")[0]].append(v / 1e3 if x["Metric Unit"] == "ns" else v)
-tot = sum(sum(v) for v in per.values())
-L.append("## Launch list (gpu__time_duration.sum)\n\n| kernel | launches | avg us | min | max | share |\n|---|---|---|---|---|---|")
-for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
-    L.append(f"| `{k}` | {len(v)} | {sum(v)/len(v):.2f} | {min(v):.2f} | {max(v):.2f} | {sum(v)/tot:.1%} |")
+def launch_table(path, title):
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path, errors="ignore")))
+    hdr, per = None, collections.defaultdict(list)
+    for r in rows:
+        if "Kernel Name" in r:
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr):
+            x = dict(zip(hdr, r))
+            if x.get("Metric Name") == "gpu__time_duration.sum":
+                v = float(x["Metric Value"].replace(",", ""))
+                per[x["Kernel Name"].split("(")[0]].append(v / 1e3 if x["Metric Unit"] == "ns" else v)
+    tot = sum(sum(v) for v in per.values())
+    L.append(f"## {title}\n\n| kernel | launches | avg us | min | max | share |\n|---|---|---|---|---|---|")
+    for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+        L.append(f"| `{k}` | {len(v)} | {sum(v)/len(v):.2f} | {min(v):.2f} | {max(v):.2f} | {sum(v)/tot:.1%} |")
+    L.append("")
+
+launch_table(f"{d}/launches.csv", "Launch list, default path (gpu__time_duration.sum)")
+launch_table(f"{d}/launches_scatter.csv", "Launch list, `--scatter` path (gpu__time_duration.sum)")
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__throughput.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -34,7 +40,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"]
-for name in ("recompute", "apply"):
+for name in ("fused", "recompute", "apply"):
     rep = f"{d}/prof_{name}.ncu-rep"
     if not os.path.exists(rep):
         continue
@@ -56,6 +62,9 @@ for name in ("recompute", "apply"):
 try:
     b = json.loads(open(f"{d}/bench.json").read().strip().splitlines()[-1])
     L.append("\n## bench.py line of the same build (live CUDA events, not under ncu)\n\n```json\n" + json.dumps(b, indent=1) + "\n```")
+    if os.path.exists(f"{d}/bench_scatter.json"):
+        b2 = json.loads(open(f"{d}/bench_scatter.json").read().strip().splitlines()[-1])
+        L.append("\n## bench.py --scatter (general two-kernel path) of the same build\n\n```json\n" + json.dumps(b2, indent=1) + "\n```")
 except Exception as e:
     L.append(f"\n(no bench.json: {e})")
 open(out, "w").write("\n".join(L) + "\n")

@@ -102,14 +102,16 @@ struct HostPool {
         cv_start.notify_all();
         cv_done.wait(lk, [&] { return pending == 0; });
     }
-    void worker(int idx, cpu_set_t cpus, bool pin) {
+    void worker(int idx, cpu_set_t cpus, bool pin, int first_cpu) {
         if (pin) {
             // one CPU per worker, taken in order from the GPU-local list (its first half are
-            // distinct physical cores on these hosts; SMT siblings come after)
+            // distinct physical cores on these hosts; SMT siblings come after), starting at an
+            // offset derived from the device index so that the arenas of several GPUs on the same
+            // socket (one process per GPU) do not pile onto the same cores
             cpu_set_t one;
             CPU_ZERO(&one);
             int seen = 0, chosen = -1;
-            const int want = idx % std::max(1, CPU_COUNT(&cpus));
+            const int want = (first_cpu + idx) % std::max(1, CPU_COUNT(&cpus));
             for (int c = 0; c < CPU_SETSIZE; c++)
                 if (CPU_ISSET(c, &cpus) && seen++ == want) {
                     chosen = c;
@@ -1240,7 +1242,8 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, 
         want = std::max(1, std::min({want, static_cast<int>(a->n_rings), std::max(1, avail)}));
         a->pool = new HostPool();
         for (int t = 0; t < want; t++)
-            a->pool->threads.emplace_back(&HostPool::worker, a->pool, t, a->local_cpus, a->have_local_cpus);
+            a->pool->threads.emplace_back(&HostPool::worker, a->pool, t, a->local_cpus, a->have_local_cpus,
+                                          a->device * want);
     }
     const int T = static_cast<int>(a->pool->threads.size());
     if (n < 4096 || T == 1) {

@@ -10,7 +10,8 @@ python - <<PY
 import json
 try:
     d=json.loads(open("$OUT/bench.json").read().strip().splitlines()[-1])
-    print("value=%.3e ms/step=%.4f"%(d["value"],d["ms_per_step"]), [(k["kernel"],round(k["avg_us"],1),round(k["frac"],3)) for k in d["kernels"]], "e2e=%.3e"%d["e2e"]["value"], d["e2e"].get("host_ms_per_step"), "e2e ms/step=%.3f"%d["e2e"]["ms_per_step"], "| zero-copy:", d.get("e2e_zero_copy"))
+    print("value=%.3e ms/step=%.4f"%(d["value"],d["ms_per_step"]), [(k["kernel"],round(k["avg_us"],1),round(k["frac"],3)) for k in d["kernels"]])
+    print("e2e (zero-copy)=%.3e  %.3f ms/step | staged=%.3e %.3f ms/step"%(d["e2e"]["value"],d["e2e"]["ms_per_step"],d["e2e_staged"]["value"],d["e2e_staged"]["ms_per_step"]), d["e2e_staged"].get("host_ms_per_step"))
 except Exception as e:
     print("failed", e); print(open("$OUT/bench.err").read()[-2000:])
 PY

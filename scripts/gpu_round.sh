@@ -20,7 +20,7 @@ import json
 for n in ("bench","bench_scatter"):
     try:
         d=json.loads(open("$OUT/%s.json"%n).read().strip().splitlines()[-1])
-        print(n, "value=%.3e ms/step=%.4f"%(d["value"],d["ms_per_step"]), [(k["kernel"],round(k["avg_us"],1),round(k["frac"],3)) for k in d["kernels"]], "e2e=%.3e (%.3f ms)"%(d["e2e"]["value"],d["e2e"]["ms_per_step"]), "zc=%.3e"%d["e2e_zero_copy"]["value"], "cpu=", d.get("cpu_baseline",{}).get("value"))
+        print(n, "value=%.3e ms/step=%.4f"%(d["value"],d["ms_per_step"]), [(k["kernel"],round(k["avg_us"],1),round(k["frac"],3)) for k in d["kernels"]], "staged=%.3e (%.3f ms)"%(d["e2e_staged"]["value"],d["e2e_staged"]["ms_per_step"]), "e2e(zero-copy)=%.3e"%d["e2e"]["value"], "cpu=", d.get("cpu_baseline",{}).get("value"))
     except Exception as e:
         print(n, "failed", e)
 PY

@@ -115,12 +115,12 @@ def gpu_local_cpus(torch, device: int):
         return set()
 
 
-def cpu_leg(n_groups, seed, rounds_wanted, threads, budget_s=20.0):
+def cpu_leg(n_groups, seed, rounds_wanted, threads, budget_s=20.0, joint=False):
     """The oracle (oracle/raft_oracle.c: apply + recompute, range-partitioned over `threads`
     pthreads) on a bounded sample of the same workload.  Only used as the CPU baseline."""
     B = importlib.import_module("raft-rs_b200").binding
     from oracle import oracle as O
-    synth = B.Synth(n_groups, seed, k_peers=K_PEERS)
+    synth = B.Synth(n_groups, seed, k_peers=K_PEERS, joint=joint)
     cols = O.copy_columns(synth.initial)
     total, done, times = 0.0, 0, []
     for _ in range(rounds_wanted):
@@ -145,7 +145,9 @@ def run_reference(args, rank, world):
     # warmup rounds are part of the same stream; time exactly `steps` rounds after them
     B = importlib.import_module("raft-rs_b200").binding
     from oracle import oracle as O
-    synth = B.Synth(N_GROUPS, SEED, k_peers=K_PEERS)
+    joint = args.workload == "cfg4"
+    seed0 = 0x5EED0004 if joint else SEED
+    synth = B.Synth(N_GROUPS, seed0, k_peers=K_PEERS, joint=joint)
     cols = O.copy_columns(synth.initial)
     for _ in range(args.warmup):
         O.bench_step(cols, synth.next_round(), threads, fast=True)
@@ -159,11 +161,13 @@ def run_reference(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "cfg3: 1M raft groups x 5 peers, one synthetic AppendResponse round "
-                               "per step (apply + recompute)", "groups": N_GROUPS, "peers": K_PEERS,
-                   "seed": hex(SEED)},
+        "config": {"workload": ("cfg4: 1M raft groups x 7 peer slots under joint consensus, one synthetic "
+                                "AppendResponse round per step (apply + recompute)") if joint else
+                               ("cfg3: 1M raft groups x 5 peers, one synthetic AppendResponse round "
+                                "per step (apply + recompute)"), "groups": N_GROUPS,
+                   "peers": 7 if joint else K_PEERS, "seed": hex(seed0)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} rounds of the cfg3 stream, {threads} pthreads, "
+                         "sample": f"{args.steps} rounds of the {args.workload} stream, {threads} pthreads, "
                                    "oracle/raft_oracle.c tuned path (ro_bench_step_fast, == the literal port)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -178,6 +182,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--groups", type=int, default=N_GROUPS, help=argparse.SUPPRESS)
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg3 (default, the headline): 1M groups x 5 peers; cfg4: 1M groups x 7 peer slots under "
+                         "joint consensus (incoming {0..4}, outgoing {0,1,2,5,6}), 90 B per recompute")
     ap.add_argument("--e2e-threads", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="pipelined e2e steps per timed chunk")
@@ -216,6 +223,10 @@ def main():
 
     n = args.groups
     K, W = args.steps, args.warmup
+    joint = args.workload == "cfg4"
+    k_union = 7 if joint else K_PEERS
+    seed0 = 0x5EED0004 if joint else SEED
+    b_alg_recompute = 8 * k_union + 34
     peak_gbs, peak_src = peaks()
 
     # ---- synthetic inputs: N_ARENAS independent 1M-group stores, K+W rounds in total ----------
@@ -224,10 +235,10 @@ def main():
     per_arena = [(W + K + N_ARENAS - 1 - a) // N_ARENAS for a in range(N_ARENAS)]
     arenas, round_len, d_recs, d_offs = [], [], [], []
     fused = not (args.scatter or args.public_records)
-    pack_buf = np.empty((5 * n + 64, 2), dtype=np.uint64)
+    pack_buf = np.empty((7 * n + 64, 2), dtype=np.uint64)
     for a in range(N_ARENAS):
-        seed = SEED + 0x100 * a + 0x10000 * rank
-        s = B.Synth(n, seed, k_peers=K_PEERS)
+        seed = seed0 + 0x100 * a + 0x10000 * rank
+        s = B.Synth(n, seed, k_peers=K_PEERS, joint=joint)
         ar = B.Arena(n, device=local_rank, n_rings=1, ring_records=4096)
         assert ar.group_alloc_range(n) == 0
         ar.load_columns(s.initial)
@@ -323,11 +334,11 @@ def main():
     os.environ.setdefault("RAFTGPU_HOST_THREADS", str(e2e_threads))
     chunk = max(2, args.e2e_chunk)
     e2e_steps = 0 if args.profile else (args.e2e_steps or K)
-    es = B.Synth(n, SEED + 0x10000 * rank, k_peers=K_PEERS)
+    es = B.Synth(n, seed0 + 0x10000 * rank, k_peers=K_PEERS, joint=joint)
     ea = B.Arena(n, device=local_rank, n_rings=e2e_threads)
     assert ea.group_alloc_range(n) == 0
     ea.load_columns(es.initial)
-    bufs = [np.empty(5 * n + 64, dtype=B.APPEND_RESP_DTYPE) for _ in range(chunk)]
+    bufs = [np.empty((7 if joint else 5) * n + 64, dtype=B.APPEND_RESP_DTYPE) for _ in range(chunk)]
 
     def split(recs):
         return recs
@@ -383,7 +394,7 @@ def main():
     # promise) + raftgpu_step_wait, two steps in flight.
     zc = {"value": None}
     if e2e_steps:
-        pk = [ea.host_alloc_packed(5 * n + 64) for _ in range(chunk)]
+        pk = [ea.host_alloc_packed((7 if joint else 5) * n + 64) for _ in range(chunk)]
         zc_s, zc_timed, zc_dma = 0.0, 0, [0, 0]
         while zc_timed < e2e_steps:
             m = min(chunk, e2e_steps - zc_timed)
@@ -428,10 +439,10 @@ def main():
     if rank == 0:
         kernels = []
         if fused:
-            klist = (("step_tile_kernel", ms_apply, n_records * B_ALG_APPLY + n * K * B_ALG_RECOMPUTE),)
+            klist = (("step_tile_kernel", ms_apply, n_records * B_ALG_APPLY + n * K * b_alg_recompute),)
         else:
             klist = (("apply_kernel", ms_apply, n_records * B_ALG_APPLY),
-                     ("recompute_kernel", ms_recompute, n * K * B_ALG_RECOMPUTE))
+                     ("recompute_kernel", ms_recompute, n * K * b_alg_recompute))
         for name, ms, alg_bytes in klist:
             gbs = alg_bytes / (ms * 1e-3) / 1e9
             kernels.append({"kernel": name, "avg_us": 1e3 * ms / K, "share": ms / ms_total,
@@ -450,9 +461,11 @@ def main():
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {
-                "workload": "cfg3: 1M raft groups x 5 peers per GPU, one synthetic AppendResponse "
-                            "round per step (apply + recompute)",
-                "groups_per_gpu": n, "peers": K_PEERS, "seed": hex(SEED),
+                "workload": ("cfg4: 1M raft groups x 7 peer slots per GPU under joint consensus (two 5-voter "
+                             "majorities), one synthetic AppendResponse round per step (apply + recompute)")
+                if joint else ("cfg3: 1M raft groups x 5 peers per GPU, one synthetic AppendResponse "
+                               "round per step (apply + recompute)"),
+                "groups_per_gpu": n, "peers": k_union, "seed": hex(seed0),
                 "records_per_step": n_records / K,
                 "record_format": "24 B public" if args.public_records else "16 B packed (raftgpu_pack_records)",
                 "device_path": "fused tile kernel (raftgpu_step_sorted_device, group-ordered batch + tile index)"
@@ -491,10 +504,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core
             threads = len(all_cpus)
-            v, done, _ = cpu_leg(n, SEED, 64, threads, budget_s=15.0)
+            v, done, _ = cpu_leg(n, seed0, 64, threads, budget_s=15.0, joint=joint)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": f"{done} rounds of the same cfg3 stream (apply + recompute), {threads} "
+                "sample": f"{done} rounds of the same {args.workload} stream (apply + recompute), {threads} "
                           "pthreads, oracle/raft_oracle.c tuned path (ro_bench_step_fast, == the literal port)"}
         print(json.dumps(line), flush=True)
     for a in arenas:

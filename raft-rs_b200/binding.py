@@ -280,7 +280,7 @@ class Synth:
         fresh host pages are expensive on the GPU boxes' VMs, so one buffer is reused."""
         if out is None:
             if self._buf is None:
-                cap = min(self.max_records_per_round(), 5 * self.n_groups + 64)
+                cap = min(self.max_records_per_round(), (7 if self.joint else 5) * self.n_groups + 64)
                 self._buf = np.empty(cap, dtype=APPEND_RESP_DTYPE)
             out = self._buf
         n = C.c_uint64()

@@ -392,27 +392,42 @@ def main():
     # arena's NUMA-local pinned memory (untimed, like the generation above); timed is
     # raftgpu_step_begin_packed (H2D straight from that buffer, the GPU verifies the one-wave
     # promise) + raftgpu_step_wait, two steps in flight.
-    zc = {"value": None}
-    if e2e_steps:
-        pk = [ea.host_alloc_packed((7 if joint else 5) * n + 64) for _ in range(chunk)]
+    def zero_copy_leg(compact):
+        if compact:
+            cap_b = B.compact_bound((7 if joint else 5) * n + 64)
+            pk = [ea.host_alloc_bytes(cap_b) for _ in range(chunk)]
+        else:
+            pk = [ea.host_alloc_packed((7 if joint else 5) * n + 64) for _ in range(chunk)]
         zc_s, zc_timed, zc_dma = 0.0, 0, [0, 0]
         while zc_timed < e2e_steps:
             m = min(chunk, e2e_steps - zc_timed)
-            ks = [ea.pack_records(es.next_round(bufs[j]), pk[j]) for j in range(m)]   # untimed
+            if compact:   # untimed, like the generation of the records themselves
+                ks = [B.pack_compact(es.next_round(bufs[j]), pk[j])[0] for j in range(m)]
+                begin = ea.step_begin_compact
+            else:
+                ks = [ea.pack_records(es.next_round(bufs[j]), pk[j]) for j in range(m)]
+                begin = ea.step_begin_packed
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            ea.step_begin_packed(pk[0], ks[0], flags)
+            begin(pk[0], ks[0], flags)
             for j in range(m):
                 if j + 1 < m:
-                    ea.step_begin_packed(pk[j + 1], ks[j + 1], flags)
+                    begin(pk[j + 1], ks[j + 1], flags)
                 sr = ea.step_wait()
                 zc_dma[0] += sr.h2d_bytes
                 zc_dma[1] += sr.d2h_bytes
             zc_s += time.perf_counter() - t0
             zc_timed += m
-        zc = {"seconds": zc_s, "steps": zc_timed, "h2d": zc_dma[0] / zc_timed, "d2h": zc_dma[1] / zc_timed}
+        for b_ in pk:
+            ea.host_free(b_)
+        return {"seconds": zc_s, "steps": zc_timed, "h2d": zc_dma[0] / zc_timed, "d2h": zc_dma[1] / zc_timed}
+
+    zc, zp = {"value": None}, {"value": None}
+    if e2e_steps:
+        zp = zero_copy_leg(False)
+        zc = zero_copy_leg(True)
     h2d = dma[0] / max(1, e2e_timed)
     d2h = dma[1] / max(1, e2e_timed)
     caller_bytes = h2d_bytes / max(1, e2e_timed)
@@ -431,7 +446,8 @@ def main():
         {"groups_device": n * K, "groups_e2e": n * e2e_timed,
          "recomputes": sum(c["recomputes"] for c in cnt), "advanced": sum(c["advanced"] for c in cnt),
          "records": sum(c["records"] for c in cnt)},
-        {"ms_total": ms_total, "e2e_s": e2e_s, "zc_s": zc.get("seconds", 0.0)}, device="cuda")
+        {"ms_total": ms_total, "e2e_s": e2e_s, "zc_s": zc.get("seconds", 0.0), "zp_s": zp.get("seconds", 0.0)},
+        device="cuda")
     ms_max, e2e_max = maxes["ms_total"], maxes["e2e_s"]
     value = sums["groups_device"] / (ms_max * 1e-3)
     e2e_value = sums["groups_e2e"] / e2e_max if e2e_max > 0 else None
@@ -491,12 +507,18 @@ def main():
                 "value": world * n * zc["steps"] / maxes["zc_s"], "unit": UNIT,
                 "ms_per_step": 1e3 * maxes["zc_s"] / zc["steps"], "steps": zc["steps"],
                 "h2d_bytes_per_step": zc["h2d"], "d2h_bytes_per_step": zc["d2h"],
-                "api": "raftgpu_step_begin_packed + raftgpu_step_wait: the step's records sit in pinned host "
-                       "memory (raftgpu_host_alloc) in the packed wire form the caller built them in; timed: "
-                       "H2D of the records, apply (device-side one-wave check) + recompute kernels, D2H of the "
-                       "advanced bitmap and new commit indexes; two steps in flight.  e2e_staged is the same "
-                       "through raftgpu_enqueue_bulk, i.e. with the library copying + packing 24-byte records "
-                       "from pageable memory first"},
+                "api": "raftgpu_step_begin_compact + raftgpu_step_wait: the step's records sit in pinned host "
+                       "memory (raftgpu_host_alloc) as the compact stream the caller built them in "
+                       "(raftgpu_pack_compact, untimed like the generation of the records); timed: H2D of the "
+                       "stream, apply (device-side decode + one-wave check) + recompute kernels, D2H of the "
+                       "advanced bitmap and new commit indexes; two steps in flight.  e2e_packed16 is the same "
+                       "with the 16-byte packed form (raftgpu_step_begin_packed); e2e_staged goes through "
+                       "raftgpu_enqueue_bulk, i.e. with the library copying + packing 24-byte records from "
+                       "pageable memory first"},
+            "e2e_packed16": None if not zp.get("steps") else {
+                "value": world * n * zp["steps"] / maxes["zp_s"], "unit": UNIT,
+                "ms_per_step": 1e3 * maxes["zp_s"] / zp["steps"], "steps": zp["steps"],
+                "h2d_bytes_per_step": zp["h2d"], "d2h_bytes_per_step": zp["d2h"]},
             "gpu_launches": (1 if fused else 2) * K,
             "clocks": clocks,
             "counters": {"recomputes": sums["recomputes"], "advanced": sums["advanced"], "records": sums["records"]},

@@ -394,6 +394,56 @@ int32_t raftgpu_pack_records(const raftgpu_append_resp *records, uint64_t n, raf
 int32_t raftgpu_step_begin_packed(raftgpu_arena *arena, const raftgpu_packed_rec *pinned_records,
                                   uint64_t n_packed, uint32_t flags);
 
+/* ---- compact stream (the narrow wire form) -------------------------------------
+ * PCIe is the end-to-end bottleneck of a step, so the bytes per record are the
+ * end-to-end cost.  The compact stream carries a batch as 4-byte units instead of 16-byte
+ * packed records: the records of one group (consecutive in the input, as a multi-raft ready
+ * loop produces them) form a RUN
+ *      [HDR_A][HDR_B] rec rec rec ...          (at most 8 units after the header)
+ * whose header names the group and a 48-bit base index, and each record is a slot, a 15-bit
+ * index delta above the base and an 8-bit commit delta:
+ *      unit & 3 == 0  REC    [2] LOCAL  [3,6) back  [6,9) peer slot  [9,24) index - base
+ *                            [24,32) message: index - commit; LOCAL: commit - index (255 = none)
+ *                            (the run's header sits at unit positions i-back-2 and i-back-1)
+ *      unit & 3 == 1  HDR_A  [2,32) base bits [0,30)
+ *      unit & 3 == 2  HDR_B  [2,14) group - g_base[block of HDR_A]   [14,32) base bits [30,48)
+ *      unit & 3 == 3  ESC    [2,32) index into the side table (0x3fffffff = padding, a no-op)
+ * g_base[] holds one group id per block of RAFTGPU_COMPACT_BLOCK units.  Whatever does not fit
+ * (every REJECT with its EXT, an index more than 32767 below the run's largest, a commit
+ * delta above 254, a base above 2^48, a group more than 4095 above its block's g_base) is an ESC
+ * unit pointing at the full 24-byte public record in the side table -- the format is lossless
+ * for ANY input, only less compact for hostile ones.  A 5-peer round is ~22 bytes per group
+ * instead of ~57.  The blob is position independent: header, g_base[], units[], side[].
+ * Same contract as raftgpu_step_begin_packed: pinned buffer (raftgpu_host_alloc), ONE wave
+ * checked on the GPU, buffer untouched until the step's raftgpu_step_wait returns.  Result
+ * bytes (RAFTGPU_STEP_READ_RESULTS) are per UNIT; raftgpu_pack_compact can report the unit
+ * of every public record. */
+#define RAFTGPU_COMPACT_MAGIC 0x31434752u /* "RGC1" */
+#define RAFTGPU_COMPACT_BLOCK 2048u
+typedef struct raftgpu_compact_hdr {
+    uint32_t magic;
+    uint32_t n_units;   /* 4-byte units */
+    uint32_t n_blocks;  /* ceil(n_units / RAFTGPU_COMPACT_BLOCK) */
+    uint32_t n_side;    /* 24-byte records in the side table */
+    uint64_t n_records; /* public records represented (EXT continuations not counted) */
+    uint64_t off_blocks, off_units, off_side; /* byte offsets from the start of the blob, 16-byte aligned */
+    uint64_t total_bytes;
+    uint64_t reserved;
+} raftgpu_compact_hdr;
+/* Upper bound of the blob size for n public records (EXT records included in n). */
+uint64_t raftgpu_compact_bound(uint64_t n);
+/* records[0..n) -> blob at out (out_capacity bytes; any host memory, pinned for the zero-copy
+ * step).  unit_of_record: optional [n], the unit index holding record i's result byte
+ * (UINT32_MAX for EXT records). */
+int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, void *out, uint64_t out_capacity,
+                             uint64_t *out_bytes, uint32_t *unit_of_record);
+int32_t raftgpu_step_begin_compact(raftgpu_arena *arena, const void *pinned_blob, uint64_t blob_bytes,
+                                   uint32_t flags);
+/* Result bytes of the last completed ZERO-COPY step (packed: one per packed record, compact:
+ * one per unit; 0 for EXT payloads / headers), valid until the next raftgpu_step_wait.  Needs
+ * RAFTGPU_STEP_READ_RESULTS.  raft.rs:1663-1743: what handle_append_response decided per message. */
+int32_t raftgpu_step_slot_results(raftgpu_arena *arena, const uint8_t **results, uint64_t *n_slots);
+
 /* One batched step over everything enqueued: H2D of the staged records, the
  * apply kernel per wave, ONE recompute pass over all allocated groups, D2H of
  * the results.  raftgpu_step = raftgpu_step_begin + raftgpu_step_wait.  Between

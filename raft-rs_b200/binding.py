@@ -110,6 +110,62 @@ class SynthColumns(C.Structure):
                                    "sim_last", "sim_flags")]
 
 
+def compact_bound(n_records: int) -> int:
+    return int(lib().raftgpu_compact_bound(n_records))
+
+
+def pack_compact(recs: np.ndarray, out: np.ndarray, want_units: bool = False):
+    """records -> compact stream blob in `out` (u8, 16-byte aligned).  Returns (bytes, unit_of_record|None)."""
+    assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous and out.dtype == np.uint8
+    nb = C.c_uint64()
+    units = np.empty(len(recs), dtype=np.uint32) if want_units else None
+    rc = lib().raftgpu_pack_compact(recs.ctypes.data, len(recs), out.ctypes.data, out.nbytes, C.byref(nb),
+                                    units.ctypes.data if want_units else None)
+    if rc != 0:
+        raise RuntimeError(f"raftgpu_pack_compact failed: {rc}")
+    return nb.value, units
+
+
+COMPACT_HDR_DTYPE = np.dtype([("magic", "<u4"), ("n_units", "<u4"), ("n_blocks", "<u4"), ("n_side", "<u4"),
+                              ("n_records", "<u8"), ("off_blocks", "<u8"), ("off_units", "<u8"),
+                              ("off_side", "<u8"), ("total_bytes", "<u8"), ("reserved", "<u8")])
+
+
+def unpack_compact(blob: np.ndarray) -> np.ndarray:
+    """Decode a compact stream back to public records (tests; mirrors load_compact in kernels.cuh)."""
+    h = blob[:COMPACT_HDR_DTYPE.itemsize].view(COMPACT_HDR_DTYPE)[0]
+    assert h["magic"] == 0x31434752
+    nu, ns = int(h["n_units"]), int(h["n_side"])
+    units = blob[int(h["off_units"]):int(h["off_units"]) + 4 * nu].view(np.uint32)
+    g_base = blob[int(h["off_blocks"]):int(h["off_blocks"]) + 4 * int(h["n_blocks"])].view(np.uint32)
+    side = blob[int(h["off_side"]):int(h["off_side"]) + 24 * ns].view(APPEND_RESP_DTYPE)
+    out = []
+    for i in range(nu):
+        u = int(units[i])
+        kind = u & 3
+        if kind == 3:
+            k = u >> 2
+            if k < ns:
+                out.append(tuple(side[k]))
+                if (side[k]["flags"] & REC_REJECT) and k + 1 < ns and (side[k + 1]["flags"] & REC_EXT):
+                    out.append(tuple(side[k + 1]))
+            continue
+        if kind != 0:
+            continue
+        back = (u >> 3) & 7
+        hpos = i - back - 2
+        ha, hb = int(units[hpos]), int(units[hpos + 1])
+        assert ha & 3 == 1 and hb & 3 == 2
+        g = int(g_base[hpos // 2048]) + ((hb >> 2) & 0xfff)
+        base = (ha >> 2) | ((hb >> 14) << 30)
+        index = base + ((u >> 9) & 0x7fff)
+        cd = u >> 24
+        local = bool(u & 4)
+        commit = (0 if cd == 255 else index + cd) if local else index - cd
+        out.append((g, (u >> 6) & 7, REC_LOCAL if local else 0, 0, index, commit))
+    return np.array(out, dtype=APPEND_RESP_DTYPE)
+
+
 def declared_symbols() -> list[str]:
     """Every function include/raftgpu.h declares (parsed from the header text)."""
     with open(HEADER_PATH, encoding="utf-8") as f:
@@ -167,6 +223,10 @@ def lib() -> C.CDLL:
             "raftgpu_step_begin": ([vp, u32], i32),
             "raftgpu_step_begin_packed": ([vp, vp, u64, u32], i32),
             "raftgpu_pack_records": ([vp, u64, vp, u64, C.POINTER(u64)], i32),
+            "raftgpu_compact_bound": ([u64], u64),
+            "raftgpu_pack_compact": ([vp, u64, vp, u64, C.POINTER(u64), vp], i32),
+            "raftgpu_step_begin_compact": ([vp, vp, u64, u32], i32),
+            "raftgpu_step_slot_results": ([vp, C.POINTER(vp), C.POINTER(u64)], i32),
             "raftgpu_host_alloc": ([vp, u64, C.POINTER(vp)], i32),
             "raftgpu_host_free": ([vp, vp], i32),
             "raftgpu_step_wait": ([vp, C.POINTER(StepResult)], i32),
@@ -522,6 +582,19 @@ class Arena:
         self._ck(self._L.raftgpu_step_begin_packed(self._h, packed.ctypes.data, n_packed, flags),
                  "step_begin_packed")
 
+    def host_alloc_bytes(self, n_bytes: int) -> np.ndarray:
+        """NUMA-local pinned byte buffer owned by the arena (16-byte aligned)."""
+        p = C.c_void_p()
+        self._ck(self._L.raftgpu_host_alloc(self._h, n_bytes, C.byref(p)), "host_alloc")
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n_bytes,))
+
+    def host_free(self, buf: np.ndarray):
+        self._ck(self._L.raftgpu_host_free(self._h, buf.ctypes.data), "host_free")
+
+    def step_begin_compact(self, blob: np.ndarray, n_bytes: int, flags=0):
+        self._ck(self._L.raftgpu_step_begin_compact(self._h, blob.ctypes.data, n_bytes, flags),
+                 "step_begin_compact")
+
     def step_begin(self, flags=0):
         self._ck(self._L.raftgpu_step_begin(self._h, flags), "step_begin")
 
@@ -546,6 +619,14 @@ class Arena:
         bm = np.ctypeslib.as_array(C.cast(pa, C.POINTER(C.c_uint32)), shape=(words,))
         com = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_uint64)), shape=(n_groups,)) if pc.value else None
         return bm, com
+
+    def slot_results(self) -> np.ndarray:
+        """Result bytes of the last zero-copy step, one per packed record / compact unit (a view)."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._L.raftgpu_step_slot_results(self._h, C.byref(p), C.byref(n)), "step_slot_results")
+        if n.value == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,))
 
     def record_results(self, ring: int = 0) -> np.ndarray:
         """Result bytes of the records enqueued on `ring` in the last step, in enqueue order."""

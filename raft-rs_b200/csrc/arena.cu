@@ -544,7 +544,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
         TRY(pin_alloc(a, &s.h_overflow, a->overflow_records));
         TRY(pin_alloc(a, &s.h_adv_bitmap, a->cap / 32));
         TRY(pin_alloc(a, &s.h_committed, a->cap));
-        TRY(pin_alloc(a, &s.h_results, rec_total));
+        TRY(pin_alloc(a, &s.h_results, 4 * rec_total));  // one byte per slot; a compact stream has 4-byte units
         TRY(pin_alloc(a, &s.h_step_adv, 4));
         s.rings.assign(a->n_rings, Ring());
         s.touched = static_cast<uint8_t *>(calloc(a->cap, 1));
@@ -552,7 +552,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
         TRY(dev_alloc(a, &s.d_recs, rec_total, false));
         TRY(dev_alloc(a, &s.d_adv_bitmap, a->cap / 32));
         TRY(dev_alloc(a, &s.d_commit_out, a->cap));
-        TRY(dev_alloc(a, &s.d_results, rec_total));
+        TRY(dev_alloc(a, &s.d_results, 4 * rec_total));
         TRY(dev_alloc(a, &s.d_step_adv, 4));
         TRY(dev_alloc(a, &s.d_touched, a->cap / 4));
         TRYC(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
@@ -1292,16 +1292,19 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, 
 
 // Submit one step.  ext != nullptr: zero-copy -- wave 0 is the caller's pinned packed buffer and the
 // GPU verifies the one-record-per-cell promise; otherwise wave 0 is what the rings staged.
-static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ext, uint64_t ext_n) {
+static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ext, uint64_t ext_n,
+                           const raftgpu_compact_hdr *cb = nullptr) {
     if (!a) return RAFTGPU_ERR_INVALID;
     if (a->n_inflight >= 2) return fail(a, RAFTGPU_ERR_BUSY, "two steps already in flight: call raftgpu_step_wait");
     CK(a, cudaSetDevice(a->device));
     StagingSet &s = a->sets[a->fill];
-    if (ext) {
+    if (ext || cb) {
         if (s.next_chunk.load() != 0 || !s.overflow_waves.empty())
             return fail(a, RAFTGPU_ERR_INVALID, "records were enqueued for this step: cannot mix with a zero-copy batch");
         if (ext_n > static_cast<uint64_t>(a->n_chunks) * kChunk)
             return fail(a, RAFTGPU_ERR_FULL, "zero-copy batch larger than the device staging buffer");
+        if (cb && cb->total_bytes > (static_cast<uint64_t>(a->n_chunks) * kChunk + a->overflow_records) * sizeof(PackedRec))
+            return fail(a, RAFTGPU_ERR_FULL, "compact batch larger than the device staging buffer");
     }
     // pad every ring's last chunk, then ONE H2D of the used prefix of the shared buffer
     uint64_t n_real = 0;
@@ -1312,9 +1315,12 @@ static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ex
         for (; rg.fill < kChunk; rg.fill++) dst[rg.fill] = PackedRec{kPkExt, 0};
     }
     const uint32_t used_chunks = std::min(s.next_chunk.load(), a->n_chunks);
-    const uint64_t wave0 = ext ? ext_n : static_cast<uint64_t>(used_chunks) * kChunk;
+    const uint64_t wave0 = cb ? cb->n_units : ext ? ext_n : static_cast<uint64_t>(used_chunks) * kChunk;
     if (ext) n_real = ext_n;
-    if (wave0)
+    if (cb) n_real = cb->n_records;
+    if (cb)
+        CK(a, cudaMemcpyAsync(s.d_recs, cb, cb->total_bytes, cudaMemcpyHostToDevice, a->s_h2d));
+    else if (wave0)
         CK(a, cudaMemcpyAsync(s.d_recs, ext ? ext : s.h_recs, wave0 * sizeof(PackedRec),
                               cudaMemcpyHostToDevice, a->s_h2d));
     std::vector<uint64_t> wave_sizes;
@@ -1343,7 +1349,22 @@ static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ex
     uint8_t *d_res = (flags & RAFTGPU_STEP_READ_RESULTS) ? s.d_results : nullptr;
     CK(a, cudaMemsetAsync(s.d_step_adv, 0, 8, a->s_compute));
     int32_t rc = RAFTGPU_OK;
-    if (ext) {
+    if (cb) {
+        CK(a, cudaMemsetAsync(s.d_touched, 0, a->cap, a->s_compute));
+        if (wave0) {
+            const uint8_t *d_blob = reinterpret_cast<const uint8_t *>(s.d_recs);
+            CompactSrc src;
+            src.units = reinterpret_cast<const uint32_t *>(d_blob + cb->off_units);
+            src.g_base = reinterpret_cast<const uint32_t *>(d_blob + cb->off_blocks);
+            src.side = reinterpret_cast<const raftgpu_append_resp *>(d_blob + cb->off_side);
+            src.n_units = cb->n_units;
+            src.n_side = cb->n_side;
+            const uint32_t blocks = std::min<uint32_t>(div_up(wave0, 256), static_cast<uint32_t>(a->grid_apply));
+            apply_compact_kernel<true><<<blocks, 256, 0, a->s_compute>>>(a->cols, src, d_res, a->d_counters, s.d_touched,
+                                                                        s.d_step_adv + 1);
+            CKL(a);
+        }
+    } else if (ext) {
         CK(a, cudaMemsetAsync(s.d_touched, 0, a->cap, a->s_compute));
         if (wave0) {
             const uint32_t blocks = std::min<uint32_t>(div_up(wave0, 256), static_cast<uint32_t>(a->grid_apply));
@@ -1384,7 +1405,7 @@ static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ex
     s.flags = flags;
     s.wave0_slots = wave0;
     s.result.n_records = n_real + ov_orig;
-    s.result.h2d_bytes = (wave0 + ov) * sizeof(PackedRec);
+    s.result.h2d_bytes = cb ? cb->total_bytes : (wave0 + ov) * sizeof(PackedRec);
     s.result.d2h_bytes = 8 + (hi ? 4ull * ((hi + 31) / 32) : 0) +
                          (((flags & RAFTGPU_STEP_READ_COMMITTED) && hi) ? 8ull * hi : 0) + ((d_res && woff) ? woff : 0);
     s.result.n_waves = static_cast<uint32_t>((n_real ? 1 : 0) + wave_sizes.size());
@@ -1432,6 +1453,150 @@ int32_t raftgpu_pack_records(const raftgpu_append_resp *records, uint64_t n, raf
     }
     *out_n = k;
     return RAFTGPU_OK;
+}
+
+static inline uint64_t align16(uint64_t x) { return (x + 15u) & ~15ull; }
+
+uint64_t raftgpu_compact_bound(uint64_t n) {
+    // worst case per record: its own run (2 header units + 1) or an ESC unit plus 24 side bytes
+    const uint64_t units = 3 * n + 8;
+    return sizeof(raftgpu_compact_hdr) + align16(4 * (units / RAFTGPU_COMPACT_BLOCK + 2)) + align16(4 * units) + 24 * n + 64;
+}
+
+int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, void *out, uint64_t out_capacity,
+                             uint64_t *out_bytes, uint32_t *unit_of_record) {
+    if ((!records && n) || !out || !out_bytes) return RAFTGPU_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(out) & 15u) return RAFTGPU_ERR_INVALID;
+    const uint64_t max_units = 3 * n + 8;
+    const uint64_t off_blocks = sizeof(raftgpu_compact_hdr);
+    const uint64_t off_units = off_blocks + align16(4 * (max_units / RAFTGPU_COMPACT_BLOCK + 2));
+    if (off_units > out_capacity) return RAFTGPU_ERR_FULL;
+    uint8_t *blob = static_cast<uint8_t *>(out);
+    uint32_t *g_base = reinterpret_cast<uint32_t *>(blob + off_blocks);
+    uint32_t *units = reinterpret_cast<uint32_t *>(blob + off_units);
+    const uint64_t unit_cap = std::min<uint64_t>((out_capacity - off_units) / 4, 0xfffffff0ull);
+    std::vector<raftgpu_append_resp> side;
+    uint64_t nu = 0, n_rec = 0;
+    uint64_t blocks_set = 0;  // g_base[b] is defined for b < blocks_set
+    auto esc = [&](uint64_t i) -> bool {  // record i (and its EXT) to the side table, one ESC unit
+        if (nu >= unit_cap || side.size() >= kCuPad - 2) return false;
+        units[nu] = kCuEsc | (static_cast<uint32_t>(side.size()) << 2);
+        if (unit_of_record) unit_of_record[i] = static_cast<uint32_t>(nu);
+        nu++;
+        side.push_back(records[i]);
+        if ((records[i].flags & RAFTGPU_REC_REJECT) && i + 1 < n && (records[i + 1].flags & RAFTGPU_REC_EXT))
+            side.push_back(records[i + 1]);
+        return true;
+    };
+    uint64_t i = 0;
+    while (i < n) {
+        if (records[i].flags & RAFTGPU_REC_EXT) {  // stray continuation: carries nothing by itself
+            if (unit_of_record) unit_of_record[i] = UINT32_MAX;
+            i++;
+            continue;
+        }
+        // the run: consecutive records of one group, at most 8 units
+        const uint32_t g = records[i].group;
+        uint64_t e = i, max_index = 0;
+        uint32_t run_units = 0;
+        bool any = false;
+        while (e < n && run_units < 8) {
+            const raftgpu_append_resp &r = records[e];
+            if (r.flags & RAFTGPU_REC_EXT) {
+                e++;
+                continue;
+            }
+            if (r.group != g) break;
+            run_units++;
+            if (!(r.flags & RAFTGPU_REC_REJECT) && r.peer_slot < RAFTGPU_SLOTS) {
+                any = true;
+                max_index = std::max(max_index, r.index);
+            }
+            e++;
+        }
+        while (e < n && (records[e].flags & RAFTGPU_REC_EXT)) e++;  // the EXT of the run's last record
+        const uint64_t base = max_index > 0x7fffu ? max_index - 0x7fffu : 0;
+        bool header = any && base < (1ull << 48);
+        if (header) {
+            const uint64_t b = nu / RAFTGPU_COMPACT_BLOCK;
+            while (blocks_set <= b) g_base[blocks_set++] = g;  // first header of the block names its g_base
+            const uint32_t gb = g_base[b];
+            if (g < gb || g - gb > 0xfffu) header = false;
+        }
+        if (nu + 2 + run_units > unit_cap) return RAFTGPU_ERR_FULL;
+        if (header) {
+            const uint32_t gl = g - g_base[nu / RAFTGPU_COMPACT_BLOCK];
+            units[nu++] = kCuHdrA | (static_cast<uint32_t>(base & 0x3fffffffu) << 2);
+            units[nu++] = kCuHdrB | (gl << 2) | (static_cast<uint32_t>(base >> 30) << 14);
+        }
+        uint32_t back = 0;
+        for (uint64_t k = i; k < e; k++) {
+            const raftgpu_append_resp &r = records[k];
+            if (r.flags & RAFTGPU_REC_EXT) {
+                if (unit_of_record) unit_of_record[k] = UINT32_MAX;
+                continue;
+            }
+            n_rec++;
+            bool compact = header && !(r.flags & RAFTGPU_REC_REJECT) && r.peer_slot < RAFTGPU_SLOTS &&
+                           !(r.flags & ~(RAFTGPU_REC_LOCAL)) && r.index >= base && r.index - base <= 0x7fffu;
+            uint32_t cd = 0;
+            if (compact) {
+                if (r.flags & RAFTGPU_REC_LOCAL) {
+                    if (r.commit == 0)
+                        cd = kCuNoCommit;
+                    else if (r.commit >= r.index && r.commit - r.index < kCuNoCommit)
+                        cd = static_cast<uint32_t>(r.commit - r.index);
+                    else
+                        compact = false;
+                } else if (r.commit <= r.index && r.index - r.commit <= 255u) {
+                    cd = static_cast<uint32_t>(r.index - r.commit);
+                } else {
+                    compact = false;
+                }
+            }
+            if (compact) {
+                units[nu] = kCuRec | ((r.flags & RAFTGPU_REC_LOCAL) ? kCuLocal : 0u) | (back << 3) |
+                            (static_cast<uint32_t>(r.peer_slot) << 6) | (static_cast<uint32_t>(r.index - base) << 9) | (cd << 24);
+                if (unit_of_record) unit_of_record[k] = static_cast<uint32_t>(nu);
+                nu++;
+            } else if (!esc(k)) {
+                return RAFTGPU_ERR_FULL;
+            }
+            back++;
+        }
+        i = e;
+    }
+    const uint64_t n_blocks = (nu + RAFTGPU_COMPACT_BLOCK - 1) / RAFTGPU_COMPACT_BLOCK;
+    while (blocks_set < n_blocks) g_base[blocks_set++] = 0;
+    const uint64_t off_side = off_units + align16(4 * nu);
+    const uint64_t total = off_side + align16(side.size() * sizeof(raftgpu_append_resp));
+    if (total > out_capacity) return RAFTGPU_ERR_FULL;
+    if (!side.empty()) memcpy(blob + off_side, side.data(), side.size() * sizeof(raftgpu_append_resp));
+    raftgpu_compact_hdr h{};
+    h.magic = RAFTGPU_COMPACT_MAGIC;
+    h.n_units = static_cast<uint32_t>(nu);
+    h.n_blocks = static_cast<uint32_t>(n_blocks);
+    h.n_side = static_cast<uint32_t>(side.size());
+    h.n_records = n_rec;
+    h.off_blocks = off_blocks;
+    h.off_units = off_units;
+    h.off_side = off_side;
+    h.total_bytes = total;
+    memcpy(blob, &h, sizeof(h));
+    *out_bytes = total;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_step_begin_compact(raftgpu_arena *a, const void *pinned_blob, uint64_t blob_bytes, uint32_t flags) {
+    if (!a || !pinned_blob || blob_bytes < sizeof(raftgpu_compact_hdr)) return RAFTGPU_ERR_INVALID;
+    const raftgpu_compact_hdr *h = static_cast<const raftgpu_compact_hdr *>(pinned_blob);
+    const uint64_t need_blocks = (static_cast<uint64_t>(h->n_units) + RAFTGPU_COMPACT_BLOCK - 1) / RAFTGPU_COMPACT_BLOCK;
+    if (h->magic != RAFTGPU_COMPACT_MAGIC || h->total_bytes > blob_bytes || h->n_blocks < need_blocks ||
+        (h->off_blocks & 3u) || (h->off_units & 15u) || (h->off_side & 15u) ||
+        h->off_blocks + 4ull * h->n_blocks > h->total_bytes || h->off_units + 4ull * h->n_units > h->total_bytes ||
+        h->off_side + 24ull * h->n_side > h->total_bytes)
+        return fail(a, RAFTGPU_ERR_INVALID, "malformed compact batch header");
+    return step_submit(a, flags, nullptr, 0, h);
 }
 
 int32_t raftgpu_host_alloc(raftgpu_arena *a, uint64_t bytes, void **out_pinned) {
@@ -1490,6 +1655,17 @@ int32_t raftgpu_step_results(raftgpu_arena *a, const uint32_t **adv_bitmap, cons
     StagingSet &s = a->sets[a->last_done];
     if (adv_bitmap) *adv_bitmap = s.h_adv_bitmap;
     if (committed) *committed = (s.flags & RAFTGPU_STEP_READ_COMMITTED) ? s.h_committed : nullptr;
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_step_slot_results(raftgpu_arena *a, const uint8_t **results, uint64_t *n_slots) {
+    if (!a || !results || !n_slots) return RAFTGPU_ERR_INVALID;
+    if (a->last_done < 0) return fail(a, RAFTGPU_ERR_INVALID, "no completed step");
+    StagingSet &s = a->sets[a->last_done];
+    if (!(s.flags & RAFTGPU_STEP_READ_RESULTS))
+        return fail(a, RAFTGPU_ERR_INVALID, "step ran without RAFTGPU_STEP_READ_RESULTS");
+    *results = s.h_results;
+    *n_slots = s.wave0_slots;
     return RAFTGPU_OK;
 }
 

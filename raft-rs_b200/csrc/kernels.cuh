@@ -875,6 +875,106 @@ apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__re
 }
 
 // ---------------------------------------------------------------------------
+// The compact stream (raftgpu.h "compact stream"): 4-byte units, group runs with a header.
+constexpr uint32_t kCuRec = 0, kCuHdrA = 1, kCuHdrB = 2, kCuEsc = 3;
+constexpr uint32_t kCuLocal = 4u, kCuPad = 0x3fffffffu, kCuNoCommit = 255u;
+struct CompactSrc {
+    const uint32_t *units;
+    const uint32_t *g_base;              // one per block of RAFTGPU_COMPACT_BLOCK units
+    const raftgpu_append_resp *side;     // ESC targets, public layout (a REJECT is followed by its EXT)
+    uint32_t n_units, n_side;
+};
+
+// Unit i as a record in the public register layout.  Headers, padding and malformed units come
+// back as EXT (a no-op); for an ESC unit `sidx` is the side-table position of the record.
+// `units` may point at shared memory (the fused kernel) with `gi` the global position of unit 0.
+__device__ __forceinline__ RecRegs load_compact(const CompactSrc &s, const uint32_t *units, uint64_t i, uint64_t n,
+                                                uint64_t gi, uint32_t &sidx) {
+    RecRegs r;
+    r.w0 = static_cast<uint64_t>(RAFTGPU_REC_EXT) << 40;
+    r.index = 0;
+    r.commit = 0;
+    sidx = 0;
+    if (i >= n) return r;
+    const uint32_t u = units[i];
+    const uint32_t kind = u & 3u;
+    if (kind == kCuEsc) {
+        const uint32_t k = u >> 2;
+        if (k < s.n_side) {
+            const uint64_t *p = reinterpret_cast<const uint64_t *>(s.side + k);
+            sidx = k;
+            r.w0 = p[0];
+            r.index = p[1];
+            r.commit = p[2];
+        }
+        return r;
+    }
+    if (kind != kCuRec) return r;
+    const uint32_t back = (u >> 3) & 7u;
+    if (i < back + 2u) return r;
+    const uint64_t h = i - back - 2u;
+    const uint32_t ha = units[h], hb = units[h + 1];
+    if ((ha & 3u) != kCuHdrA || (hb & 3u) != kCuHdrB) return r;
+    const uint32_t g = s.g_base[(gi + h) / RAFTGPU_COMPACT_BLOCK] + ((hb >> 2) & 0xfffu);
+    const uint64_t base = static_cast<uint64_t>(ha >> 2) | (static_cast<uint64_t>(hb >> 14) << 30);
+    const uint32_t slot = (u >> 6) & 7u;
+    const uint64_t index = base + ((u >> 9) & 0x7fffu);
+    const uint32_t cd = u >> 24;
+    const bool local = (u & kCuLocal) != 0;
+    r.index = index;
+    r.commit = local ? (cd == kCuNoCommit ? 0 : index + cd) : (index >= cd ? index - cd : 0);
+    r.w0 = static_cast<uint64_t>(g) | (static_cast<uint64_t>(slot) << 32) |
+           (static_cast<uint64_t>(local ? RAFTGPU_REC_LOCAL : 0u) << 40);
+    return r;
+}
+
+// apply_kernel for a compact stream: the same three-deep pipeline, one thread per UNIT (header
+// units idle).  A run's header sits in the cache lines its records' neighbours load, so the
+// decode adds L1/L2 hits, not HBM trips.  REJECTs only arrive through ESC units, whose payload
+// (and EXT continuation) is read from the side table in the public layout.
+template <bool kCheckDup>
+__global__ void __launch_bounds__(256, 4)
+apply_compact_kernel(Columns c, CompactSrc src, uint8_t *__restrict__ results, unsigned long long *__restrict__ counters,
+                     uint32_t *__restrict__ touched, uint32_t *__restrict__ dup_count) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t n = src.n_units;
+    uint32_t local[5] = {0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    uint32_t sx_a, sx_b, sx_c;
+    RecRegs rec_a = load_compact(src, src.units, i, n, 0, sx_a);
+    RecRegs rec_b = load_compact(src, src.units, i + stride, n, 0, sx_b);
+    CellRegs cell_a = load_cell(c, rec_a);
+    for (; i < n; i += stride) {
+        const RecRegs rec_c = load_compact(src, src.units, i + 2 * stride, n, 0, sx_c);
+        const CellRegs cell_b = load_cell(c, rec_b);
+        bool skip = false;
+        if constexpr (kCheckDup) {
+            const uint32_t g = static_cast<uint32_t>(rec_a.w0), slot = static_cast<uint32_t>(rec_a.w0 >> 32) & 0xffu;
+            if (!((rec_a.w0 >> 40) & RAFTGPU_REC_EXT) && g < c.cap && slot < kSlots) {
+                const uint32_t bit = 1u << (8 * (g & 3u) + slot);
+                if (atomicOr(&touched[g >> 2], bit) & bit) {  // second record for this cell in one wave
+                    atomicAdd(dup_count, 1u);
+                    skip = true;
+                }
+            }
+        }
+        uint32_t res = 0;
+        if (!skip) {
+            const CellPtrs gp = global_cell_ptrs(c, rec_a);
+            res = apply_one<false>(c, src.side, src.n_side, sx_a, rec_a, cell_a, gp, local);
+        }
+        if (results) results[i] = static_cast<uint8_t>(res);
+        rec_a = rec_b;
+        cell_a = cell_b;
+        rec_b = rec_c;
+        sx_a = sx_b;
+        sx_b = sx_c;
+    }
+    const int which[5] = {kCntRecords, kCntUpdates, kCntRejects, kCntDecrements, kCntNoProgress};
+    block_flush_counts<5>(local, which, counters, nullptr);
+}
+
+// ---------------------------------------------------------------------------
 // step_tile_kernel: apply + recompute FUSED, for batches whose records are in group order.
 //
 // The scatter apply kernel above moves ~12 MB in flight but tops out near 3.7 TB/s: its cell

@@ -1,0 +1,143 @@
+"""The compact stream (include/raftgpu.h "compact stream", raftgpu_pack_compact in csrc/arena.cu,
+load_compact in kernels.cuh) is lossless: decoding the blob the way the kernel does gives back the
+public 24-byte records -- field for field, in order -- for ANY input (hostile values go through
+the ESC side table), and a synthetic multi-raft round shrinks to ~22 bytes per group.  CPU only
+(host functions of the library, no device call)."""
+import numpy as np
+import pytest
+
+from helpers import B
+
+M64 = (1 << 64) - 1
+
+
+def pack(recs):
+    out = np.zeros(B.compact_bound(len(recs)), dtype=np.uint8)
+    nb, units = B.pack_compact(recs, out, want_units=True)
+    return out[:nb], units
+
+
+def normalise(recs):
+    """What the stream promises to carry: main records, a REJECT's EXT right behind it; stray EXT
+    records (no REJECT in front) carry nothing and are dropped."""
+    keep = []
+    for i, r in enumerate(recs):
+        if r["flags"] & B.REC_EXT:
+            if i and (recs[i - 1]["flags"] & B.REC_REJECT) and not (recs[i - 1]["flags"] & B.REC_EXT):
+                keep.append(i)
+            continue
+        keep.append(i)
+    out = recs[keep].copy()
+    out["reserved"] = 0
+    return out
+
+
+def check_round_trip(recs):
+    blob, units = pack(recs)
+    got = B.unpack_compact(blob)
+    want = normalise(recs)
+    # the compact form does not carry `reserved`
+    got["reserved"] = 0
+    # an ESC record is shipped verbatim, reserved included
+    assert len(got) == len(want)
+    for name in ("group", "peer_slot", "flags", "index", "commit"):
+        np.testing.assert_array_equal(got[name], want[name], err_msg=name)
+    hdr = blob[:B.COMPACT_HDR_DTYPE.itemsize].view(B.COMPACT_HDR_DTYPE)[0]
+    assert hdr["total_bytes"] == len(blob)
+    assert hdr["n_records"] == int(np.count_nonzero(~(recs["flags"] & B.REC_EXT).astype(bool)))
+    # unit_of_record: every main record has a unit, units are distinct and increasing
+    main = ~(recs["flags"] & B.REC_EXT).astype(bool)
+    u = units[main].astype(np.int64)
+    assert np.all(np.diff(u) > 0) and (len(u) == 0 or u[-1] < hdr["n_units"])
+    assert np.all(units[~main] == 0xFFFFFFFF)
+    return hdr
+
+
+def test_empty_batch():
+    hdr = check_round_trip(np.zeros(0, dtype=B.APPEND_RESP_DTYPE))
+    assert hdr["n_units"] == 0 and hdr["n_side"] == 0
+
+
+def test_round_trip_random_records():
+    rng = np.random.default_rng(5)
+    edge = [0, 1, 2, 254, 255, 256, 0x7ffe, 0x7fff, 0x8000, (1 << 30) - 1, 1 << 30, (1 << 48) - 1, 1 << 48,
+            (1 << 48) + 0x7fff, (1 << 48) + 0x8000, 1 << 63, M64 - 1, M64]
+    rows = []
+    g = 0
+    for _ in range(3000):
+        g += int(rng.integers(0, 3)) if rng.random() < 0.95 else int(rng.integers(0, 1 << 16))
+        g &= 0xFFFFFFFF
+        base = edge[int(rng.integers(0, len(edge)))] if rng.random() < 0.3 else int(rng.integers(0, 1 << 50))
+        for _ in range(int(rng.integers(1, 12))):   # runs longer than 8 split
+            kind = rng.random()
+            off = int(rng.integers(0, 40000)) if rng.random() < 0.2 else int(rng.integers(0, 64))
+            index = max(0, base - off) if rng.random() < 0.8 else min(M64, base + off)
+            slot = int(rng.integers(0, 8)) if rng.random() < 0.97 else int(rng.integers(8, 256))
+            if kind < 0.7:
+                cd = int(rng.integers(0, 4)) if rng.random() < 0.8 else int(rng.integers(250, 260))
+                commit = max(0, index - cd) if rng.random() < 0.9 else min(M64, index + cd + 1)
+                rows.append((g, slot, 0, 0, index, commit))
+            elif kind < 0.85:
+                cd = int(rng.integers(0, 64)) if rng.random() < 0.8 else int(rng.integers(250, 260))
+                commit = 0 if rng.random() < 0.2 else min(M64, index + cd)
+                if rng.random() < 0.05:
+                    commit = max(1, index - 1)     # a "new last_index" below index: still lossless
+                rows.append((g, slot, B.REC_LOCAL, 0, index, commit))
+            else:
+                rows.append((g, slot, B.REC_REJECT, 0, index, int(rng.integers(0, 1 << 40))))
+                if rng.random() < 0.8:
+                    rows.append((g, slot, B.REC_EXT, 0, int(rng.integers(0, 1 << 40)),
+                                 0 if rng.random() < 0.7 else int(rng.integers(1, 1 << 40))))
+    recs = np.array(rows, dtype=B.APPEND_RESP_DTYPE)
+    hdr = check_round_trip(recs)
+    assert hdr["n_side"] > 0
+
+
+def test_unsorted_and_stray_ext():
+    rng = np.random.default_rng(6)
+    n = 5000
+    recs = np.zeros(n, dtype=B.APPEND_RESP_DTYPE)
+    recs["group"] = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)   # random order, huge ids
+    recs["peer_slot"] = rng.integers(0, 8, n)
+    recs["index"] = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+    recs["commit"] = recs["index"] - np.minimum(recs["index"], rng.integers(0, 4, n).astype(np.uint64))
+    recs["flags"][rng.random(n) < 0.05] = B.REC_EXT   # stray EXT records: dropped
+    check_round_trip(recs)
+
+
+def test_descending_groups_escape():
+    # groups below their block's g_base cannot be named by a header: ESC, still lossless
+    n = 3000
+    recs = np.zeros(n, dtype=B.APPEND_RESP_DTYPE)
+    recs["group"] = np.arange(n, 0, -1)
+    recs["index"] = 1000 + np.arange(n)
+    recs["commit"] = recs["index"]
+    hdr = check_round_trip(recs)
+    assert hdr["n_side"] >= n - 4      # one header per block of units still works
+
+
+def test_synth_round_is_compact():
+    n = 20000
+    s = B.Synth(n, 0xC0FFEE, k_peers=5)
+    for _ in range(3):
+        recs = s.next_round().copy()
+        hdr = check_round_trip(recs)
+        main = int(hdr["n_records"])
+        # 2 header units per group + 1 per record; only REJECTs (2%) escape
+        assert hdr["n_units"] == 2 * n + main
+        rejects = int(np.count_nonzero(recs["flags"] & B.REC_REJECT))
+        assert hdr["n_side"] == 2 * rejects
+        assert hdr["total_bytes"] < 0.48 * 16 * (main + rejects)    # vs the 16-byte packed form
+
+
+def test_joint_round_is_compact():
+    s = B.Synth(5000, 7, k_peers=5, joint=True)
+    hdr = check_round_trip(s.next_round().copy())
+    assert hdr["n_units"] == 2 * 5000 + hdr["n_records"]
+
+
+def test_capacity_errors():
+    recs = B.Synth(100, 1, k_peers=5).next_round().copy()
+    out = np.zeros(128, dtype=np.uint8)
+    with pytest.raises(RuntimeError):
+        B.pack_compact(recs, out)

@@ -511,6 +511,78 @@ def test_zero_copy_packed_submission_and_duplicate_detection():
     arena.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,joint", [(100_003, False), (40_000, True)])
+def test_compact_stream_submission_vs_oracle(n, joint):
+    """raftgpu_step_begin_compact: the 4-byte-unit stream (group runs + ESC side table) goes over PCIe
+    as is and apply_compact_kernel decodes it; columns, bitmap, committed and the per-record result
+    bytes equal the oracle's; hostile values take the ESC path; duplicates are caught on the device."""
+    synth = B.Synth(n, 0x5EED0009, joint=joint)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    cap_bytes = B.compact_bound(8 * n)
+    bufs = [arena.host_alloc_bytes(cap_bytes) for _ in range(2)]
+    for rnd in range(4):
+        recs = synth.next_round().copy()
+        nb, units = B.pack_compact(recs, bufs[rnd % 2], want_units=True)
+        assert nb < 0.5 * 16 * len(recs)
+        arena.step_begin_compact(bufs[rnd % 2], nb, B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS)
+        r = arena.step_wait()
+        want_res = O.arena_apply(ref, recs, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        main = (recs["flags"] & B.REC_EXT) == 0
+        assert r.n_advanced == want_adv and r.n_duplicates == 0 and r.h2d_bytes == nb
+        assert r.n_records == np.count_nonzero(main)
+        bm, com = arena.step_results(n)
+        assert np.array_equal(bm, want_bm[: len(bm)])
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+        res = arena.slot_results()
+        assert np.array_equal(res[units[main]], want_res[main]), "per-record results differ"
+        other = np.ones(len(res), dtype=bool)
+        other[units[main]] = False
+        assert not res[other].any()
+        assert_columns_equal(arena.read_columns(n), ref, n, f"compact round {rnd}")
+    # hostile values: huge indices, commit above index, lagging peers, LOCAL with commit < index
+    odd = np.zeros(8, dtype=B.APPEND_RESP_DTYPE)
+    odd[0] = (5, 1, 0, 0, 10, 1 << 40)
+    odd[1] = (6, 2, 0, 0, (1 << 50) + 7, 3)
+    odd[2] = (6, 3, 0, 0, (1 << 50) + 7 - 40000, (1 << 50))
+    odd[3] = (7, 0, B.REC_LOCAL, 0, 9, 4)
+    odd[4] = (8, 1, 0, 0, (1 << 63) + 11, (1 << 63) + 2)
+    odd[5] = (9, 9, 0, 0, 77, 70)                         # no such peer slot: NO_PROGRESS
+    odd[6] = (n - 1, 7, 0, 0, 77, 70)                     # a slot the group has no peer in
+    odd[7] = (12, 1, 0, 0, int(ref.matched[1, 12]) + 300, int(ref.matched[1, 12]))   # commit delta 300
+    nb, units = B.pack_compact(odd, bufs[0], want_units=True)
+    arena.step_begin_compact(bufs[0], nb, B.STEP_READ_RESULTS)
+    arena.step_wait()
+    want_res = O.arena_apply(ref, odd, mode=0)
+    O.arena_recompute(ref)
+    assert np.array_equal(arena.slot_results()[units], want_res)
+    assert_columns_equal(arena.read_columns(n), ref, n, "hostile values")
+    # an empty batch still recomputes
+    nb, _ = B.pack_compact(np.zeros(0, dtype=B.APPEND_RESP_DTYPE), bufs[1])
+    arena.step_begin_compact(bufs[1], nb, 0)
+    r = arena.step_wait()
+    assert r.n_records == 0 and r.n_advanced == 0
+    # two records for one cell in one batch: detected by the kernel
+    dup = np.zeros(2, dtype=B.APPEND_RESP_DTYPE)
+    dup[0] = (11, 1, 0, 0, int(ref.matched[1, 11]) + 5, 0)
+    dup[1] = (11, 1, 0, 0, int(ref.matched[1, 11]) + 9, 0)
+    nb, _ = B.pack_compact(dup, bufs[1])
+    arena.step_begin_compact(bufs[1], nb, 0)
+    r = arena.step_wait(check=False)
+    assert r.status == B.ERR_INVALID and r.n_duplicates == 1
+    # a mangled header is refused before anything is submitted
+    bad = bufs[0]
+    bad[:4] = 0
+    with pytest.raises(RuntimeError):
+        arena.step_begin_compact(bad, 64, 0)
+    arena.close()
+
+
 def _fused_round(arena, n, recs, ref, pk, d_bufs):
     """One fused step (raftgpu_step_sorted_device) on `recs` (group order) checked against the oracle."""
     k = arena.pack_records(recs, pk)

@@ -349,7 +349,10 @@ int32_t raftgpu_apply_device_packed(raftgpu_arena *arena, void *stream, const vo
  * (raftgpu_tile_index builds and validates it on the host).  One wave per call, like
  * raftgpu_apply_device; processes all allocated groups [0, hi).  A record found outside its tile
  * is not applied and reported as RAFTGPU_RES_NO_PROGRESS.  Asynchronous on `stream`. */
+#ifndef RAFTGPU_TILE_GROUPS
 #define RAFTGPU_TILE_GROUPS 256
+#endif
+uint32_t raftgpu_tile_groups(void); /* the value the library was built with */
 int32_t raftgpu_step_sorted_device(raftgpu_arena *arena, void *stream, const void *d_packed_records,
                                    uint64_t n_packed, const uint32_t *d_tile_off, uint8_t *d_results,
                                    uint32_t *d_adv_bitmap, uint64_t *d_commit_out);
@@ -400,20 +403,23 @@ int32_t raftgpu_step_begin_packed(raftgpu_arena *arena, const raftgpu_packed_rec
  * packed records: the records of one group (consecutive in the input, as a multi-raft ready
  * loop produces them) form a RUN
  *      [HDR_A][HDR_B] rec rec rec ...          (at most 8 units after the header)
- * whose header names the group and a 48-bit base index, and each record is a slot, a 15-bit
+ * whose header names the group and a 48-bit base index, and each record is a slot, a 14-bit
  * index delta above the base and an 8-bit commit delta:
- *      unit & 3 == 0  REC    [2] LOCAL  [3,6) back  [6,9) peer slot  [9,24) index - base
+ *      unit & 3 == 0  REC    [2] LOCAL  [3,6) back  [6,9) peer slot  [9] REJECT  [10,24) index - base
  *                            [24,32) message: index - commit; LOCAL: commit - index (255 = none)
- *                            (the run's header sits at unit positions i-back-2 and i-back-1)
+ *                            (the run's header sits at unit positions i-back-2 and i-back-1; a
+ *                            REJECT is followed by a payload unit with its next_probe_index hint)
  *      unit & 3 == 1  HDR_A  [2,32) base bits [0,30)
  *      unit & 3 == 2  HDR_B  [2,14) group - g_base[block of HDR_A]   [14,32) base bits [30,48)
- *      unit & 3 == 3  ESC    [2,32) index into the side table (0x3fffffff = padding, a no-op)
+ *      unit & 3 == 3  ESC    [2,32) < 0x1fffffff: index into the side table; == 0x1fffffff: padding;
+ *                            bit 31 set: the payload of the REJECT in front, [2,31) = hint - index (signed)
  * g_base[] holds one group id per block of RAFTGPU_COMPACT_BLOCK units.  Whatever does not fit
- * (every REJECT with its EXT, an index more than 32767 below the run's largest, a commit
- * delta above 254, a base above 2^48, a group more than 4095 above its block's g_base) is an ESC
- * unit pointing at the full 24-byte public record in the side table -- the format is lossless
- * for ANY input, only less compact for hostile ones.  A 5-peer round is ~22 bytes per group
- * instead of ~57.  The blob is position independent: header, g_base[], units[], side[].
+ * (a REJECT that asks for a snapshot, an index more than 16383 below the run's largest, a commit
+ * delta above 254, a base above 2^48, a group more than 4095 above its block's g_base, flag bits
+ * the format does not know) is an ESC unit pointing at the full 24-byte public record (and its
+ * EXT) in the side table -- the format is lossless for ANY input, only less compact for hostile
+ * ones.  A 5-peer round is ~22 bytes per group instead of ~57.  The blob is position
+ * independent: header, g_base[], units[] (padded to 16 bytes), side[].
  * Same contract as raftgpu_step_begin_packed: pinned buffer (raftgpu_host_alloc), ONE wave
  * checked on the GPU, buffer untouched until the step's raftgpu_step_wait returns.  Result
  * bytes (RAFTGPU_STEP_READ_RESULTS) are per UNIT; raftgpu_pack_compact can report the unit
@@ -428,8 +434,17 @@ typedef struct raftgpu_compact_hdr {
     uint64_t n_records; /* public records represented (EXT continuations not counted) */
     uint64_t off_blocks, off_units, off_side; /* byte offsets from the start of the blob, 16-byte aligned */
     uint64_t total_bytes;
-    uint64_t reserved;
+    uint32_t flags;     /* RAFTGPU_COMPACT_TILEABLE */
+    uint32_t reserved;
 } raftgpu_compact_hdr;
+/* Set by raftgpu_pack_compact when the groups of the runs ascend and every run has a header
+ * (records of one group contiguous, groups in increasing order, no group too far from its
+ * block's g_base): the fused tile kernel can then take the stream -- and, because one thread
+ * walks a group's records in order, such a stream may hold SEVERAL records per (group, peer). */
+#define RAFTGPU_COMPACT_TILEABLE 0x1u
+/* ... and no (group, peer) cell occurs twice: the fused kernel may then use one thread per unit
+ * (faster than the ordered per-group walk); the kernel still verifies it. */
+#define RAFTGPU_COMPACT_ONE_WAVE 0x2u
 /* Upper bound of the blob size for n public records (EXT records included in n). */
 uint64_t raftgpu_compact_bound(uint64_t n);
 /* records[0..n) -> blob at out (out_capacity bytes; any host memory, pinned for the zero-copy
@@ -439,6 +454,22 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
                              uint64_t *out_bytes, uint32_t *unit_of_record);
 int32_t raftgpu_step_begin_compact(raftgpu_arena *arena, const void *pinned_blob, uint64_t blob_bytes,
                                    uint32_t flags);
+/* The same step for a blob that already sits in device memory (hdr = a host copy of its
+ * header): raftgpu_compact_tile_index_device builds the tile table in d_tile_off -- room for
+ * 3 * (ceil(n_groups / RAFTGPU_TILE_GROUPS) + 2) + 2 u32: the first unit of every tile, then each
+ * tile's group-id bases -- and bumps *d_bad if the stream is not tileable after all, then
+ * raftgpu_step_compact_device runs ONE fused kernel: the records of every tile applied to
+ * its rows in shared memory, Raft::maybe_commit for its groups, rows stored back. */
+int32_t raftgpu_compact_tile_index_device(raftgpu_arena *arena, void *stream, const void *d_blob,
+                                          const raftgpu_compact_hdr *hdr, uint32_t *d_tile_off, uint32_t *d_bad);
+/* flags: RAFTGPU_COMPACT_STEP_ORDERED forces the per-group walk (records of a cell applied in stream
+ * order); otherwise a ONE_WAVE stream gets one thread per unit, and d_dup_count (nullable) is bumped
+ * for every record that turns out to be the second one on its cell (such a record is not applied). */
+#define RAFTGPU_COMPACT_STEP_ORDERED 0x1u
+int32_t raftgpu_step_compact_device(raftgpu_arena *arena, void *stream, const void *d_blob,
+                                    const raftgpu_compact_hdr *hdr, const uint32_t *d_tile_off, uint8_t *d_results,
+                                    uint32_t *d_adv_bitmap, uint64_t *d_commit_out, uint32_t *d_dup_count,
+                                    uint32_t flags);
 /* Result bytes of the last completed ZERO-COPY step (packed: one per packed record, compact:
  * one per unit; 0 for EXT payloads / headers), valid until the next raftgpu_step_wait.  Needs
  * RAFTGPU_STEP_READ_RESULTS.  raft.rs:1663-1743: what handle_append_response decided per message. */

@@ -128,7 +128,8 @@ def pack_compact(recs: np.ndarray, out: np.ndarray, want_units: bool = False):
 
 COMPACT_HDR_DTYPE = np.dtype([("magic", "<u4"), ("n_units", "<u4"), ("n_blocks", "<u4"), ("n_side", "<u4"),
                               ("n_records", "<u8"), ("off_blocks", "<u8"), ("off_units", "<u8"),
-                              ("off_side", "<u8"), ("total_bytes", "<u8"), ("reserved", "<u8")])
+                              ("off_side", "<u8"), ("total_bytes", "<u8"), ("flags", "<u4"), ("reserved", "<u4")])
+COMPACT_TILEABLE, COMPACT_ONE_WAVE = 0x1, 0x2
 
 
 def unpack_compact(blob: np.ndarray) -> np.ndarray:
@@ -145,7 +146,7 @@ def unpack_compact(blob: np.ndarray) -> np.ndarray:
         kind = u & 3
         if kind == 3:
             k = u >> 2
-            if k < ns:
+            if k < 0x1fffffff and k < ns:     # (payload units and padding carry no record of their own)
                 out.append(tuple(side[k]))
                 if (side[k]["flags"] & REC_REJECT) and k + 1 < ns and (side[k + 1]["flags"] & REC_EXT):
                     out.append(tuple(side[k + 1]))
@@ -158,11 +159,18 @@ def unpack_compact(blob: np.ndarray) -> np.ndarray:
         assert ha & 3 == 1 and hb & 3 == 2
         g = int(g_base[hpos // 2048]) + ((hb >> 2) & 0xfff)
         base = (ha >> 2) | ((hb >> 14) << 30)
-        index = base + ((u >> 9) & 0x7fff)
+        index = base + ((u >> 10) & 0x3fff)
         cd = u >> 24
-        local = bool(u & 4)
+        local, reject = bool(u & 4), bool(u & (1 << 9))
         commit = (0 if cd == 255 else index + cd) if local else index - cd
-        out.append((g, (u >> 6) & 7, REC_LOCAL if local else 0, 0, index, commit))
+        out.append((g, (u >> 6) & 7, REC_LOCAL if local else (REC_REJECT if reject else 0), 0, index, commit))
+        if reject:
+            pl = int(units[i + 1])
+            assert pl & 3 == 3 and (pl >> 2) & (1 << 29)
+            d = (pl >> 2) & ((1 << 29) - 1)
+            if d >= 1 << 28:
+                d -= 1 << 29
+            out.append((g, (u >> 6) & 7, REC_EXT, 0, (index + d) & ((1 << 64) - 1), 0))
     return np.array(out, dtype=APPEND_RESP_DTYPE)
 
 
@@ -218,6 +226,7 @@ def lib() -> C.CDLL:
             "raftgpu_apply_device_packed": ([vp, vp, vp, u64, vp], i32),
             "raftgpu_step_sorted_device": ([vp, vp, vp, u64, vp, vp, vp, vp], i32),
             "raftgpu_tile_index": ([vp, u64, u32, vp, u64], i32),
+            "raftgpu_tile_groups": ([], u32),
             "raftgpu_enqueue_append_resp": ([vp, u32, vp, u64], i32),
             "raftgpu_enqueue_bulk": ([vp, vp, u64, u32], i32),
             "raftgpu_step_begin": ([vp, u32], i32),
@@ -227,6 +236,8 @@ def lib() -> C.CDLL:
             "raftgpu_pack_compact": ([vp, u64, vp, u64, C.POINTER(u64), vp], i32),
             "raftgpu_step_begin_compact": ([vp, vp, u64, u32], i32),
             "raftgpu_step_slot_results": ([vp, C.POINTER(vp), C.POINTER(u64)], i32),
+            "raftgpu_compact_tile_index_device": ([vp, vp, vp, vp, vp, vp], i32),
+            "raftgpu_step_compact_device": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, u32], i32),
             "raftgpu_host_alloc": ([vp, u64, C.POINTER(vp)], i32),
             "raftgpu_host_free": ([vp, vp], i32),
             "raftgpu_step_wait": ([vp, C.POINTER(StepResult)], i32),
@@ -263,9 +274,14 @@ def strerror(status: int) -> str:
 TILE_GROUPS = 256
 
 
+def tile_groups() -> int:
+    return int(lib().raftgpu_tile_groups())
+
+
 def tile_index(packed: np.ndarray, n_packed: int, n_groups: int) -> np.ndarray:
     """raftgpu_tile_index: first packed record of every 256-group tile (+ the end)."""
-    n_tiles = (n_groups + TILE_GROUPS - 1) // TILE_GROUPS
+    tg = int(lib().raftgpu_tile_groups())
+    n_tiles = (n_groups + tg - 1) // tg
     out = np.zeros(n_tiles + 1, dtype=np.uint32)
     rc = lib().raftgpu_tile_index(packed.ctypes.data, n_packed, n_groups, out.ctypes.data, len(out))
     if rc != OK:
@@ -587,6 +603,17 @@ class Arena:
         p = C.c_void_p()
         self._ck(self._L.raftgpu_host_alloc(self._h, n_bytes, C.byref(p)), "host_alloc")
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n_bytes,))
+
+    def compact_tile_index_device(self, d_blob, hdr_blob: np.ndarray, d_tile_off, d_bad, stream=None):
+        """hdr_blob: host bytes that start with the blob's raftgpu_compact_hdr."""
+        self._ck(self._L.raftgpu_compact_tile_index_device(self._h, stream, d_blob, hdr_blob.ctypes.data, d_tile_off,
+                                                           d_bad), "compact_tile_index_device")
+
+    def step_compact_device(self, d_blob, hdr_blob: np.ndarray, d_tile_off, stream=None, d_results=None, d_adv=None,
+                            d_commit=None, d_dup=None, ordered=False):
+        self._ck(self._L.raftgpu_step_compact_device(self._h, stream, d_blob, hdr_blob.ctypes.data, d_tile_off,
+                                                     d_results, d_adv, d_commit, d_dup, 1 if ordered else 0),
+                 "step_compact_device")
 
     def host_free(self, buf: np.ndarray):
         self._ck(self._L.raftgpu_host_free(self._h, buf.ctypes.data), "host_free")

@@ -72,6 +72,7 @@ struct StagingSet {
     uint32_t *d_adv_bitmap = nullptr;
     uint64_t *d_commit_out = nullptr;
     uint8_t *d_results = nullptr;
+    uint32_t *d_tile_off = nullptr;  // [cap / kFTile + 2]: tile index of a tileable compact stream
     uint32_t *d_step_adv = nullptr;  // [0] advanced groups of the step, [1] duplicate records (zero-copy)
     uint32_t *d_touched = nullptr;   // [cap/4] zero-copy steps: one bit per (group, slot)
     // sync
@@ -390,6 +391,7 @@ void free_set(StagingSet &s) {
     cudaFree(s.d_adv_bitmap);
     cudaFree(s.d_commit_out);
     cudaFree(s.d_results);
+    cudaFree(s.d_tile_off);
     cudaFree(s.d_step_adv);
     cudaFree(s.d_touched);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
@@ -486,17 +488,38 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
                               static_cast<int>(a->tma_smem)));
     TRYC(cudaFuncSetAttribute(recompute_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               static_cast<int>(a->tma_smem)));
-    a->tile_smem = 226u * 1024u;
+    a->tile_smem = 227u * 1024u - 512u;  // 227 KB per CTA minus the kernels' static shared memory
 #define RAFTGPU_TILE_ATTR(CT, NG)                                                                             \
     TRYC(cudaFuncSetAttribute(step_tile_kernel<false, CT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                               static_cast<int>(a->tile_smem)));                                              \
     TRYC(cudaFuncSetAttribute(step_tile_kernel<true, CT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                               static_cast<int>(a->tile_smem)))
+#if RAFTGPU_TILE_GROUPS == 128
+    RAFTGPU_TILE_ATTR(128, 3);
+    RAFTGPU_TILE_ATTR(128, 4);
+    RAFTGPU_TILE_ATTR(128, 6);
+    RAFTGPU_TILE_ATTR(256, 2);
+    RAFTGPU_TILE_ATTR(256, 3);
+#else
     RAFTGPU_TILE_ATTR(256, 1);
     RAFTGPU_TILE_ATTR(256, 2);
     RAFTGPU_TILE_ATTR(256, 3);
     RAFTGPU_TILE_ATTR(512, 1);
+#endif
 #undef RAFTGPU_TILE_ATTR
+#define RAFTGPU_CTILE_ATTR(NG)                                                                                   \
+    TRYC(cudaFuncSetAttribute(step_tile_compact_kernel<false, NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                              static_cast<int>(a->tile_smem)));                                                      \
+    TRYC(cudaFuncSetAttribute(step_tile_compact_kernel<true, NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                              static_cast<int>(a->tile_smem)));                                                      \
+    TRYC(cudaFuncSetAttribute(step_tile_compact_kernel<false, NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                              static_cast<int>(a->tile_smem)));                                                      \
+    TRYC(cudaFuncSetAttribute(step_tile_compact_kernel<true, NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                              static_cast<int>(a->tile_smem)))
+    RAFTGPU_CTILE_ATTR(1);
+    RAFTGPU_CTILE_ATTR(2);
+    RAFTGPU_CTILE_ATTR(3);
+#undef RAFTGPU_CTILE_ATTR
     {
         const char *e = getenv("RAFTGPU_TMA");
         a->use_tma = e && e[0] == '1';
@@ -553,6 +576,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
         TRY(dev_alloc(a, &s.d_adv_bitmap, a->cap / 32));
         TRY(dev_alloc(a, &s.d_commit_out, a->cap));
         TRY(dev_alloc(a, &s.d_results, 4 * rec_total));
+        TRY(dev_alloc(a, &s.d_tile_off, 3 * (a->cap / kFTile + 2) + 2));
         TRY(dev_alloc(a, &s.d_step_adv, 4));
         TRY(dev_alloc(a, &s.d_touched, a->cap / 4));
         TRYC(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
@@ -1057,15 +1081,174 @@ int32_t raftgpu_step_sorted_device(raftgpu_arena *a, void *stream, const void *d
         else                                                                               \
             step_tile_kernel<false, CT, NG><<<blocks, CT * NG + 64, smem, st>>>(a->cols, t); \
     } while (0)
+#if RAFTGPU_TILE_GROUPS == 128
+    switch (variant) {
+    case 1283: RAFTGPU_LAUNCH_TILE(128, 3); break;
+    case 1286: RAFTGPU_LAUNCH_TILE(128, 6); break;
+    case 2562: RAFTGPU_LAUNCH_TILE(256, 2); break;
+    case 2563: RAFTGPU_LAUNCH_TILE(256, 3); break;
+    default: RAFTGPU_LAUNCH_TILE(128, 4); break;
+    }
+#else
     switch (variant) {
     case 2561: RAFTGPU_LAUNCH_TILE(256, 1); break;
     case 2563: RAFTGPU_LAUNCH_TILE(256, 3); break;
     case 5121: RAFTGPU_LAUNCH_TILE(512, 1); break;
     default: RAFTGPU_LAUNCH_TILE(256, 2); break;
     }
+#endif
 #undef RAFTGPU_LAUNCH_TILE
     CKL(a);
     return RAFTGPU_OK;
+}
+
+namespace {
+
+__global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
+CompactSrc compact_src(const void *d_blob, const raftgpu_compact_hdr &h) {
+    const uint8_t *b = static_cast<const uint8_t *>(d_blob);
+    CompactSrc src;
+    src.units = reinterpret_cast<const uint32_t *>(b + h.off_units);
+    src.g_base = reinterpret_cast<const uint32_t *>(b + h.off_blocks);
+    src.side = reinterpret_cast<const raftgpu_append_resp *>(b + h.off_side);
+    src.n_units = h.n_units;
+    src.n_side = h.n_side;
+    return src;
+}
+
+bool compact_hdr_ok(const raftgpu_compact_hdr &h, uint64_t blob_bytes) {
+    const uint64_t need_blocks = (static_cast<uint64_t>(h.n_units) + RAFTGPU_COMPACT_BLOCK - 1) / RAFTGPU_COMPACT_BLOCK;
+    return h.magic == RAFTGPU_COMPACT_MAGIC && h.total_bytes <= blob_bytes && h.n_blocks >= need_blocks &&
+           !(h.off_blocks & 3u) && !(h.off_units & 15u) && !(h.off_side & 15u) &&
+           h.off_blocks + 4ull * h.n_blocks <= h.total_bytes &&
+           h.off_units + 4ull * ((static_cast<uint64_t>(h.n_units) + 3u) & ~3ull) <= h.total_bytes &&
+           h.off_side + 24ull * h.n_side <= h.total_bytes;
+}
+
+// the tile table is one device buffer: u32 tile_off[n_tiles + 1], padding to 8 bytes, uint2 tile_gb[n_tiles]
+inline uint2 *tile_gb_of(uint32_t *d_tile_off, uint32_t n_tiles) {
+    return reinterpret_cast<uint2 *>(d_tile_off + ((n_tiles + 2u) & ~1u));
+}
+inline const uint2 *tile_gb_of_c(const uint32_t *d_tile_off, uint32_t n_tiles) {
+    return reinterpret_cast<const uint2 *>(d_tile_off + ((n_tiles + 2u) & ~1u));
+}
+
+// tile_off[0..n_tiles] of a tileable stream over [0, hi): everything = n_units, then the headers write
+int32_t launch_compact_tile_index(raftgpu_arena *a, cudaStream_t st, const CompactSrc &src, uint32_t *d_tile_off,
+                                  uint32_t *d_bad) {
+    const uint32_t n_tiles = div_up(a->hi, kFTile);
+    fill_u32_kernel<<<div_up(n_tiles + 1, 256), 256, 0, st>>>(d_tile_off, n_tiles + 1, src.n_units);
+    CKL(a);
+    if (src.n_units) {
+        const uint32_t blocks = std::min<uint32_t>(div_up(src.n_units, 256), 8u * static_cast<uint32_t>(a->sm_count));
+        compact_tile_index_kernel<<<blocks, 256, 0, st>>>(src, a->hi, d_tile_off, d_bad);
+        CKL(a);
+    }
+    // behind the offsets (8-byte aligned): the g_base pair of every tile
+    compact_tile_gb_kernel<<<div_up(n_tiles, 256), 256, 0, st>>>(src, n_tiles, d_tile_off, tile_gb_of(d_tile_off, n_tiles));
+    CKL(a);
+    return RAFTGPU_OK;
+}
+
+// Can the fused compact kernel run this arena's configuration?  (stages that fit in shared memory)
+bool ctile_plan(const raftgpu_arena *a, bool simple5, uint32_t *hint_out, uint32_t *unit_cap_out, int *stages_out,
+                int *ng_out) {
+    static const int ng_env = getenv("RAFTGPU_CTILE_GROUPS") ? atoi(getenv("RAFTGPU_CTILE_GROUPS")) : 3;
+    static const int cap_env = getenv("RAFTGPU_CTILE_UNITCAP") ? atoi(getenv("RAFTGPU_CTILE_UNITCAP")) : 1536;
+    const uint32_t hint = simple5 ? 0x1fu : (a->voter_hint & 0xffu);
+    const uint32_t H = static_cast<uint32_t>(__builtin_popcount(hint));
+    const int ng = std::max(1, std::min(3, ng_env));
+    uint32_t unit_cap = static_cast<uint32_t>(std::max(64, cap_env)) & ~3u;
+    if (H == 0) return false;
+    int stages = 0;
+    for (int s = kFMaxStages; s >= 2; s--)
+        if (ctile_smem_bytes(H, unit_cap, s, ng) <= a->tile_smem) {
+            stages = s;
+            break;
+        }
+    if (stages < 2) return false;
+    *hint_out = hint;
+    *unit_cap_out = unit_cap;
+    *stages_out = stages;
+    *ng_out = ng;
+    return true;
+}
+
+int32_t launch_tile_compact(raftgpu_arena *a, cudaStream_t st, const CompactSrc &src, const uint32_t *d_tile_off,
+                            uint8_t *d_results, uint32_t *d_adv_bitmap, uint64_t *d_commit_out, uint32_t *d_step_adv,
+                            bool ordered, uint32_t *d_dup_count) {
+    const uint32_t hi = a->hi;
+    if (hi == 0) return RAFTGPU_OK;
+    const bool simple5 = range_simple5(a, 0, hi) && !a->force_general;
+    uint32_t hint = 0, unit_cap = 0;
+    int stages = 0, ng = 0;
+    if (!ctile_plan(a, simple5, &hint, &unit_cap, &stages, &ng))
+        return fail(a, RAFTGPU_ERR_INVALID, "configuration too wide for the fused tile kernel");
+    const uint32_t H = static_cast<uint32_t>(__builtin_popcount(hint));
+    CTileArgs t{};
+    t.src = src;
+    t.tile_off = d_tile_off;
+    t.tile_gb = tile_gb_of_c(d_tile_off, div_up(hi, kFTile));
+    t.n_groups = hi;
+    t.hint = hint;
+    t.n_stages = stages;
+    t.unit_cap = unit_cap;
+    t.results = d_results;
+    t.adv_bitmap = d_adv_bitmap;
+    t.commit_out = d_commit_out;
+    t.step_advanced = d_step_adv;
+    t.counters = a->d_counters;
+    static const bool tile_debug = getenv("RAFTGPU_TILE_DEBUG") != nullptr;
+    t.dbg = tile_debug ? a->d_counters + kCntCount : nullptr;
+    t.dup_count = ordered ? nullptr : d_dup_count;
+    const uint32_t n_tiles = div_up(hi, kFTile);
+    const uint32_t blocks = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(a->sm_count));
+    const size_t smem = ctile_smem_bytes(H, unit_cap, stages, ng);
+#define RAFTGPU_LAUNCH_CTILE(NG)                                                                                \
+    do {                                                                                                        \
+        if (simple5 && ordered)                                                                                 \
+            step_tile_compact_kernel<true, NG, true><<<blocks, kFTile * NG + 64, smem, st>>>(a->cols, t);       \
+        else if (simple5)                                                                                       \
+            step_tile_compact_kernel<true, NG, false><<<blocks, kFTile * NG + 64, smem, st>>>(a->cols, t);      \
+        else if (ordered)                                                                                       \
+            step_tile_compact_kernel<false, NG, true><<<blocks, kFTile * NG + 64, smem, st>>>(a->cols, t);      \
+        else                                                                                                    \
+            step_tile_compact_kernel<false, NG, false><<<blocks, kFTile * NG + 64, smem, st>>>(a->cols, t);     \
+    } while (0)
+    switch (ng) {
+    case 1: RAFTGPU_LAUNCH_CTILE(1); break;
+    case 3: RAFTGPU_LAUNCH_CTILE(3); break;
+    default: RAFTGPU_LAUNCH_CTILE(2); break;
+    }
+#undef RAFTGPU_LAUNCH_CTILE
+    CKL(a);
+    return RAFTGPU_OK;
+}
+
+}  // namespace
+
+int32_t raftgpu_compact_tile_index_device(raftgpu_arena *a, void *stream, const void *d_blob,
+                                          const raftgpu_compact_hdr *hdr, uint32_t *d_tile_off, uint32_t *d_bad) {
+    if (!a || !d_blob || !hdr || !d_tile_off || !d_bad) return RAFTGPU_ERR_INVALID;
+    if (!compact_hdr_ok(*hdr, hdr->total_bytes)) return fail(a, RAFTGPU_ERR_INVALID, "malformed compact batch header");
+    CK(a, cudaSetDevice(a->device));
+    return launch_compact_tile_index(a, pick_stream(a, stream), compact_src(d_blob, *hdr), d_tile_off, d_bad);
+}
+
+int32_t raftgpu_step_compact_device(raftgpu_arena *a, void *stream, const void *d_blob, const raftgpu_compact_hdr *hdr,
+                                    const uint32_t *d_tile_off, uint8_t *d_results, uint32_t *d_adv_bitmap,
+                                    uint64_t *d_commit_out, uint32_t *d_dup_count, uint32_t flags) {
+    if (!a || !d_blob || !hdr || !d_tile_off) return RAFTGPU_ERR_INVALID;
+    if (!compact_hdr_ok(*hdr, hdr->total_bytes)) return fail(a, RAFTGPU_ERR_INVALID, "malformed compact batch header");
+    if (!(hdr->flags & RAFTGPU_COMPACT_TILEABLE))
+        return fail(a, RAFTGPU_ERR_INVALID, "the stream is not tileable (groups not ascending, or a run without a header)");
+    CK(a, cudaSetDevice(a->device));
+    const bool ordered = (flags & RAFTGPU_COMPACT_STEP_ORDERED) || !(hdr->flags & RAFTGPU_COMPACT_ONE_WAVE);
+    return launch_tile_compact(a, pick_stream(a, stream), compact_src(d_blob, *hdr), d_tile_off, d_results, d_adv_bitmap,
+                               d_commit_out, nullptr, ordered, d_dup_count);
 }
 
 int32_t raftgpu_tile_index(const raftgpu_packed_rec *packed, uint64_t n_packed, uint32_t n_groups, uint32_t *out,
@@ -1349,16 +1532,26 @@ static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ex
     uint8_t *d_res = (flags & RAFTGPU_STEP_READ_RESULTS) ? s.d_results : nullptr;
     CK(a, cudaMemsetAsync(s.d_step_adv, 0, 8, a->s_compute));
     int32_t rc = RAFTGPU_OK;
+    bool fused = false;  // the fused tile kernel did apply AND recompute
     if (cb) {
-        CK(a, cudaMemsetAsync(s.d_touched, 0, a->cap, a->s_compute));
-        if (wave0) {
-            const uint8_t *d_blob = reinterpret_cast<const uint8_t *>(s.d_recs);
-            CompactSrc src;
-            src.units = reinterpret_cast<const uint32_t *>(d_blob + cb->off_units);
-            src.g_base = reinterpret_cast<const uint32_t *>(d_blob + cb->off_blocks);
-            src.side = reinterpret_cast<const raftgpu_append_resp *>(d_blob + cb->off_side);
-            src.n_units = cb->n_units;
-            src.n_side = cb->n_side;
+        const CompactSrc src = compact_src(s.d_recs, *cb);
+        static const bool force_scatter = getenv("RAFTGPU_COMPACT_SCATTER") != nullptr;
+        uint32_t ph = 0, pc = 0;
+        int ps = 0, pn = 0;
+        fused = (cb->flags & RAFTGPU_COMPACT_TILEABLE) && !force_scatter && a->hi > 0 &&
+                ctile_plan(a, range_simple5(a, 0, a->hi) && !a->force_general, &ph, &pc, &ps, &pn);
+        if (fused) {
+            // a tileable stream: tile index (d_step_adv[1] counts violations of the promise), then ONE kernel
+            if (d_res && wave0) CK(a, cudaMemsetAsync(d_res, 0, wave0, a->s_compute));  // header units get no result
+            rc = launch_compact_tile_index(a, a->s_compute, src, s.d_tile_off, s.d_step_adv + 1);
+            if (rc != RAFTGPU_OK) return rc;
+            static const bool force_ordered = getenv("RAFTGPU_COMPACT_ORDERED") != nullptr;
+            rc = launch_tile_compact(a, a->s_compute, src, s.d_tile_off, d_res, s.d_adv_bitmap,
+                                     (flags & RAFTGPU_STEP_READ_COMMITTED) ? s.d_commit_out : nullptr, s.d_step_adv,
+                                     force_ordered || !(cb->flags & RAFTGPU_COMPACT_ONE_WAVE), s.d_step_adv + 1);
+            if (rc != RAFTGPU_OK) return rc;
+        } else if (wave0) {
+            CK(a, cudaMemsetAsync(s.d_touched, 0, a->cap, a->s_compute));
             const uint32_t blocks = std::min<uint32_t>(div_up(wave0, 256), static_cast<uint32_t>(a->grid_apply));
             apply_compact_kernel<true><<<blocks, 256, 0, a->s_compute>>>(a->cols, src, d_res, a->d_counters, s.d_touched,
                                                                         s.d_step_adv + 1);
@@ -1383,10 +1576,12 @@ static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ex
         woff += wsz;
     }
     const uint32_t hi = a->hi;
-    rc = launch_recompute(a, a->s_compute, 0, hi, a->voter_hint, s.d_adv_bitmap,
-                          (flags & RAFTGPU_STEP_READ_COMMITTED) ? s.d_commit_out : nullptr, nullptr, nullptr,
-                          s.d_step_adv);
-    if (rc != RAFTGPU_OK) return rc;
+    if (!fused) {
+        rc = launch_recompute(a, a->s_compute, 0, hi, a->voter_hint, s.d_adv_bitmap,
+                              (flags & RAFTGPU_STEP_READ_COMMITTED) ? s.d_commit_out : nullptr, nullptr, nullptr,
+                              s.d_step_adv);
+        if (rc != RAFTGPU_OK) return rc;
+    }
     CK(a, cudaEventRecord(s.ev_compute, a->s_compute));
 
     // D2H of the results
@@ -1426,6 +1621,8 @@ static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ex
     a->fill = other;
     return RAFTGPU_OK;
 }
+
+uint32_t raftgpu_tile_groups(void) { return RAFTGPU_TILE_GROUPS; }
 
 int32_t raftgpu_step_begin(raftgpu_arena *a, uint32_t flags) { return step_submit(a, flags, nullptr, 0); }
 
@@ -1478,6 +1675,9 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
     std::vector<raftgpu_append_resp> side;
     uint64_t nu = 0, n_rec = 0;
     uint64_t blocks_set = 0;  // g_base[b] is defined for b < blocks_set
+    bool tileable = true, have_prev_group = false;  // groups ascend and every run has a header
+    bool one_wave = true;                           // no (group, peer) cell twice (meaningful when tileable)
+    uint32_t prev_group = 0, seen_slots = 0;
     auto esc = [&](uint64_t i) -> bool {  // record i (and its EXT) to the side table, one ESC unit
         if (nu >= unit_cap || side.size() >= kCuPad - 2) return false;
         units[nu] = kCuEsc | (static_cast<uint32_t>(side.size()) << 2);
@@ -1495,28 +1695,26 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
             i++;
             continue;
         }
-        // the run: consecutive records of one group, at most 8 units
+        // the run: consecutive records of one group, at most 8 units (a REJECT may take two: its hint
+        // rides in a payload unit)
         const uint32_t g = records[i].group;
         uint64_t e = i, max_index = 0;
         uint32_t run_units = 0;
-        bool any = false;
-        while (e < n && run_units < 8) {
+        while (e < n) {
             const raftgpu_append_resp &r = records[e];
             if (r.flags & RAFTGPU_REC_EXT) {
                 e++;
                 continue;
             }
-            if (r.group != g) break;
-            run_units++;
-            if (!(r.flags & RAFTGPU_REC_REJECT) && r.peer_slot < RAFTGPU_SLOTS) {
-                any = true;
-                max_index = std::max(max_index, r.index);
-            }
+            const uint32_t need = (r.flags & RAFTGPU_REC_REJECT) ? 2u : 1u;
+            if (r.group != g || run_units + need > 8u) break;
+            run_units += need;
+            if (r.peer_slot < RAFTGPU_SLOTS) max_index = std::max(max_index, r.index);
             e++;
         }
         while (e < n && (records[e].flags & RAFTGPU_REC_EXT)) e++;  // the EXT of the run's last record
-        const uint64_t base = max_index > 0x7fffu ? max_index - 0x7fffu : 0;
-        bool header = any && base < (1ull << 48);
+        const uint64_t base = max_index > 0x3fffu ? max_index - 0x3fffu : 0;
+        bool header = base < (1ull << 48);  // also for a run of ESC units only: the fused kernel finds records by their run
         if (header) {
             const uint64_t b = nu / RAFTGPU_COMPACT_BLOCK;
             while (blocks_set <= b) g_base[blocks_set++] = g;  // first header of the block names its g_base
@@ -1524,6 +1722,10 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
             if (g < gb || g - gb > 0xfffu) header = false;
         }
         if (nu + 2 + run_units > unit_cap) return RAFTGPU_ERR_FULL;
+        if (!header || (have_prev_group && g < prev_group)) tileable = false;
+        if (!have_prev_group || g != prev_group) seen_slots = 0;
+        prev_group = g;
+        have_prev_group = true;
         if (header) {
             const uint32_t gl = g - g_base[nu / RAFTGPU_COMPACT_BLOCK];
             units[nu++] = kCuHdrA | (static_cast<uint32_t>(base & 0x3fffffffu) << 2);
@@ -1537,11 +1739,16 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
                 continue;
             }
             n_rec++;
-            bool compact = header && !(r.flags & RAFTGPU_REC_REJECT) && r.peer_slot < RAFTGPU_SLOTS &&
-                           !(r.flags & ~(RAFTGPU_REC_LOCAL)) && r.index >= base && r.index - base <= 0x7fffu;
-            uint32_t cd = 0;
+            if (r.peer_slot < RAFTGPU_SLOTS) {
+                if ((seen_slots >> r.peer_slot) & 1u) one_wave = false;
+                seen_slots |= 1u << r.peer_slot;
+            }
+            const bool is_local = r.flags == RAFTGPU_REC_LOCAL, is_reject = r.flags == RAFTGPU_REC_REJECT;
+            bool compact = header && (r.flags == 0 || is_local || is_reject) && r.peer_slot < RAFTGPU_SLOTS &&
+                           r.index >= base && r.index - base <= 0x3fffu;
+            uint32_t cd = 0, payload = 0;
             if (compact) {
-                if (r.flags & RAFTGPU_REC_LOCAL) {
+                if (is_local) {
                     if (r.commit == 0)
                         cd = kCuNoCommit;
                     else if (r.commit >= r.index && r.commit - r.index < kCuNoCommit)
@@ -1554,20 +1761,41 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
                     compact = false;
                 }
             }
+            if (compact && is_reject) {
+                // the EXT's next_probe_index hint as a signed 29-bit delta from the index; a snapshot
+                // request (rare) sends the record to the side table
+                const bool has_ext = k + 1 < n && (records[k + 1].flags & RAFTGPU_REC_EXT);
+                const uint64_t hint = has_ext ? records[k + 1].index : 0;
+                const uint64_t snapshot = has_ext ? records[k + 1].commit : RAFTGPU_INVALID_INDEX;
+                const int64_t d = static_cast<int64_t>(hint - r.index);
+                if (snapshot != RAFTGPU_INVALID_INDEX || d < -(1ll << 28) || d >= (1ll << 28))
+                    compact = false;
+                else
+                    payload = kCuEsc | ((kCuPayload | (static_cast<uint32_t>(d) & (kCuPayload - 1u))) << 2);
+            }
             if (compact) {
-                units[nu] = kCuRec | ((r.flags & RAFTGPU_REC_LOCAL) ? kCuLocal : 0u) | (back << 3) |
-                            (static_cast<uint32_t>(r.peer_slot) << 6) | (static_cast<uint32_t>(r.index - base) << 9) | (cd << 24);
+                units[nu] = kCuRec | (is_local ? kCuLocal : 0u) | (is_reject ? kCuReject : 0u) | (back << 3) |
+                            (static_cast<uint32_t>(r.peer_slot) << 6) | (static_cast<uint32_t>(r.index - base) << 10) | (cd << 24);
                 if (unit_of_record) unit_of_record[k] = static_cast<uint32_t>(nu);
                 nu++;
-            } else if (!esc(k)) {
-                return RAFTGPU_ERR_FULL;
+                back++;
+                if (is_reject) {
+                    units[nu++] = payload;
+                    back++;
+                }
+            } else {
+                if (!esc(k)) return RAFTGPU_ERR_FULL;
+                back++;
             }
-            back++;
         }
         i = e;
     }
     const uint64_t n_blocks = (nu + RAFTGPU_COMPACT_BLOCK - 1) / RAFTGPU_COMPACT_BLOCK;
     while (blocks_set < n_blocks) g_base[blocks_set++] = 0;
+    while (nu & 3u) {
+        if (nu >= unit_cap) return RAFTGPU_ERR_FULL;
+        units[nu++] = kCuEsc | (kCuPad << 2);  // the fused kernel fetches units in 16-byte pieces
+    }
     const uint64_t off_side = off_units + align16(4 * nu);
     const uint64_t total = off_side + align16(side.size() * sizeof(raftgpu_append_resp));
     if (total > out_capacity) return RAFTGPU_ERR_FULL;
@@ -1582,6 +1810,7 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
     h.off_units = off_units;
     h.off_side = off_side;
     h.total_bytes = total;
+    h.flags = (tileable ? RAFTGPU_COMPACT_TILEABLE : 0u) | (tileable && one_wave ? RAFTGPU_COMPACT_ONE_WAVE : 0u);
     memcpy(blob, &h, sizeof(h));
     *out_bytes = total;
     return RAFTGPU_OK;
@@ -1590,12 +1819,7 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
 int32_t raftgpu_step_begin_compact(raftgpu_arena *a, const void *pinned_blob, uint64_t blob_bytes, uint32_t flags) {
     if (!a || !pinned_blob || blob_bytes < sizeof(raftgpu_compact_hdr)) return RAFTGPU_ERR_INVALID;
     const raftgpu_compact_hdr *h = static_cast<const raftgpu_compact_hdr *>(pinned_blob);
-    const uint64_t need_blocks = (static_cast<uint64_t>(h->n_units) + RAFTGPU_COMPACT_BLOCK - 1) / RAFTGPU_COMPACT_BLOCK;
-    if (h->magic != RAFTGPU_COMPACT_MAGIC || h->total_bytes > blob_bytes || h->n_blocks < need_blocks ||
-        (h->off_blocks & 3u) || (h->off_units & 15u) || (h->off_side & 15u) ||
-        h->off_blocks + 4ull * h->n_blocks > h->total_bytes || h->off_units + 4ull * h->n_units > h->total_bytes ||
-        h->off_side + 24ull * h->n_side > h->total_bytes)
-        return fail(a, RAFTGPU_ERR_INVALID, "malformed compact batch header");
+    if (!compact_hdr_ok(*h, blob_bytes)) return fail(a, RAFTGPU_ERR_INVALID, "malformed compact batch header");
     return step_submit(a, flags, nullptr, 0, h);
 }
 

@@ -18,30 +18,34 @@ def pack(recs):
 
 
 def normalise(recs):
-    """What the stream promises to carry: main records, a REJECT's EXT right behind it; stray EXT
-    records (no REJECT in front) carry nothing and are dropped."""
-    keep = []
+    """What the stream promises to carry: main records in order, each REJECT with its EXT
+    (next_probe_index hint, request_snapshot) -- a REJECT without one means (0, none), which is how
+    the kernels read it (load_reject_ext); stray EXT records carry nothing and are dropped."""
+    out = []
     for i, r in enumerate(recs):
         if r["flags"] & B.REC_EXT:
-            if i and (recs[i - 1]["flags"] & B.REC_REJECT) and not (recs[i - 1]["flags"] & B.REC_EXT):
-                keep.append(i)
             continue
-        keep.append(i)
-    out = recs[keep].copy()
-    out["reserved"] = 0
-    return out
+        out.append((r["group"], r["peer_slot"], r["flags"], 0, r["index"], r["commit"]))
+        if r["flags"] & B.REC_REJECT:
+            if i + 1 < len(recs) and (recs[i + 1]["flags"] & B.REC_EXT):
+                e = recs[i + 1]
+                out.append((r["group"], r["peer_slot"], B.REC_EXT, 0, e["index"], e["commit"]))
+            else:
+                out.append((r["group"], r["peer_slot"], B.REC_EXT, 0, 0, 0))
+    return np.array(out, dtype=B.APPEND_RESP_DTYPE)
 
 
 def check_round_trip(recs):
     blob, units = pack(recs)
-    got = B.unpack_compact(blob)
+    got = normalise(B.unpack_compact(blob))
     want = normalise(recs)
-    # the compact form does not carry `reserved`
-    got["reserved"] = 0
-    # an ESC record is shipped verbatim, reserved included
     assert len(got) == len(want)
+    ext = (want["flags"] & B.REC_EXT) != 0
     for name in ("group", "peer_slot", "flags", "index", "commit"):
-        np.testing.assert_array_equal(got[name], want[name], err_msg=name)
+        if name in ("group", "peer_slot"):     # an EXT's own group / slot fields mean nothing
+            np.testing.assert_array_equal(got[name][~ext], want[name][~ext], err_msg=name)
+        else:
+            np.testing.assert_array_equal(got[name], want[name], err_msg=name)
     hdr = blob[:B.COMPACT_HDR_DTYPE.itemsize].view(B.COMPACT_HDR_DTYPE)[0]
     assert hdr["total_bytes"] == len(blob)
     assert hdr["n_records"] == int(np.count_nonzero(~(recs["flags"] & B.REC_EXT).astype(bool)))
@@ -60,7 +64,7 @@ def test_empty_batch():
 
 def test_round_trip_random_records():
     rng = np.random.default_rng(5)
-    edge = [0, 1, 2, 254, 255, 256, 0x7ffe, 0x7fff, 0x8000, (1 << 30) - 1, 1 << 30, (1 << 48) - 1, 1 << 48,
+    edge = [0, 1, 2, 254, 255, 256, 0x3ffe, 0x3fff, 0x4000, 0x7ffe, 0x7fff, 0x8000, (1 << 28) - 1, 1 << 28, (1 << 28) + 1, (1 << 30) - 1, 1 << 30, (1 << 48) - 1, 1 << 48,
             (1 << 48) + 0x7fff, (1 << 48) + 0x8000, 1 << 63, M64 - 1, M64]
     rows = []
     g = 0
@@ -84,9 +88,12 @@ def test_round_trip_random_records():
                     commit = max(1, index - 1)     # a "new last_index" below index: still lossless
                 rows.append((g, slot, B.REC_LOCAL, 0, index, commit))
             else:
-                rows.append((g, slot, B.REC_REJECT, 0, index, int(rng.integers(0, 1 << 40))))
+                cd = int(rng.integers(0, 6)) if rng.random() < 0.7 else int(rng.integers(0, 1 << 40))
+                rows.append((g, slot, B.REC_REJECT, 0, index, max(0, index - cd)))
                 if rng.random() < 0.8:
-                    rows.append((g, slot, B.REC_EXT, 0, int(rng.integers(0, 1 << 40)),
+                    hd = int(rng.integers(-8, 8)) if rng.random() < 0.7 else \
+                        int(rng.choice([-(1 << 28) - 1, -(1 << 28), (1 << 28) - 1, 1 << 28, 1 << 40]))
+                    rows.append((g, slot, B.REC_EXT, 0, min(M64, max(0, index + hd)),
                                  0 if rng.random() < 0.7 else int(rng.integers(1, 1 << 40))))
     recs = np.array(rows, dtype=B.APPEND_RESP_DTYPE)
     hdr = check_round_trip(recs)
@@ -102,7 +109,8 @@ def test_unsorted_and_stray_ext():
     recs["index"] = rng.integers(0, 1 << 62, n, dtype=np.uint64)
     recs["commit"] = recs["index"] - np.minimum(recs["index"], rng.integers(0, 4, n).astype(np.uint64))
     recs["flags"][rng.random(n) < 0.05] = B.REC_EXT   # stray EXT records: dropped
-    check_round_trip(recs)
+    hdr = check_round_trip(recs)
+    assert not (hdr["flags"] & B.COMPACT_TILEABLE)
 
 
 def test_descending_groups_escape():
@@ -114,6 +122,7 @@ def test_descending_groups_escape():
     recs["commit"] = recs["index"]
     hdr = check_round_trip(recs)
     assert hdr["n_side"] >= n - 4      # one header per block of units still works
+    assert not (hdr["flags"] & B.COMPACT_TILEABLE)
 
 
 def test_synth_round_is_compact():
@@ -124,16 +133,20 @@ def test_synth_round_is_compact():
         hdr = check_round_trip(recs)
         main = int(hdr["n_records"])
         # 2 header units per group + 1 per record; only REJECTs (2%) escape
-        assert hdr["n_units"] == 2 * n + main
-        rejects = int(np.count_nonzero(recs["flags"] & B.REC_REJECT))
-        assert hdr["n_side"] == 2 * rejects
-        assert hdr["total_bytes"] < 0.48 * 16 * (main + rejects)    # vs the 16-byte packed form
+        # 2 header units per group, 1 per record, 1 more for the hint of a REJECT; only a REJECT
+        # that asks for a snapshot (0.25 % of the records) goes to the side table
+        rej = np.nonzero(recs["flags"] & B.REC_REJECT)[0]
+        want_snapshot = int(np.count_nonzero(recs["commit"][rej + 1]))
+        assert hdr["n_units"] == (2 * n + main + (len(rej) - want_snapshot) + 3) & ~3      # padded to 16 bytes
+        assert hdr["flags"] & B.COMPACT_TILEABLE
+        assert hdr["n_side"] == 2 * want_snapshot
+        assert hdr["total_bytes"] < 0.42 * 16 * (main + len(rej))    # vs the 16-byte packed form
 
 
 def test_joint_round_is_compact():
     s = B.Synth(5000, 7, k_peers=5, joint=True)
     hdr = check_round_trip(s.next_round().copy())
-    assert hdr["n_units"] == 2 * 5000 + hdr["n_records"]
+    assert hdr["flags"] & B.COMPACT_TILEABLE and hdr["n_side"] < 0.01 * hdr["n_records"]
 
 
 def test_capacity_errors():

@@ -512,12 +512,22 @@ def test_zero_copy_packed_submission_and_duplicate_detection():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,joint", [(100_003, False), (40_000, True)])
-def test_compact_stream_submission_vs_oracle(n, joint):
+@pytest.mark.parametrize("n,joint,shuffle", [(100_003, False, False), (40_000, True, False), (50_000, False, True)])
+def test_compact_stream_submission_vs_oracle(n, joint, shuffle):
     """raftgpu_step_begin_compact: the 4-byte-unit stream (group runs + ESC side table) goes over PCIe
-    as is and apply_compact_kernel decodes it; columns, bitmap, committed and the per-record result
-    bytes equal the oracle's; hostile values take the ESC path; duplicates are caught on the device."""
+    as is.  A tileable stream (groups ascending) takes the fused tile kernel; with the groups in
+    random order (`shuffle`) it is not tileable and apply_compact_kernel + the recompute pass run
+    instead.  Either way columns, bitmap, committed and the per-record result bytes equal the
+    oracle's; hostile values take the ESC path; a second record for a cell is applied in order by
+    the fused kernel and refused (on the device) by the scatter kernel."""
     synth = B.Synth(n, 0x5EED0009, joint=joint)
+    rank = np.random.default_rng(3).permutation(n + 1)
+
+    def arrange(recs):
+        if not shuffle:
+            return recs
+        return np.ascontiguousarray(recs[np.argsort(rank[recs["group"]], kind="stable")])
+
     arena = B.Arena(n)
     arena.group_alloc_range(n)
     arena.load_columns(synth.initial)
@@ -525,9 +535,11 @@ def test_compact_stream_submission_vs_oracle(n, joint):
     cap_bytes = B.compact_bound(8 * n)
     bufs = [arena.host_alloc_bytes(cap_bytes) for _ in range(2)]
     for rnd in range(4):
-        recs = synth.next_round().copy()
+        recs = arrange(synth.next_round().copy())
         nb, units = B.pack_compact(recs, bufs[rnd % 2], want_units=True)
-        assert nb < 0.5 * 16 * len(recs)
+        assert shuffle or nb < 0.45 * 16 * len(recs)
+        hdr = bufs[rnd % 2][:64].view(B.COMPACT_HDR_DTYPE)[0]
+        assert bool(hdr["flags"] & B.COMPACT_TILEABLE) == (not shuffle)
         arena.step_begin_compact(bufs[rnd % 2], nb, B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS)
         r = arena.step_wait()
         want_res = O.arena_apply(ref, recs, mode=0)
@@ -553,8 +565,9 @@ def test_compact_stream_submission_vs_oracle(n, joint):
     odd[3] = (7, 0, B.REC_LOCAL, 0, 9, 4)
     odd[4] = (8, 1, 0, 0, (1 << 63) + 11, (1 << 63) + 2)
     odd[5] = (9, 9, 0, 0, 77, 70)                         # no such peer slot: NO_PROGRESS
-    odd[6] = (n - 1, 7, 0, 0, 77, 70)                     # a slot the group has no peer in
-    odd[7] = (12, 1, 0, 0, int(ref.matched[1, 12]) + 300, int(ref.matched[1, 12]))   # commit delta 300
+    odd[6] = (12, 1, 0, 0, int(ref.matched[1, 12]) + 300, int(ref.matched[1, 12]))   # commit delta 300
+    odd[7] = (n - 1, 7, 0, 0, 77, 70)                     # a slot the group has no peer in
+    odd = arrange(odd)
     nb, units = B.pack_compact(odd, bufs[0], want_units=True)
     arena.step_begin_compact(bufs[0], nb, B.STEP_READ_RESULTS)
     arena.step_wait()
@@ -567,14 +580,24 @@ def test_compact_stream_submission_vs_oracle(n, joint):
     arena.step_begin_compact(bufs[1], nb, 0)
     r = arena.step_wait()
     assert r.n_records == 0 and r.n_advanced == 0
-    # two records for one cell in one batch: detected by the kernel
-    dup = np.zeros(2, dtype=B.APPEND_RESP_DTYPE)
+    # two records for one cell in one batch
+    dup = np.zeros(3, dtype=B.APPEND_RESP_DTYPE)
     dup[0] = (11, 1, 0, 0, int(ref.matched[1, 11]) + 5, 0)
     dup[1] = (11, 1, 0, 0, int(ref.matched[1, 11]) + 9, 0)
-    nb, _ = B.pack_compact(dup, bufs[1])
-    arena.step_begin_compact(bufs[1], nb, 0)
+    dup[2] = (3, 1, 0, 0, int(ref.matched[1, 3]) + 1, 0)       # descending after group 11: scatter path when shuffled
+    if not shuffle:
+        dup = dup[[2, 0, 1]]
+    nb, units = B.pack_compact(dup, bufs[1], want_units=True)
+    arena.step_begin_compact(bufs[1], nb, B.STEP_READ_RESULTS)
     r = arena.step_wait(check=False)
-    assert r.status == B.ERR_INVALID and r.n_duplicates == 1
+    if shuffle:    # the scatter kernel has one thread per record: a second record for a cell is refused
+        assert r.status == B.ERR_INVALID and r.n_duplicates == 1
+    else:          # the fused kernel walks a group's records in order: applied one after the other
+        assert r.status == B.OK and r.n_duplicates == 0
+        want_res = O.arena_apply(ref, dup, mode=0)
+        O.arena_recompute(ref)
+        assert np.array_equal(arena.slot_results()[units], want_res)
+        assert_columns_equal(arena.read_columns(n), ref, n, "two records for one cell, in order")
     # a mangled header is refused before anything is submitted
     bad = bufs[0]
     bad[:4] = 0
@@ -686,6 +709,145 @@ def test_fused_tile_step_learners_group_commit_and_crowded_tiles():
     assert res[1] == B.RES_NO_PROGRESS and res[0] & B.RES_OK
     with pytest.raises(B.RaftGpuError):
         B.tile_index(np.ascontiguousarray(pk[:k][::-1]), k, n)   # not in group order
+    arena.close()
+
+
+def _compact_round(arena, n, recs, ref, blob, d_bufs, ordered=False):
+    """One fused compact step (raftgpu_step_compact_device) on `recs` (group order) vs the oracle."""
+    nb, units = B.pack_compact(recs, blob, want_units=True)
+    hdr = blob[:64].view(B.COMPACT_HDR_DTYPE)[0]
+    assert hdr["flags"] & B.COMPACT_TILEABLE
+    d_blob, d_off, d_res, d_bm, d_com, d_bad = d_bufs
+    nu = int(hdr["n_units"])
+    arena.h2d(d_blob, blob[:nb])
+    arena.h2d(d_bm, np.zeros(arena.cap // 32, dtype=np.uint32))
+    arena.h2d(d_res, np.zeros(max(nu, 1), dtype=np.uint8))
+    arena.h2d(d_bad, np.zeros(1, dtype=np.uint32))
+    arena.compact_tile_index_device(d_blob, blob, d_off, d_bad)
+    arena.step_compact_device(d_blob, blob, d_off, d_results=d_res, d_adv=d_bm, d_commit=d_com, d_dup=d_bad,
+                              ordered=ordered)
+    res = np.zeros(max(nu, 1), dtype=np.uint8)
+    bm = np.zeros(arena.cap // 32, dtype=np.uint32)
+    bad = np.zeros(1, dtype=np.uint32)
+    arena.d2h(res, d_res)
+    arena.d2h(bm, d_bm)
+    arena.d2h(bad, d_bad)
+    assert bad[0] == 0
+    want_res = O.arena_apply(ref, recs, mode=0)
+    want_adv, want_bm, _, _ = O.arena_recompute(ref)
+    main = (recs["flags"] & B.REC_EXT) == 0
+    assert np.array_equal(res[units[main]], want_res[main]), "per-record results differ"
+    other = np.ones(len(res), dtype=bool)
+    other[units[main]] = False
+    assert not res[other].any()
+    words = (n + 31) // 32
+    assert np.array_equal(bm[:words], want_bm[:words])
+    assert_columns_equal(arena.read_columns(n), ref, n, "fused compact step")
+    return want_adv
+
+
+def _compact_bufs(arena, n, per_group):
+    cap_b = B.compact_bound(per_group * n + 64)
+    blob = np.zeros(cap_b, dtype=np.uint8)
+    d = (arena.device_alloc(cap_b), arena.device_alloc(4 * (3 * (arena.cap // B.tile_groups() + 2) + 2)),
+         arena.device_alloc(3 * per_group * n + 64), arena.device_alloc(arena.cap // 8),
+         arena.device_alloc(8 * arena.cap), arena.device_alloc(4))
+    return blob, d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,joint,ordered", [(100_003, False, False), (100_003, False, True), (70_001, True, False),
+                                             (70_001, True, True), (1_000_000, False, False)])
+def test_fused_compact_step_vs_oracle(n, joint, ordered):
+    """raftgpu_step_compact_device: the fused kernel on compact streams -- one thread per unit, or
+    (`ordered`) the per-group walk -- including a ragged last tile, the general (joint, hint 0x7f)
+    instantiation and 1M groups."""
+    synth = B.Synth(n, 0x5EED000A, joint=joint)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    blob, d_bufs = _compact_bufs(arena, n, 9)
+    total = 0
+    for _ in range(3 if n >= 1_000_000 else 6):
+        total += _compact_round(arena, n, synth.next_round().copy(), ref, blob, d_bufs, ordered=ordered)
+    assert total > n // 2
+    cnt = arena.counters()
+    assert cnt["recomputes"] % n == 0 and cnt["advanced"] == total
+    arena.close()
+
+
+@pytest.mark.gpu
+def test_fused_compact_step_corner_cases():
+    """Learners outside the voter hint (HBM path), group-commit groups, a tile with more units than
+    the shared-memory staging holds, groups with more than 8 records (several runs), several records
+    for one cell (applied in stream order), Snapshot-state peers, sparse batches with empty tiles."""
+    n = 3000
+    synth = B.Synth(n, 0x5EED000B)
+    cols = synth.initial
+    rng = np.random.default_rng(8)
+    learners = rng.random(n) < 0.3
+    cols.meta[:n] |= (learners.astype(np.uint32) << np.uint32(16 + 6))
+    cols.next_idx[6, :n] = np.where(learners, cols.matched[0, :n] - 5, 0)
+    cols.pflags[6, :n] = np.where(learners, O.STATE_PROBE, 0)
+    gc = rng.random(n) < 0.2
+    cols.meta[:n] |= np.where(gc, O.META_GROUP_COMMIT, 0).astype(np.uint32)
+    cols.commit_group_id[:5, :n] = rng.integers(0, 3, (5, n))
+    snap = rng.random(n) < 0.1                           # slot 2 is in Snapshot state in 10 % of the groups
+    cols.pflags[2, :n] = np.where(snap, O.STATE_SNAPSHOT, cols.pflags[2, :n])
+    cols.pending_snapshot[2, :n] = np.where(snap, cols.matched[2, :n] + 3, 0)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(cols)
+    ref = O.copy_columns(cols)
+    blob, d_bufs = _compact_bufs(arena, n, 40)
+    tg = B.tile_groups()
+    for rnd in range(4):
+        base = synth.next_round().copy()
+        extra = []
+        for g in np.nonzero(learners)[0]:
+            extra.append((g, 6, 0, 0, int(ref.matched[0, g]) - 3 + rnd, 0))
+        if rnd == 1:   # tile 1 crowded: every follower rejects (ESC units + side table) and acks twice more
+            for g in range(tg, 2 * tg):
+                for s_ in range(1, 5):
+                    extra.append((g, s_, B.REC_REJECT, 0, int(ref.next_idx[s_, g]) - 1, 0))
+                    extra.append((g, s_, B.REC_EXT, 0, int(ref.matched[s_, g]), 77 if s_ == 1 else 0))
+                    extra.append((g, s_, 0, 0, int(ref.matched[s_, g]) + 2, int(ref.matched[s_, g])))
+                    extra.append((g, s_, 0, 0, int(ref.matched[s_, g]) + 7, int(ref.matched[s_, g]) + 1))
+        if rnd == 2:   # pipelined acks: the same cell several times, out of order too
+            for g in range(0, n, 7):
+                m = int(ref.matched[1, g])
+                for d_ in (4, 2, 9, 9, 1):
+                    extra.append((g, 1, 0, 0, m + d_, m))
+        recs = np.concatenate([base, np.array(extra, dtype=B.APPEND_RESP_DTYPE)]) if extra else base
+        if rnd == 3:   # a sparse batch: most tiles get no units at all
+            recs = recs[(recs["group"] % 700) < 3]
+        # group order; inside a group arrival order, with each EXT right behind its REJECT
+        order = np.argsort(recs["group"], kind="stable")
+        _compact_round(arena, n, np.ascontiguousarray(recs[order]), ref, blob, d_bufs)
+    # empty stream
+    _compact_round(arena, n, np.zeros(0, dtype=B.APPEND_RESP_DTYPE), ref, blob, d_bufs)
+    # a stream that claims ONE_WAVE but holds two records for one cell: the per-unit kernel applies
+    # the first it sees, refuses the other and counts it
+    dup = np.zeros(2, dtype=B.APPEND_RESP_DTYPE)
+    m = int(ref.matched[1, 40])
+    dup[0] = (40, 1, 0, 0, m + 5, m)
+    dup[1] = (40, 1, 0, 0, m + 5, m)
+    nb, _ = B.pack_compact(dup, blob)
+    hdr = blob[:64].view(B.COMPACT_HDR_DTYPE)
+    assert not (hdr[0]["flags"] & B.COMPACT_ONE_WAVE)
+    hdr[0]["flags"] |= B.COMPACT_ONE_WAVE
+    d_blob, d_off, d_res, d_bm, d_com, d_bad = d_bufs
+    arena.h2d(d_blob, blob[:nb])
+    arena.h2d(d_bad, np.zeros(1, dtype=np.uint32))
+    arena.compact_tile_index_device(d_blob, blob, d_off, d_bad)
+    arena.step_compact_device(d_blob, blob, d_off, d_dup=d_bad)
+    bad = np.zeros(1, dtype=np.uint32)
+    arena.d2h(bad, d_bad)
+    assert bad[0] == 1
+    O.arena_apply(ref, dup[:1], mode=0)
+    O.arena_recompute(ref)
+    assert_columns_equal(arena.read_columns(n), ref, n, "duplicate refused")
     arena.close()
 
 

@@ -40,7 +40,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"]
-for name in ("fused", "recompute", "apply"):
+for name in ("fused", "ctile", "recompute", "apply"):
     rep = f"{d}/prof_{name}.ncu-rep"
     if not os.path.exists(rep):
         continue
@@ -62,6 +62,9 @@ for name in ("fused", "recompute", "apply"):
 try:
     b = json.loads(open(f"{d}/bench.json").read().strip().splitlines()[-1])
     L.append("\n## bench.py line of the same build (live CUDA events, not under ncu)\n\n```json\n" + json.dumps(b, indent=1) + "\n```")
+    if os.path.exists(f"{d}/bench_compact.json"):
+        b3 = json.loads(open(f"{d}/bench_compact.json").read().strip().splitlines()[-1])
+        L.append("\n## bench.py --compact-device (compact stream + its fused kernel, device-resident leg) of the same build\n\n```json\n" + json.dumps(b3, indent=1) + "\n```")
     if os.path.exists(f"{d}/bench_scatter.json"):
         b2 = json.loads(open(f"{d}/bench_scatter.json").read().strip().splitlines()[-1])
         L.append("\n## bench.py --scatter (general two-kernel path) of the same build\n\n```json\n" + json.dumps(b2, indent=1) + "\n```")

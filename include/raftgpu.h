@@ -500,6 +500,36 @@ int32_t raftgpu_step_results(raftgpu_arena *arena, const uint32_t **adv_bitmap,
 int32_t raftgpu_step_record_results(raftgpu_arena *arena, uint32_t ring, uint8_t *out,
                                     uint64_t out_capacity, uint64_t *out_n);
 
+/* ---- post-commit send decisions --------------------- */
+
+/* The step right after the path: when a group's commit index advanced the leader calls
+ * bcast_append (raft.rs:1745-1748, 1012-1013 -> raft.rs:857-865), i.e. send_append for every
+ * peer but itself, and maybe_send_append drops the paused ones first (raft.rs:780-788;
+ * Progress::is_paused, progress.rs:210-216: Probe -> paused, Replicate -> ins.full(),
+ * Snapshot -> always).  raftgpu_send_list_device turns the advanced bitmap of a step into that
+ * work list -- one entry per (group, peer) the host has to build a MsgAppend for -- with a
+ * stream-compaction kernel: groups [first, first+n) whose bit is set in d_adv_bitmap (NULL = every
+ * group: a plain bcast_append), peers = voters and learners of the group except its own slot.
+ * Entries come out in no particular order (neither does HashMap iteration in the reference).
+ * *d_count = number of entries the pass produced (u64, zeroed here first); entries beyond
+ * `capacity` are dropped, so count > capacity means "call again with a larger buffer". */
+typedef struct raftgpu_send_entry {
+    uint32_t group;
+    uint8_t peer_slot;
+    uint8_t flags;     /* RAFTGPU_SEND_SNAPSHOT */
+    uint16_t reserved;
+    uint64_t next_idx; /* Progress::next_idx: entries from here (raft.rs:799) */
+} raftgpu_send_entry;
+/* pending_request_snapshot != INVALID_INDEX: prepare_send_snapshot comes first (raft.rs:792-797) */
+#define RAFTGPU_SEND_SNAPSHOT 0x1u
+int32_t raftgpu_send_list_device(raftgpu_arena *arena, void *stream, uint32_t first, uint32_t n,
+                                 const uint32_t *d_adv_bitmap, raftgpu_send_entry *d_out, uint64_t capacity,
+                                 uint64_t *d_count);
+/* The same for the last completed step (its advanced bitmap, all allocated groups), entries
+ * copied to host memory; synchronous.  RAFTGPU_ERR_FULL (with *out_n = the number needed) when
+ * `capacity` is too small. */
+int32_t raftgpu_step_send_list(raftgpu_arena *arena, raftgpu_send_entry *out, uint64_t capacity, uint64_t *out_n);
+
 /* ---- votes ----------------------------------------- */
 
 /* ProgressTracker::reset_votes / record_vote (tracker.rs:301-310). */

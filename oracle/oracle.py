@@ -145,6 +145,8 @@ def lib() -> C.CDLL:
         L.ro_arena_vote_result.argtypes = [pv, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
                                            C.POINTER(C.c_uint32)]
         L.ro_arena_vote_result.restype = i32
+        L.ro_arena_send_list.argtypes = [pv, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ro_arena_send_list.restype = C.c_uint64
         L.ro_bench_recompute.argtypes = [pv, i32, i32, p64]
         L.ro_bench_recompute.restype = C.c_double
         L.ro_bench_step.argtypes = [pv, C.c_void_p, sz, i32, p64]
@@ -285,6 +287,22 @@ def arena_vote_result(c, votes: np.ndarray, g: int):
     v = view(c)
     r = lib().ro_arena_vote_result(C.byref(v), votes.ctypes.data, g, C.byref(gr), C.byref(rj))
     return gr.value, rj.value, r
+
+
+SEND_ENTRY_DTYPE = np.dtype([("group", "<u4"), ("peer_slot", "u1"), ("flags", "u1"), ("reserved", "<u2"),
+                             ("next_idx", "<u8")])
+
+
+def arena_send_list(c, adv_bitmap=None, first: int = 0, n: int | None = None):
+    """bcast_append over the advanced groups (raft.rs:857-865, 780-788): entries in (group, slot) order."""
+    n = c.n_groups - first if n is None else n
+    v = view(c)
+    bm = None if adv_bitmap is None else np.ascontiguousarray(adv_bitmap, dtype=np.uint32)
+    need = lib().ro_arena_send_list(C.byref(v), first, n, None if bm is None else bm.ctypes.data, None, 0)
+    out = np.zeros(need, dtype=SEND_ENTRY_DTYPE)
+    got = lib().ro_arena_send_list(C.byref(v), first, n, None if bm is None else bm.ctypes.data, out.ctypes.data, need)
+    assert got == need
+    return out
 
 
 def bench_recompute(c, n_threads: int, iters: int):

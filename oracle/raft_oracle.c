@@ -593,6 +593,41 @@ int ro_arena_vote_result(const ro_arena_view *a, const uint8_t *votes, uint32_t 
     return ro_joint_vote_result(in_ids, n_in, out_ids, n_out, &vm);
 }
 
+/* progress.rs:210-216 */
+static int progress_is_paused(uint8_t flags) {
+    switch (flags & RO_PF_STATE_MASK) {
+    case RO_STATE_PROBE: return (flags & RO_PF_PAUSED) != 0;
+    case RO_STATE_REPLICATE: return (flags & RO_PF_INS_FULL) != 0; /* ins.full(), reported by the host */
+    default: return 1;                                              /* Snapshot */
+    }
+}
+
+/* raft.rs:857-865 bcast_append over the advanced groups; raft.rs:780-788 maybe_send_append's gate */
+uint64_t ro_arena_send_list(const ro_arena_view *a, uint32_t first, uint32_t n, const uint32_t *adv_bitmap,
+                            ro_send_entry *out, uint64_t cap) {
+    uint64_t k = 0;
+    for (uint32_t g = first; g < first + n; g++) {
+        if (adv_bitmap && !(adv_bitmap[g >> 5] & (1u << (g & 31)))) continue;
+        uint32_t meta = a->meta[g];
+        uint32_t peers = RO_META_IN(meta) | RO_META_OUT(meta) | RO_META_LEARN(meta);
+        for (uint32_t s = 0; s < RO_SLOTS; s++) {
+            if (!(peers & (1u << s))) continue;
+            if ((meta & RO_META_HAS_SELF) && RO_META_SELF(meta) == s) continue; /* :863 id != self_id */
+            size_t c = cell(a, s, g);
+            if (progress_is_paused(a->pflags[c])) continue;                       /* :780 */
+            if (k < cap) {
+                out[k].group = g;
+                out[k].peer_slot = (uint8_t)s;
+                out[k].flags = a->pending_request_snapshot[c] != 0 ? 1 : 0;           /* :792 */
+                out[k].reserved = 0;
+                out[k].next_idx = a->next_idx[c];
+            }
+            k++;
+        }
+    }
+    return k;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Tuned CPU path for the baseline arm: same results as the literal functions  */
 /* above (tests/test_oracle_fast.py), but written the way a CPU implementation */

@@ -237,6 +237,20 @@ uint64_t ro_arena_recompute(ro_arena_view *a, uint32_t first, uint32_t n, uint32
 int ro_arena_vote_result(const ro_arena_view *a, const uint8_t *votes, uint32_t g,
                          uint32_t *granted, uint32_t *rejected);
 
+/* Post-commit send decisions: bcast_append (raft.rs:857-865) for the groups of [first, first+n)
+ * whose bit is set in adv_bitmap (NULL = all), each send_append gated by Progress::is_paused
+ * (raft.rs:780-788, progress.rs:210-216).  One entry per (group, peer != self, not paused), in
+ * (group, slot) order; returns the number of entries (only the first `cap` are stored). */
+typedef struct {
+    uint32_t group;
+    uint8_t peer_slot;
+    uint8_t flags; /* 1 = pending_request_snapshot != INVALID_INDEX (raft.rs:792-797) */
+    uint16_t reserved;
+    uint64_t next_idx;
+} ro_send_entry;
+uint64_t ro_arena_send_list(const ro_arena_view *a, uint32_t first, uint32_t n, const uint32_t *adv_bitmap,
+                            ro_send_entry *out, uint64_t cap);
+
 /* ---- CPU baseline timing (bench.py cpu_baseline / --impl reference) ----- */
 
 /* Runs `iters` recompute passes over the whole arena with n_threads pthreads

@@ -46,6 +46,10 @@ APPEND_RESP_DTYPE = np.dtype(
      ("index", "<u8"), ("commit", "<u8")]
 )
 assert APPEND_RESP_DTYPE.itemsize == 24
+SEND_ENTRY_DTYPE = np.dtype([("group", "<u4"), ("peer_slot", "u1"), ("flags", "u1"), ("reserved", "<u2"),
+                             ("next_idx", "<u8")])
+assert SEND_ENTRY_DTYPE.itemsize == 16
+SEND_SNAPSHOT = 0x1
 
 # host column name -> (column id, numpy dtype, per-peer?)
 COLUMNS = {
@@ -247,6 +251,8 @@ def lib() -> C.CDLL:
             "raftgpu_reset_votes": ([vp, u32], i32),
             "raftgpu_record_vote": ([vp, u32, u32, i32], i32),
             "raftgpu_tally_votes": ([vp, vp, u32, u32, vp], i32),
+            "raftgpu_send_list_device": ([vp, vp, u32, u32, vp, vp, u64, vp], i32),
+            "raftgpu_step_send_list": ([vp, vp, u64, C.POINTER(u64)], i32),
             "raftgpu_vote_result": ([vp, u32, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)], i32),
             "raftgpu_counters_read": ([vp, C.POINTER(Counters)], i32),
             "raftgpu_synchronize": ([vp], i32),
@@ -672,6 +678,17 @@ class Arena:
 
     def record_vote(self, g, slot, vote: bool):
         self._ck(self._L.raftgpu_record_vote(self._h, g, slot, int(vote)), "record_vote")
+
+    def send_list_device(self, first, n, d_adv, d_out, capacity, d_count, stream=None):
+        self._ck(self._L.raftgpu_send_list_device(self._h, stream, first, n, d_adv, d_out, capacity, d_count),
+                 "send_list_device")
+
+    def step_send_list(self, capacity: int) -> np.ndarray:
+        """Post-commit send decisions of the last completed step (raftgpu_step_send_list)."""
+        out = np.zeros(capacity, dtype=SEND_ENTRY_DTYPE)
+        n = C.c_uint64()
+        self._ck(self._L.raftgpu_step_send_list(self._h, out.ctypes.data, capacity, C.byref(n)), "step_send_list")
+        return out[: n.value]
 
     def tally_votes(self, first, n, d_out, stream=None):
         self._ck(self._L.raftgpu_tally_votes(self._h, stream, first, n, d_out), "tally_votes")

@@ -1949,6 +1949,46 @@ int32_t raftgpu_record_vote(raftgpu_arena *a, uint32_t g, uint32_t peer_slot, in
     });
 }
 
+int32_t raftgpu_send_list_device(raftgpu_arena *a, void *stream, uint32_t first, uint32_t n,
+                                 const uint32_t *d_adv_bitmap, raftgpu_send_entry *d_out, uint64_t capacity,
+                                 uint64_t *d_count) {
+    static_assert(sizeof(raftgpu_send_entry) == 16, "send entry layout");
+    if (!a || !d_count || (!d_out && capacity)) return RAFTGPU_ERR_INVALID;
+    if (static_cast<uint64_t>(first) + n > a->cap) return RAFTGPU_ERR_RANGE;
+    CK(a, cudaSetDevice(a->device));
+    cudaStream_t st = pick_stream(a, stream);
+    CK(a, cudaMemsetAsync(d_count, 0, 8, st));
+    if (n == 0) return RAFTGPU_OK;
+    const uint32_t blocks = std::min<uint32_t>(div_up(n, 256), 8u * static_cast<uint32_t>(a->sm_count));
+    send_list_kernel<<<blocks, 256, 0, st>>>(a->cols, first, n, d_adv_bitmap, d_out, capacity,
+                                             reinterpret_cast<unsigned long long *>(d_count));
+    CKL(a);
+    return RAFTGPU_OK;
+}
+
+int32_t raftgpu_step_send_list(raftgpu_arena *a, raftgpu_send_entry *out, uint64_t capacity, uint64_t *out_n) {
+    if (!a || !out_n || (!out && capacity)) return RAFTGPU_ERR_INVALID;
+    if (a->last_done < 0) return fail(a, RAFTGPU_ERR_INVALID, "no completed step");
+    std::lock_guard<std::mutex> ctl_lock(a->ctl_mu);
+    StagingSet &s = a->sets[a->last_done];
+    CK(a, cudaSetDevice(a->device));
+    // the set's record staging is idle between its step_wait and its next submission: the entries go there
+    const uint64_t room = (static_cast<uint64_t>(a->n_chunks) * kChunk + a->overflow_records) * sizeof(PackedRec) / sizeof(raftgpu_send_entry);
+    const uint64_t cap_dev = std::min(capacity, room);
+    uint64_t *d_count = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(a->d_scratch) + 128);
+    int32_t rc = raftgpu_send_list_device(a, a->s_compute, 0, a->hi, s.d_adv_bitmap,
+                                          reinterpret_cast<raftgpu_send_entry *>(s.d_recs), cap_dev, d_count);
+    if (rc != RAFTGPU_OK) return rc;
+    uint8_t *hs = static_cast<uint8_t *>(a->h_scratch);
+    CK(a, cudaMemcpyAsync(hs + 128, d_count, 8, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    const uint64_t total = *reinterpret_cast<uint64_t *>(hs + 128);
+    *out_n = total;
+    if (total > cap_dev) return fail(a, RAFTGPU_ERR_FULL, "send list larger than the buffer");
+    if (total) CK(a, cudaMemcpy(out, s.d_recs, total * sizeof(raftgpu_send_entry), cudaMemcpyDeviceToHost));
+    return RAFTGPU_OK;
+}
+
 int32_t raftgpu_tally_votes(raftgpu_arena *a, void *stream, uint32_t first, uint32_t n, uint32_t *d_out) {
     if (!a || !d_out) return RAFTGPU_ERR_INVALID;
     if (static_cast<uint64_t>(first) + n > a->cap) return RAFTGPU_ERR_RANGE;

@@ -2042,6 +2042,78 @@ compact_tile_gb_kernel(CompactSrc src, uint32_t n_tiles, const uint32_t *__restr
 }
 
 // ---------------------------------------------------------------------------
+// send_list_kernel: bcast_append (raft.rs:857-865) behind Raft::maybe_commit (raft.rs:1745-1748) as a
+// stream compaction.  One lane per group, a warp per 32 groups = one word of the advanced bitmap;
+// a selected group contributes one entry per present peer other than itself that is not paused
+// (progress.rs:210-216).  Lanes count their entries, a warp scan turns the counts into offsets, ONE
+// global atomic per warp reserves the range, each lane writes its 16-byte entries.
+// Algorithmic bytes: 4 per 32 groups (bitmap) + per advanced group 4 (meta) + K x 17 (pflags,
+// next_idx, pending_request_snapshot of its peers) read, 16 written per entry.
+__global__ void __launch_bounds__(256)
+send_list_kernel(Columns c, uint32_t first, uint32_t n, const uint32_t *__restrict__ adv_bitmap,
+                 raftgpu_send_entry *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ count) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t base = first & ~31u;
+    const uint32_t n_tiles = static_cast<uint32_t>((static_cast<uint64_t>(first - base) + n + 31) >> 5);
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
+        const uint32_t g = base + tile * 32u + lane;
+        const uint32_t word = adv_bitmap ? adv_bitmap[g >> 5] : 0xffffffffu;
+        const bool sel = g >= first && g < first + n && ((word >> lane) & 1u);
+        uint32_t send = 0;
+        uint64_t nx[kSlots], prs[kSlots];  // loaded together with the flag bytes: one round trip, not one per entry
+        if (sel) {
+            const uint32_t meta = c.meta[g];
+            uint32_t peers = RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
+            if (meta & RAFTGPU_META_HAS_SELF) peers &= ~(1u << RAFTGPU_META_SELF(meta));  // raft.rs:863 id != self_id
+            uint32_t f[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; s++) {
+                f[s] = RAFTGPU_STATE_SNAPSHOT;
+                nx[s] = 0;
+                prs[s] = 0;
+                if ((peers >> s) & 1u) {
+                    const size_t cell = static_cast<size_t>(s) * c.cap + g;
+                    f[s] = c.pflags[cell];
+                    nx[s] = c.next_idx[cell];
+                    prs[s] = c.pending_req_snapshot[cell];
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < kSlots; s++) {
+                const uint32_t state = f[s] & RAFTGPU_PF_STATE_MASK;
+                const bool paused = state == RAFTGPU_STATE_PROBE ? (f[s] & RAFTGPU_PF_PAUSED) != 0
+                                                                 : (state == RAFTGPU_STATE_REPLICATE ? (f[s] & RAFTGPU_PF_INS_FULL) != 0 : true);
+                if (((peers >> s) & 1u) && !paused) send |= 1u << s;
+            }
+        }
+        const uint32_t cnt = __popc(send);
+        uint32_t incl = cnt;  // inclusive warp scan
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= static_cast<uint32_t>(d)) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;
+        unsigned long long pos = 0;
+        if (lane == 31) pos = atomicAdd(count, static_cast<unsigned long long>(total));
+        pos = __shfl_sync(0xffffffffu, pos, 31) + (incl - cnt);
+#pragma unroll
+        for (int s = 0; s < kSlots; s++) {
+            if (!((send >> s) & 1u)) continue;
+            if (pos < capacity) {
+                const uint64_t w0 = static_cast<uint64_t>(g) | (static_cast<uint64_t>(s) << 32) |
+                                    (static_cast<uint64_t>(prs[s] != RAFTGPU_INVALID_INDEX ? RAFTGPU_SEND_SNAPSHOT : 0u) << 40);
+                reinterpret_cast<ulonglong2 *>(out)[pos] = make_ulonglong2(w0, nx[s]);
+            }
+            pos++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // tally_kernel: ProgressTracker::tally_votes (tracker.rs:313-340) per group:
 // granted / rejected over voters, JointConfig::vote_result (joint.rs:56-67) over
 // MajorityConfig::vote_result (majority.rs:130-154).

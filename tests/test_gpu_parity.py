@@ -914,6 +914,62 @@ def test_partial_ranges_and_bitmap_edges():
     arena.close()
 
 
+def test_send_list_vs_oracle():
+    """the post-commit send decisions (bcast_append over the groups whose commit
+    advanced, gated by Progress::is_paused) as a stream-compaction kernel; the same entries as the
+    oracle's loop, as a set (the reference iterates a HashMap: no order is promised)."""
+    n = 60_001
+    synth = B.Synth(n, 0x5EED000C)
+    cols = synth.initial
+    rng = np.random.default_rng(12)
+    learners = rng.random(n) < 0.3                      # a learner in slot 6: gets appends too
+    cols.meta[:n] |= (learners.astype(np.uint32) << np.uint32(16 + 6))
+    cols.next_idx[6, :n] = np.where(learners, cols.matched[0, :n] - 5, 0)
+    cols.pflags[6, :n] = np.where(learners, O.STATE_REPLICATE, 0)
+    # every pause reason: paused probes, full inflight windows, snapshot state, pending snapshot requests
+    cols.pflags[1, :n] |= np.where(rng.random(n) < 0.2, O.PF_INS_FULL, 0).astype(np.uint8)
+    cols.pflags[2, :n] = np.where(rng.random(n) < 0.1, O.STATE_SNAPSHOT, cols.pflags[2, :n])
+    cols.pflags[3, :n] = np.where(rng.random(n) < 0.1, O.STATE_PROBE | O.PF_PAUSED, cols.pflags[3, :n])
+    cols.pending_request_snapshot[4, :n] = np.where(rng.random(n) < 0.05, 77, 0)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(cols)
+    ref = O.copy_columns(cols)
+
+    def as_set(e):
+        return sorted(zip(e["group"].tolist(), e["peer_slot"].tolist(), e["flags"].tolist(), e["next_idx"].tolist()))
+
+    for rnd in range(3):
+        recs = synth.next_round().copy()
+        arena.enqueue(recs)
+        arena.step(0)
+        O.arena_apply(ref, recs, mode=0)
+        _, want_bm, _, _ = O.arena_recompute(ref)
+        want = O.arena_send_list(ref, want_bm)
+        got = arena.step_send_list(8 * n)
+        assert len(got) == len(want) > n // 10
+        assert as_set(got) == as_set(want), f"send list differs in round {rnd}"
+        assert not np.any(got["peer_slot"] == 0)                      # never to the leader itself
+    # a plain bcast_append (no bitmap) over a sub-range, through the device entry point
+    d_out, d_cnt = arena.device_alloc(16 * 8 * n), arena.device_alloc(8)
+    first, cnt = 1000, 40_003
+    arena.send_list_device(first, cnt, None, d_out, 8 * n, d_cnt)
+    total = np.zeros(1, dtype=np.uint64)
+    arena.d2h(total, d_cnt)
+    want = O.arena_send_list(ref, None, first, cnt)
+    assert total[0] == len(want)
+    got = np.zeros(len(want), dtype=B.SEND_ENTRY_DTYPE)
+    arena.d2h(got, d_out)
+    assert as_set(got) == as_set(want)
+    # too small a buffer: the count still says how many there are
+    arena.send_list_device(first, cnt, None, d_out, 10, d_cnt)
+    arena.d2h(total, d_cnt)
+    assert total[0] == len(want)
+    with pytest.raises(B.RaftGpuError):
+        arena.step_send_list(5)
+    arena.close()
+
+
 def test_vote_tally_batched_vs_oracle():
     n = 50_000
     rng = np.random.default_rng(7)

@@ -338,3 +338,41 @@ def test_vote_result_arena_matches_quorum_functions():
         assert r == O.joint_vote_result(a, b, vm)
         assert gr == sum(1 for s in range(8) if (inc | out) >> s & 1 and votes[s, 0] == 2)
         assert rj == sum(1 for s in range(8) if (inc | out) >> s & 1 and votes[s, 0] == 1)
+
+
+# ---- bcast_append behind maybe_commit (raft.rs:857-865, 1745-1748), every
+# send gated by Progress::is_paused (raft.rs:780-788).  The arena restatement must agree, peer by
+# peer, with the Progress-level is_paused that progress.rs:264-283 pins above.
+def test_send_list_arena_matches_progress_is_paused():
+    import random
+    rng = random.Random(9)
+    n = 300
+    c = O.new_columns(n, n)
+    expect = []
+    bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+    for g in range(n):
+        inc, out = rng.randrange(0, 256), rng.choice([0, rng.randrange(0, 256)])
+        learners = rng.randrange(0, 256) & ~(inc | out)
+        present = inc | out | learners
+        self_slot = rng.choice([None] + [s for s in range(8) if present >> s & 1]) if present else None
+        c.meta[g] = O.make_meta(inc, out, learners, self_slot)
+        adv = rng.random() < 0.5
+        if adv:
+            bm[g >> 5] |= np.uint32(1 << (g & 31))
+        for s in range(8):
+            state = rng.choice([PROBE, REPL, SNAP])
+            paused, full = rng.random() < 0.4, rng.random() < 0.4
+            c.pflags[s, g] = state | (O.PF_PAUSED if paused else 0) | (O.PF_INS_FULL if full else 0) | \
+                (O.PF_RECENT_ACTIVE if rng.random() < 0.5 else 0)
+            c.next_idx[s, g] = rng.randrange(1, 1 << 40)
+            c.pending_request_snapshot[s, g] = rng.choice([0, 0, 0, rng.randrange(1, 1 << 30)])
+            p = new_progress(state, 0, 0)
+            p.paused, p.ins_full = int(paused), int(full)
+            if adv and (present >> s & 1) and s != self_slot and not L.ro_progress_is_paused(C.byref(p)):
+                expect.append((g, s, 1 if c.pending_request_snapshot[s, g] else 0, int(c.next_idx[s, g])))
+    got = O.arena_send_list(c, bm)
+    assert list(zip(got["group"].tolist(), got["peer_slot"].tolist(), got["flags"].tolist(),
+                    got["next_idx"].tolist())) == expect
+    # no bitmap = a plain bcast_append over every group of the range
+    every = O.arena_send_list(c, None, 10, 100)
+    assert set(every["group"].tolist()) <= set(range(10, 110)) and len(every) > len(got) // 4

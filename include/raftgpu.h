@@ -454,6 +454,16 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
                              uint64_t *out_bytes, uint32_t *unit_of_record);
 int32_t raftgpu_step_begin_compact(raftgpu_arena *arena, const void *pinned_blob, uint64_t blob_bytes,
                                    uint32_t flags);
+/* Records in ordinary (pageable) host memory -> one step: the library's staging threads pack
+ * slices of the batch into the compact stream in pinned memory (cut at group boundaries, so the
+ * records of a group must be contiguous for the result to be tileable; any other order still
+ * works through the scatter kernel, one record per cell), then the step is submitted like
+ * raftgpu_step_begin_compact.  Nothing may have been enqueued for this step.  `records` can be
+ * reused as soon as the call returns.  A batch too hostile for the compact form (every record
+ * escaping to the side table) goes through raftgpu_enqueue_bulk + raftgpu_step_begin instead.
+ * raft.rs:1663-1743 + 893-904 for a whole tick, as one call. */
+int32_t raftgpu_step_begin_records(raftgpu_arena *arena, const raftgpu_append_resp *records, uint64_t n,
+                                   uint32_t flags);
 /* The same step for a blob that already sits in device memory (hdr = a host copy of its
  * header): raftgpu_compact_tile_index_device builds the tile table in d_tile_off -- room for
  * 3 * (ceil(n_groups / RAFTGPU_TILE_GROUPS) + 2) + 2 u32: the first unit of every tile, then each

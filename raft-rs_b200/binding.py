@@ -239,6 +239,7 @@ def lib() -> C.CDLL:
             "raftgpu_compact_bound": ([u64], u64),
             "raftgpu_pack_compact": ([vp, u64, vp, u64, C.POINTER(u64), vp], i32),
             "raftgpu_step_begin_compact": ([vp, vp, u64, u32], i32),
+            "raftgpu_step_begin_records": ([vp, vp, u64, u32], i32),
             "raftgpu_step_slot_results": ([vp, C.POINTER(vp), C.POINTER(u64)], i32),
             "raftgpu_compact_tile_index_device": ([vp, vp, vp, vp, vp, vp], i32),
             "raftgpu_step_compact_device": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, u32], i32),
@@ -623,6 +624,10 @@ class Arena:
 
     def host_free(self, buf: np.ndarray):
         self._ck(self._L.raftgpu_host_free(self._h, buf.ctypes.data), "host_free")
+
+    def step_begin_records(self, recs: np.ndarray, flags=0):
+        assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous
+        self._ck(self._L.raftgpu_step_begin_records(self._h, recs.ctypes.data, len(recs), flags), "step_begin_records")
 
     def step_begin_compact(self, blob: np.ndarray, n_bytes: int, flags=0):
         self._ck(self._L.raftgpu_step_begin_compact(self._h, blob.ctypes.data, n_bytes, flags),

@@ -1412,22 +1412,24 @@ int32_t raftgpu_enqueue_append_resp(raftgpu_arena *a, uint32_t ring, const raftg
     return rc;
 }
 
+static void ensure_pool(raftgpu_arena *a) {
+    if (a->pool) return;
+    int want = 16;
+    if (const char *e = getenv("RAFTGPU_HOST_THREADS")) want = atoi(e);
+    int avail = a->have_local_cpus ? CPU_COUNT(&a->local_cpus) : static_cast<int>(std::thread::hardware_concurrency());
+    want = std::max(1, std::min({want, static_cast<int>(a->n_rings), std::max(1, avail)}));
+    a->pool = new HostPool();
+    for (int t = 0; t < want; t++)
+        a->pool->threads.emplace_back(&HostPool::worker, a->pool, t, a->local_cpus, a->have_local_cpus, a->device * want);
+}
+
 int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, uint64_t n, uint32_t flags) {
     if (!a || (!recs && n)) return RAFTGPU_ERR_INVALID;
     StagingSet &s = a->sets[a->fill];
     if (s.in_flight) return RAFTGPU_ERR_BUSY;
     s.dirty = true;
     const bool sorted = (flags & RAFTGPU_BULK_SORTED) != 0;
-    if (!a->pool) {
-        int want = 16;
-        if (const char *e = getenv("RAFTGPU_HOST_THREADS")) want = atoi(e);
-        int avail = a->have_local_cpus ? CPU_COUNT(&a->local_cpus) : static_cast<int>(std::thread::hardware_concurrency());
-        want = std::max(1, std::min({want, static_cast<int>(a->n_rings), std::max(1, avail)}));
-        a->pool = new HostPool();
-        for (int t = 0; t < want; t++)
-            a->pool->threads.emplace_back(&HostPool::worker, a->pool, t, a->local_cpus, a->have_local_cpus,
-                                          a->device * want);
-    }
+    ensure_pool(a);
     const int T = static_cast<int>(a->pool->threads.size());
     if (n < 4096 || T == 1) {
         const int32_t rc = enqueue_ring(a, s, 0, recs, n, sorted, false);
@@ -1476,13 +1478,13 @@ int32_t raftgpu_enqueue_bulk(raftgpu_arena *a, const raftgpu_append_resp *recs, 
 // Submit one step.  ext != nullptr: zero-copy -- wave 0 is the caller's pinned packed buffer and the
 // GPU verifies the one-record-per-cell promise; otherwise wave 0 is what the rings staged.
 static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ext, uint64_t ext_n,
-                           const raftgpu_compact_hdr *cb = nullptr) {
+                           const raftgpu_compact_hdr *cb = nullptr, bool cb_resident = false) {
     if (!a) return RAFTGPU_ERR_INVALID;
     if (a->n_inflight >= 2) return fail(a, RAFTGPU_ERR_BUSY, "two steps already in flight: call raftgpu_step_wait");
     CK(a, cudaSetDevice(a->device));
     StagingSet &s = a->sets[a->fill];
     if (ext || cb) {
-        if (s.next_chunk.load() != 0 || !s.overflow_waves.empty())
+        if (!cb_resident && (s.next_chunk.load() != 0 || !s.overflow_waves.empty()))
             return fail(a, RAFTGPU_ERR_INVALID, "records were enqueued for this step: cannot mix with a zero-copy batch");
         if (ext_n > static_cast<uint64_t>(a->n_chunks) * kChunk)
             return fail(a, RAFTGPU_ERR_FULL, "zero-copy batch larger than the device staging buffer");
@@ -1501,8 +1503,10 @@ static int32_t step_submit(raftgpu_arena *a, uint32_t flags, const PackedRec *ex
     const uint64_t wave0 = cb ? cb->n_units : ext ? ext_n : static_cast<uint64_t>(used_chunks) * kChunk;
     if (ext) n_real = ext_n;
     if (cb) n_real = cb->n_records;
-    if (cb)
+    if (cb && !cb_resident)
         CK(a, cudaMemcpyAsync(s.d_recs, cb, cb->total_bytes, cudaMemcpyHostToDevice, a->s_h2d));
+    else if (cb)
+        ;  // raftgpu_step_begin_records has already queued the copies of its segments on s_h2d
     else if (wave0)
         CK(a, cudaMemcpyAsync(s.d_recs, ext ? ext : s.h_recs, wave0 * sizeof(PackedRec),
                               cudaMemcpyHostToDevice, a->s_h2d));
@@ -1660,35 +1664,46 @@ uint64_t raftgpu_compact_bound(uint64_t n) {
     return sizeof(raftgpu_compact_hdr) + align16(4 * (units / RAFTGPU_COMPACT_BLOCK + 2)) + align16(4 * units) + 24 * n + 64;
 }
 
-int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, void *out, uint64_t out_capacity,
-                             uint64_t *out_bytes, uint32_t *unit_of_record) {
-    if ((!records && n) || !out || !out_bytes) return RAFTGPU_ERR_INVALID;
-    if (reinterpret_cast<uintptr_t>(out) & 15u) return RAFTGPU_ERR_INVALID;
-    const uint64_t max_units = 3 * n + 8;
-    const uint64_t off_blocks = sizeof(raftgpu_compact_hdr);
-    const uint64_t off_units = off_blocks + align16(4 * (max_units / RAFTGPU_COMPACT_BLOCK + 2));
-    if (off_units > out_capacity) return RAFTGPU_ERR_FULL;
-    uint8_t *blob = static_cast<uint8_t *>(out);
-    uint32_t *g_base = reinterpret_cast<uint32_t *>(blob + off_blocks);
-    uint32_t *units = reinterpret_cast<uint32_t *>(blob + off_units);
-    const uint64_t unit_cap = std::min<uint64_t>((out_capacity - off_units) / 4, 0xfffffff0ull);
+namespace {
+
+// One packer pass over records[lo, hi) -- a slice that starts at a main record and never separates a
+// REJECT from its EXT: units and g_base words are written in place, side-table records are
+// collected in a vector.  Unit positions (and therefore g_base blocks) are relative to
+// the start of `units`, which the caller places on a RAFTGPU_COMPACT_BLOCK boundary of the stream.
+struct PackOut {
+    uint32_t *units = nullptr;
+    uint64_t unit_cap = 0;
+    uint32_t *g_base = nullptr;
+    uint64_t gbase_cap = 0;
     std::vector<raftgpu_append_resp> side;
-    uint64_t nu = 0, n_rec = 0;
-    uint64_t blocks_set = 0;  // g_base[b] is defined for b < blocks_set
-    bool tileable = true, have_prev_group = false;  // groups ascend and every run has a header
-    bool one_wave = true;                           // no (group, peer) cell twice (meaningful when tileable)
+    std::vector<uint32_t> esc_pos;  // unit positions of the ESC units (their side index is relative to `side`)
+    bool want_esc_pos = false;
+    uint64_t nu = 0, n_rec = 0, blocks_set = 0;
+    bool tileable = true, one_wave = true, any = false;
+    uint32_t first_group = 0, last_group = 0;
+};
+
+int32_t pack_core(const raftgpu_append_resp *records, uint64_t lo, uint64_t hi, PackOut &o, uint32_t *unit_of_record,
+                  uint32_t unit_base) {
+    const uint64_t n = hi, n_total = hi;
+    uint32_t *units = o.units;
+    uint32_t *g_base = o.g_base;
+    const uint64_t unit_cap = o.unit_cap;
+    uint64_t nu = o.nu;
+    bool have_prev_group = false;
     uint32_t prev_group = 0, seen_slots = 0;
     auto esc = [&](uint64_t i) -> bool {  // record i (and its EXT) to the side table, one ESC unit
-        if (nu >= unit_cap || side.size() >= kCuPad - 2) return false;
-        units[nu] = kCuEsc | (static_cast<uint32_t>(side.size()) << 2);
-        if (unit_of_record) unit_of_record[i] = static_cast<uint32_t>(nu);
+        if (nu >= unit_cap || o.side.size() >= kCuPad - 2) return false;
+        units[nu] = kCuEsc | (static_cast<uint32_t>(o.side.size()) << 2);
+        if (o.want_esc_pos) o.esc_pos.push_back(static_cast<uint32_t>(nu));
+        if (unit_of_record) unit_of_record[i] = unit_base + static_cast<uint32_t>(nu);
         nu++;
-        side.push_back(records[i]);
-        if ((records[i].flags & RAFTGPU_REC_REJECT) && i + 1 < n && (records[i + 1].flags & RAFTGPU_REC_EXT))
-            side.push_back(records[i + 1]);
+        o.side.push_back(records[i]);
+        if ((records[i].flags & RAFTGPU_REC_REJECT) && i + 1 < n_total && (records[i + 1].flags & RAFTGPU_REC_EXT))
+            o.side.push_back(records[i + 1]);
         return true;
     };
-    uint64_t i = 0;
+    uint64_t i = lo;
     while (i < n) {
         if (records[i].flags & RAFTGPU_REC_EXT) {  // stray continuation: carries nothing by itself
             if (unit_of_record) unit_of_record[i] = UINT32_MAX;
@@ -1700,6 +1715,67 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
         const uint32_t g = records[i].group;
         uint64_t e = i, max_index = 0;
         uint32_t run_units = 0;
+        // Fast path for what a round mostly consists of: a run of plain accepts / leader-local
+        // records.  Same segmentation and same units as the general code below.
+        {
+            uint32_t odd = 0;
+            while (e < n && run_units < 8u) {
+                const raftgpu_append_resp &r = records[e];
+                if (r.group != g) break;
+                odd |= (r.flags & ~RAFTGPU_REC_LOCAL) | (r.peer_slot >> 3);
+                max_index = std::max(max_index, r.index);
+                run_units++;
+                e++;
+            }
+            // the run must end where the general scan would end it: not in front of a REJECT that
+            // would still fit, nor in front of an EXT
+            if (e < n && ((records[e].flags & RAFTGPU_REC_EXT) || (records[e].group == g && run_units < 8u))) odd = 1;
+            const uint64_t base = max_index > 0x3fffu ? max_index - 0x3fffu : 0;
+            const uint64_t b = nu / RAFTGPU_COMPACT_BLOCK;
+            if (!odd && base < (1ull << 48) && b < o.gbase_cap && nu + 2 + run_units <= unit_cap) {
+                while (o.blocks_set <= b) g_base[o.blocks_set++] = g;
+                const uint32_t gb = g_base[b];
+                if (g >= gb && g - gb <= 0xfffu) {
+                    if (have_prev_group && g < prev_group) o.tileable = false;
+                    if (!have_prev_group || g != prev_group) seen_slots = 0;
+                    if (!o.any) {
+                        o.any = true;
+                        o.first_group = g;
+                    }
+                    o.last_group = g;
+                    prev_group = g;
+                    have_prev_group = true;
+                    units[nu++] = kCuHdrA | (static_cast<uint32_t>(base & 0x3fffffffu) << 2);
+                    units[nu++] = kCuHdrB | ((g - gb) << 2) | (static_cast<uint32_t>(base >> 30) << 14);
+                    bool ok = true;
+                    for (uint32_t back = 0; back < run_units; back++) {
+                        const raftgpu_append_resp &r = records[i + back];
+                        const bool is_local = r.flags != 0;
+                        if ((seen_slots >> r.peer_slot) & 1u) o.one_wave = false;
+                        seen_slots |= 1u << r.peer_slot;
+                        const uint64_t cdl = is_local ? (r.commit == 0 ? kCuNoCommit : r.commit - r.index) : r.index - r.commit;
+                        const bool fits = r.index >= base && (is_local ? (r.commit == 0 || (r.commit >= r.index && cdl < kCuNoCommit))
+                                                                         : (r.commit <= r.index && cdl <= 255u));
+                        if (fits) {
+                            units[nu] = kCuRec | (is_local ? kCuLocal : 0u) | (back << 3) | (static_cast<uint32_t>(r.peer_slot) << 6) |
+                                        (static_cast<uint32_t>(r.index - base) << 10) | (static_cast<uint32_t>(cdl) << 24);
+                            if (unit_of_record) unit_of_record[i + back] = unit_base + static_cast<uint32_t>(nu);
+                            nu++;
+                        } else if (!esc(i + back)) {
+                            ok = false;
+                            break;
+                        }
+                    }
+                    if (!ok) return RAFTGPU_ERR_FULL;
+                    o.n_rec += run_units;
+                    i = e;
+                    continue;
+                }
+            }
+            e = i;  // general path
+            max_index = 0;
+            run_units = 0;
+        }
         while (e < n) {
             const raftgpu_append_resp &r = records[e];
             if (r.flags & RAFTGPU_REC_EXT) {
@@ -1717,13 +1793,19 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
         bool header = base < (1ull << 48);  // also for a run of ESC units only: the fused kernel finds records by their run
         if (header) {
             const uint64_t b = nu / RAFTGPU_COMPACT_BLOCK;
-            while (blocks_set <= b) g_base[blocks_set++] = g;  // first header of the block names its g_base
+            if (b >= o.gbase_cap) return RAFTGPU_ERR_FULL;
+            while (o.blocks_set <= b) g_base[o.blocks_set++] = g;  // first header of the block names its g_base
             const uint32_t gb = g_base[b];
             if (g < gb || g - gb > 0xfffu) header = false;
         }
         if (nu + 2 + run_units > unit_cap) return RAFTGPU_ERR_FULL;
-        if (!header || (have_prev_group && g < prev_group)) tileable = false;
+        if (!header || (have_prev_group && g < prev_group)) o.tileable = false;
         if (!have_prev_group || g != prev_group) seen_slots = 0;
+        if (!o.any) {
+            o.any = true;
+            o.first_group = g;
+        }
+        o.last_group = g;
         prev_group = g;
         have_prev_group = true;
         if (header) {
@@ -1738,9 +1820,9 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
                 if (unit_of_record) unit_of_record[k] = UINT32_MAX;
                 continue;
             }
-            n_rec++;
+            o.n_rec++;
             if (r.peer_slot < RAFTGPU_SLOTS) {
-                if ((seen_slots >> r.peer_slot) & 1u) one_wave = false;
+                if ((seen_slots >> r.peer_slot) & 1u) o.one_wave = false;
                 seen_slots |= 1u << r.peer_slot;
             }
             const bool is_local = r.flags == RAFTGPU_REC_LOCAL, is_reject = r.flags == RAFTGPU_REC_REJECT;
@@ -1764,7 +1846,7 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
             if (compact && is_reject) {
                 // the EXT's next_probe_index hint as a signed 29-bit delta from the index; a snapshot
                 // request (rare) sends the record to the side table
-                const bool has_ext = k + 1 < n && (records[k + 1].flags & RAFTGPU_REC_EXT);
+                const bool has_ext = k + 1 < n_total && (records[k + 1].flags & RAFTGPU_REC_EXT);
                 const uint64_t hint = has_ext ? records[k + 1].index : 0;
                 const uint64_t snapshot = has_ext ? records[k + 1].commit : RAFTGPU_INVALID_INDEX;
                 const int64_t d = static_cast<int64_t>(hint - r.index);
@@ -1776,7 +1858,7 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
             if (compact) {
                 units[nu] = kCuRec | (is_local ? kCuLocal : 0u) | (is_reject ? kCuReject : 0u) | (back << 3) |
                             (static_cast<uint32_t>(r.peer_slot) << 6) | (static_cast<uint32_t>(r.index - base) << 10) | (cd << 24);
-                if (unit_of_record) unit_of_record[k] = static_cast<uint32_t>(nu);
+                if (unit_of_record) unit_of_record[k] = unit_base + static_cast<uint32_t>(nu);
                 nu++;
                 back++;
                 if (is_reject) {
@@ -1790,30 +1872,170 @@ int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, voi
         }
         i = e;
     }
+    o.nu = nu;
+    return RAFTGPU_OK;
+}
+
+}  // namespace
+
+int32_t raftgpu_pack_compact(const raftgpu_append_resp *records, uint64_t n, void *out, uint64_t out_capacity,
+                             uint64_t *out_bytes, uint32_t *unit_of_record) {
+    if ((!records && n) || !out || !out_bytes) return RAFTGPU_ERR_INVALID;
+    if (reinterpret_cast<uintptr_t>(out) & 15u) return RAFTGPU_ERR_INVALID;
+    const uint64_t max_units = 3 * n + 8;
+    const uint64_t off_blocks = sizeof(raftgpu_compact_hdr);
+    const uint64_t off_units = off_blocks + align16(4 * (max_units / RAFTGPU_COMPACT_BLOCK + 2));
+    if (off_units > out_capacity) return RAFTGPU_ERR_FULL;
+    uint8_t *blob = static_cast<uint8_t *>(out);
+    PackOut o;
+    o.g_base = reinterpret_cast<uint32_t *>(blob + off_blocks);
+    o.gbase_cap = max_units / RAFTGPU_COMPACT_BLOCK + 2;
+    o.units = reinterpret_cast<uint32_t *>(blob + off_units);
+    o.unit_cap = std::min<uint64_t>((out_capacity - off_units) / 4, 0xfffffff0ull);
+    const int32_t rc = pack_core(records, 0, n, o, unit_of_record, 0);
+    if (rc != RAFTGPU_OK) return rc;
+    uint64_t nu = o.nu;
+    uint32_t *units = o.units;
     const uint64_t n_blocks = (nu + RAFTGPU_COMPACT_BLOCK - 1) / RAFTGPU_COMPACT_BLOCK;
-    while (blocks_set < n_blocks) g_base[blocks_set++] = 0;
+    while (o.blocks_set < n_blocks) o.g_base[o.blocks_set++] = 0;
     while (nu & 3u) {
-        if (nu >= unit_cap) return RAFTGPU_ERR_FULL;
+        if (nu >= o.unit_cap) return RAFTGPU_ERR_FULL;
         units[nu++] = kCuEsc | (kCuPad << 2);  // the fused kernel fetches units in 16-byte pieces
     }
     const uint64_t off_side = off_units + align16(4 * nu);
-    const uint64_t total = off_side + align16(side.size() * sizeof(raftgpu_append_resp));
+    const uint64_t total = off_side + align16(o.side.size() * sizeof(raftgpu_append_resp));
     if (total > out_capacity) return RAFTGPU_ERR_FULL;
-    if (!side.empty()) memcpy(blob + off_side, side.data(), side.size() * sizeof(raftgpu_append_resp));
+    if (!o.side.empty()) memcpy(blob + off_side, o.side.data(), o.side.size() * sizeof(raftgpu_append_resp));
     raftgpu_compact_hdr h{};
     h.magic = RAFTGPU_COMPACT_MAGIC;
     h.n_units = static_cast<uint32_t>(nu);
     h.n_blocks = static_cast<uint32_t>(n_blocks);
-    h.n_side = static_cast<uint32_t>(side.size());
-    h.n_records = n_rec;
+    h.n_side = static_cast<uint32_t>(o.side.size());
+    h.n_records = o.n_rec;
     h.off_blocks = off_blocks;
     h.off_units = off_units;
     h.off_side = off_side;
     h.total_bytes = total;
-    h.flags = (tileable ? RAFTGPU_COMPACT_TILEABLE : 0u) | (tileable && one_wave ? RAFTGPU_COMPACT_ONE_WAVE : 0u);
+    h.flags = (o.tileable ? RAFTGPU_COMPACT_TILEABLE : 0u) | (o.tileable && o.one_wave ? RAFTGPU_COMPACT_ONE_WAVE : 0u);
     memcpy(blob, &h, sizeof(h));
     *out_bytes = total;
     return RAFTGPU_OK;
+}
+
+// Records in pageable host memory -> compact stream -> step, in one call.  The library's staging
+// threads each pack one slice of the batch (cut at group boundaries) straight into the staging set's
+// pinned buffer; a slice's units start on a unit-block boundary of the stream, so the slices need
+// nothing from each other (g_base words are per block).  The device copy is the standard blob:
+// header + g_base table, the unit segments (each padded to a block), the side records.
+static int32_t step_begin_records_compact(raftgpu_arena *a, const raftgpu_append_resp *recs, uint64_t n, uint32_t flags) {
+    if (!a || (!recs && n)) return RAFTGPU_ERR_INVALID;
+    if (a->n_inflight >= 2) return fail(a, RAFTGPU_ERR_BUSY, "two steps already in flight: call raftgpu_step_wait");
+    StagingSet &s = a->sets[a->fill];
+    if (s.in_flight) return RAFTGPU_ERR_BUSY;
+    if (s.next_chunk.load() != 0 || !s.overflow_waves.empty())
+        return fail(a, RAFTGPU_ERR_INVALID, "records were enqueued for this step: cannot mix with raftgpu_step_begin_records");
+    CK(a, cudaSetDevice(a->device));
+    ensure_pool(a);
+    const int T = (n < 8192) ? 1 : static_cast<int>(a->pool->threads.size());
+    // slices: a cut never separates a REJECT from its EXT, nor the records of one group
+    std::vector<uint64_t> cut(T + 1, n);
+    cut[0] = 0;
+    while (cut[0] < n && (recs[cut[0]].flags & RAFTGPU_REC_EXT)) cut[0]++;  // stray continuations carry nothing
+    for (int t = 1; t < T; t++) {
+        uint64_t c = std::max(cut[t - 1], n * t / T);
+        while (c < n && c > 0 && ((recs[c].flags & RAFTGPU_REC_EXT) || recs[c].group == recs[c - 1].group)) c++;
+        cut[t] = c;
+    }
+    // the staging set's pinned buffer: [header + g_base table | T unit regions | side records]
+    uint8_t *buf = reinterpret_cast<uint8_t *>(s.h_recs);
+    const uint64_t cap_bytes = static_cast<uint64_t>(a->n_chunks) * kChunk * sizeof(PackedRec);
+    const uint64_t block_bytes = 4ull * RAFTGPU_COMPACT_BLOCK;
+    const uint64_t meta_bytes = (sizeof(raftgpu_compact_hdr) + cap_bytes / RAFTGPU_COMPACT_BLOCK + 4096) & ~4095ull;
+    if (cap_bytes < meta_bytes + (T + 1) * block_bytes * 2) return RAFTGPU_ERR_FULL;
+    const uint64_t side_bytes = ((cap_bytes - meta_bytes) / 4) & ~4095ull;
+    const uint64_t region_bytes = ((cap_bytes - meta_bytes - side_bytes) / T) / block_bytes * block_bytes;
+    std::vector<PackOut> po(T);
+    std::vector<int32_t> rcs(T, RAFTGPU_OK);
+    std::vector<std::vector<uint32_t>> gb(T);
+    auto work = [&](int t) {
+        PackOut &o = po[t];
+        o.units = reinterpret_cast<uint32_t *>(buf + meta_bytes + static_cast<uint64_t>(t) * region_bytes);
+        o.unit_cap = region_bytes / 4;
+        gb[t].assign(region_bytes / block_bytes + 1, 0u);
+        o.g_base = gb[t].data();
+        o.gbase_cap = gb[t].size();
+        o.want_esc_pos = true;
+        if (cut[t + 1] > cut[t]) rcs[t] = pack_core(recs, cut[t], cut[t + 1], o, nullptr, 0);
+        if (rcs[t] != RAFTGPU_OK) return;
+        while (o.nu % RAFTGPU_COMPACT_BLOCK) o.units[o.nu++] = kCuEsc | (kCuPad << 2);  // next slice starts a block
+    };
+    if (T == 1)
+        work(0);
+    else
+        a->pool->run(work);
+    for (int t = 0; t < T; t++)
+        if (rcs[t] != RAFTGPU_OK) return rcs[t];
+    // stitch: offsets, flags, g_base table, side records (+ their ESC indexes)
+    raftgpu_compact_hdr h{};
+    h.magic = RAFTGPU_COMPACT_MAGIC;
+    h.off_blocks = sizeof(raftgpu_compact_hdr);
+    bool tileable = true, one_wave = true, have_prev = false;
+    uint32_t prev_last = 0;
+    uint64_t nu = 0, ns = 0;
+    uint32_t *g_base = reinterpret_cast<uint32_t *>(buf + h.off_blocks);
+    raftgpu_append_resp *side = reinterpret_cast<raftgpu_append_resp *>(buf + cap_bytes - side_bytes);
+    std::vector<uint64_t> unit_off(T, 0);
+    for (int t = 0; t < T; t++) {
+        PackOut &o = po[t];
+        unit_off[t] = nu;
+        tileable = tileable && o.tileable && (!o.any || !have_prev || o.first_group > prev_last);
+        one_wave = one_wave && o.one_wave;
+        if (o.any) {
+            have_prev = true;
+            prev_last = o.last_group;
+        }
+        const uint64_t nb = o.nu / RAFTGPU_COMPACT_BLOCK;
+        for (uint64_t b2 = 0; b2 < nb; b2++) g_base[nu / RAFTGPU_COMPACT_BLOCK + b2] = b2 < o.blocks_set ? gb[t][b2] : 0u;
+        if (!o.side.empty()) {
+            if ((ns + o.side.size()) * sizeof(raftgpu_append_resp) > side_bytes || ns + o.side.size() >= kCuPad - 2)
+                return RAFTGPU_ERR_FULL;
+            memcpy(side + ns, o.side.data(), o.side.size() * sizeof(raftgpu_append_resp));
+            for (uint32_t pos : o.esc_pos) o.units[pos] += static_cast<uint32_t>(ns) << 2;
+        }
+        nu += o.nu;
+        ns += o.side.size();
+        h.n_records += o.n_rec;
+    }
+    if (nu > 0xfffffff0ull) return RAFTGPU_ERR_FULL;
+    h.n_units = static_cast<uint32_t>(nu);
+    h.n_blocks = static_cast<uint32_t>(nu / RAFTGPU_COMPACT_BLOCK);
+    h.n_side = static_cast<uint32_t>(ns);
+    h.off_units = meta_bytes;
+    h.off_side = align16(h.off_units + 4 * nu);
+    h.total_bytes = h.off_side + align16(ns * sizeof(raftgpu_append_resp));
+    h.flags = (tileable ? RAFTGPU_COMPACT_TILEABLE : 0u) | (tileable && one_wave ? RAFTGPU_COMPACT_ONE_WAVE : 0u);
+    const uint64_t dev_bytes = (static_cast<uint64_t>(a->n_chunks) * kChunk + a->overflow_records) * sizeof(PackedRec);
+    if (h.total_bytes > dev_bytes) return RAFTGPU_ERR_FULL;
+    memcpy(buf, &h, sizeof(h));
+    // H2D: header + g_base, every slice's units to its place in the stream, the side records
+    uint8_t *d = reinterpret_cast<uint8_t *>(s.d_recs);
+    CK(a, cudaMemcpyAsync(d, buf, h.off_blocks + 4ull * h.n_blocks, cudaMemcpyHostToDevice, a->s_h2d));
+    for (int t = 0; t < T; t++)
+        if (po[t].nu)
+            CK(a, cudaMemcpyAsync(d + h.off_units + 4 * unit_off[t], po[t].units, 4 * po[t].nu, cudaMemcpyHostToDevice, a->s_h2d));
+    if (ns) CK(a, cudaMemcpyAsync(d + h.off_side, side, ns * sizeof(raftgpu_append_resp), cudaMemcpyHostToDevice, a->s_h2d));
+    s.dirty = true;
+    return step_submit(a, flags, nullptr, 0, &h, /*cb_resident=*/true);
+}
+
+int32_t raftgpu_step_begin_records(raftgpu_arena *a, const raftgpu_append_resp *recs, uint64_t n, uint32_t flags) {
+    int32_t rc = step_begin_records_compact(a, recs, n, flags);
+    if (rc != RAFTGPU_ERR_FULL) return rc;
+    // A batch the compact form cannot hold in the staging buffer (groups in no order, every record
+    // escaping to the side table): the general staging path -- packed 16-byte records, waves.
+    rc = raftgpu_enqueue_bulk(a, recs, n, 0);
+    if (rc != RAFTGPU_OK) return rc;
+    return raftgpu_step_begin(a, flags);
 }
 
 int32_t raftgpu_step_begin_compact(raftgpu_arena *a, const void *pinned_blob, uint64_t blob_bytes, uint32_t flags) {

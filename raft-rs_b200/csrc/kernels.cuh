@@ -1820,8 +1820,9 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
                                 rec.index = index;
                                 rec.commit = commit;
                             }
-                        } else {  // ESC: the full record sits in the side table (payload units / padding: nothing)
+                        } else {  // ESC: the full record sits in the side table (a stray payload unit: nothing)
                             const uint32_t k = u >> 2;
+                            if (k == kCuPad) break;  // padding only ever follows the last run of a slice
                             if (k < kCuPad && k < a.src.n_side) {
                                 const uint64_t *sp = reinterpret_cast<const uint64_t *>(a.src.side + k);
                                 rec.w0 = sp[0];
@@ -2004,18 +2005,27 @@ compact_tile_index_kernel(CompactSrc src, uint32_t n_groups, uint32_t *__restric
         const uint32_t hb = src.units[i + 1];
         if ((hb & 3u) != kCuHdrB) continue;
         const uint32_t g = src.g_base[i / RAFTGPU_COMPACT_BLOCK] + ((hb >> 2) & 0xfffu);
-        // previous run header, if any
+        // previous run header, if any: at most one run (2 + 8 units) back, not counting the padding
+        // that fills a staging slice up to its block boundary (raftgpu_step_begin_records)
         bool have_prev = false;
         uint32_t gp = 0;
-        for (uint32_t b = 2; b <= 11u && b <= i; b++) {
+        for (uint32_t b = 2, real = 0; b <= i && real <= 10u; b++) {
             const uint32_t ua = src.units[i - b];
+            if (ua == (kCuEsc | (kCuPad << 2))) continue;
+            real++;
             if ((ua & 3u) == kCuHdrA && (src.units[i - b + 1] & 3u) == kCuHdrB) {
                 gp = src.g_base[(i - b) / RAFTGPU_COMPACT_BLOCK] + ((src.units[i - b + 1] >> 2) & 0xfffu);
                 have_prev = true;
                 break;
             }
         }
-        if (i > 0 && !have_prev) atomicAdd(bad, 1u);       // something before this run is not a run
+        if (!have_prev) {  // the first run of the stream: everything before it must be padding
+            for (uint32_t b = 1; b <= i && b <= 12u; b++)
+                if (src.units[i - b] != (kCuEsc | (kCuPad << 2))) {
+                    atomicAdd(bad, 1u);
+                    break;
+                }
+        }
         if (have_prev && gp > g) atomicAdd(bad, 1u);       // groups must ascend
         if (g >= n_groups) {
             atomicAdd(bad, 1u);

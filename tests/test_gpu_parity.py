@@ -712,6 +712,71 @@ def test_fused_tile_step_learners_group_commit_and_crowded_tiles():
     arena.close()
 
 
+@pytest.mark.parametrize("n,joint,mode", [(100_003, False, "sorted"), (40_000, True, "sorted"), (50_000, False, "shuffled"),
+                                          (30_000, False, "pipelined"), (900, False, "sorted")])
+def test_step_begin_records_vs_oracle(n, joint, mode):
+    """raftgpu_step_begin_records: 24-byte records in pageable memory, packed into the compact stream
+    by the library's staging threads (one slice each, stitched at unit-block boundaries), one step.
+    Sorted batches take the fused kernel; `shuffled` group order the scatter kernel; `pipelined`
+    adds several acks per cell, which the fused kernel applies in order."""
+    synth = B.Synth(n, 0x5EED000D, joint=joint)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    rank = np.random.default_rng(4).permutation(n + 1)
+    for rnd in range(4):
+        recs = synth.next_round().copy()
+        if mode == "shuffled":
+            recs = np.ascontiguousarray(recs[np.argsort(rank[recs["group"]], kind="stable")])
+        if mode == "pipelined":
+            extra = []
+            for g in range(rnd, n, 5):
+                m = int(ref.matched[2, g])
+                for d_ in (3, 1, 6):
+                    extra.append((g, 2, 0, 0, m + d_, m))
+            recs = np.concatenate([recs, np.array(extra, dtype=B.APPEND_RESP_DTYPE)])
+            recs = np.ascontiguousarray(recs[np.argsort(recs["group"], kind="stable")])
+        arena.step_begin_records(recs, B.STEP_READ_COMMITTED)
+        if rnd % 2 == 0:        # two steps in flight every other round
+            recs2 = synth.next_round().copy()
+            if mode == "shuffled":
+                recs2 = np.ascontiguousarray(recs2[np.argsort(rank[recs2["group"]], kind="stable")])
+            arena.step_begin_records(recs2, B.STEP_READ_COMMITTED)
+        r = arena.step_wait()
+        O.arena_apply(ref, recs, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        assert r.n_advanced == want_adv and r.n_duplicates == 0
+        if mode != "shuffled":     # (the fallback path counts packed records, EXT payloads included)
+            assert r.n_records == np.count_nonzero((recs["flags"] & B.REC_EXT) == 0)
+            assert r.h2d_bytes < 12 * len(recs)
+        bm, com = arena.step_results(n)
+        assert np.array_equal(bm, want_bm[: len(bm)])
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+        if rnd % 2 == 0:
+            r = arena.step_wait()
+            O.arena_apply(ref, recs2, mode=0)
+            want_adv, want_bm, _, _ = O.arena_recompute(ref)
+            assert r.n_advanced == want_adv
+            bm, com = arena.step_results(n)
+            assert np.array_equal(bm, want_bm[: len(bm)])
+        assert_columns_equal(arena.read_columns(n), ref, n, f"step_begin_records {mode} round {rnd}")
+    # empty batch; then mixing with enqueued records is refused
+    arena.step_begin_records(np.zeros(0, dtype=B.APPEND_RESP_DTYPE), 0)
+    assert arena.step_wait().n_records == 0
+    one = np.zeros(1, dtype=B.APPEND_RESP_DTYPE)
+    one[0] = (3, 1, 0, 0, int(ref.matched[1, 3]) + 1, 0)
+    arena.enqueue(one)
+    with pytest.raises(B.RaftGpuError):
+        arena.step_begin_records(one, 0)
+    arena.step(0)
+    O.arena_apply(ref, one, mode=0)
+    O.arena_recompute(ref)
+    assert_columns_equal(arena.read_columns(n), ref, n, "after the refused mix")
+    arena.close()
+
+
 def _compact_round(arena, n, recs, ref, blob, d_bufs, ordered=False):
     """One fused compact step (raftgpu_step_compact_device) on `recs` (group order) vs the oracle."""
     nb, units = B.pack_compact(recs, blob, want_units=True)

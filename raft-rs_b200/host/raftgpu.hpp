@@ -295,6 +295,12 @@ class ProgressTracker {
         const auto it = slots_.find(id);
         return it == slots_.end() ? std::nullopt : std::optional<uint32_t>(it->second);
     }
+    // the peer id that lives in `slot` (0 when the slot is free): for results that name slots
+    uint64_t id_of(uint32_t slot) const {
+        for (const auto &kv : slots_)
+            if (kv.second == slot) return kv.first;
+        return 0;
+    }
     void set_self(uint64_t id) { self_id_ = id; }
 
     // tracker.rs:261-275 get / get_mut
@@ -511,8 +517,47 @@ class MultiRaftDriver {
         return (bm[group >> 5] >> (group & 31)) & 1u;
     }
 
+    // ---- one tick as one call: collect the tick's messages, hand them over together -------------
+    // (raftgpu_step_begin_records: the library packs them into the compact stream; the records of
+    // one group must be pushed back to back for the fused kernel, which then applies several
+    // responses of one peer in arrival order)
+    void push_append_response(const ProgressTracker &prs, uint64_t from, uint64_t index, uint64_t commit, bool reject = false,
+                              uint64_t next_probe_index = 0, uint64_t request_snapshot = INVALID_INDEX) {
+        const auto slot = prs.slot_of(from);
+        if (!slot) throw StepPeerNotFound();  // raw_node.rs:402-411
+        tick_.push_back({prs.group(), static_cast<uint8_t>(*slot), static_cast<uint8_t>(reject ? RAFTGPU_REC_REJECT : 0), 0, index, commit});
+        if (reject) tick_.push_back({prs.group(), static_cast<uint8_t>(*slot), RAFTGPU_REC_EXT, 0, next_probe_index, request_snapshot});
+    }
+    void push_local_progress(const ProgressTracker &prs, uint64_t self_id, uint64_t persisted, uint64_t last_index) {
+        const auto slot = prs.slot_of(self_id);
+        if (!slot) throw StepPeerNotFound();
+        tick_.push_back({prs.group(), static_cast<uint8_t>(*slot), RAFTGPU_REC_LOCAL, 0, persisted, last_index});
+    }
+    raftgpu_step_result step_tick(uint32_t flags = RAFTGPU_STEP_READ_COMMITTED) {
+        raftgpu_step_result res{};
+        arena_->check(raftgpu_step_begin_records(arena_->raw(), tick_.data(), tick_.size(), flags), "step_begin_records");
+        tick_.clear();
+        arena_->check(raftgpu_step_wait(arena_->raw(), &res), "step_wait");
+        return res;
+    }
+    // bcast_append for the groups whose commit index advanced in the last step (raft.rs:1745-1748,
+    // 857-865), minus the paused peers (raft.rs:780-788): the MsgAppends the caller has to build
+    std::vector<raftgpu_send_entry> send_list() const {
+        std::vector<raftgpu_send_entry> out(64);
+        uint64_t n = 0;
+        int32_t rc = raftgpu_step_send_list(arena_->raw(), out.data(), out.size(), &n);
+        if (rc == RAFTGPU_ERR_FULL) {
+            out.resize(n);
+            rc = raftgpu_step_send_list(arena_->raw(), out.data(), out.size(), &n);
+        }
+        arena_->check(rc, "step_send_list");
+        out.resize(n);
+        return out;
+    }
+
   private:
     std::shared_ptr<Arena> arena_;
+    std::vector<raftgpu_append_resp> tick_;
 };
 
 }  // namespace raft

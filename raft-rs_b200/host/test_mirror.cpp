@@ -299,6 +299,49 @@ static void test_leader_append_response() {
     }
 }
 
+// A whole tick as one call, then the post-commit send decisions: the acknowledgement that commits
+// index 3 makes the leader bcast_append (raft.rs:1745-1748 -> 857-865) to every follower that is not
+// paused (raft.rs:780-788); test_raft_paper.rs:499-534 test_leader_commit_entry expects exactly
+// those MsgAppends.  Two responses of one peer in one tick apply in arrival order.
+static void test_tick_batch_and_send_list() {
+    Fixture f(3);
+    f.log.reset(2, 0, 2);
+    f.log.become_leader();
+    f.log.set_log_bounds(2, 3);
+    for (uint64_t id : {2, 3}) f.prs.get_mut(id)->become_replicate();
+    MultiRaftDriver drv(g_arena);
+    drv.push_append_response(f.prs, 2, 2, 0);
+    drv.push_append_response(f.prs, 2, 3, 2);   // the same peer again: pipelined acks
+    drv.push_local_progress(f.prs, 1, 3, 3);    // the leader has persisted its own entry
+    const raftgpu_step_result r = drv.step_tick();
+    CHECK(r.n_records == 3 && r.n_advanced == 1 && r.n_duplicates == 0, "tick: %llu records, %llu advanced",
+          (unsigned long long)r.n_records, (unsigned long long)r.n_advanced);
+    CHECK(f.log.committed() == 3 && drv.advanced(f.prs.group()), "committed = %llu, want 3", (unsigned long long)f.log.committed());
+    CHECK(f.prs.get(2)->matched == 3 && f.prs.get(2)->next_idx == 4 && f.prs.get(2)->committed_index == 2, "peer 2 after both acks");
+    auto sends = drv.send_list();
+    CHECK(sends.size() == 2, "send list has %zu entries, want 2 (both followers)", sends.size());
+    std::set<uint64_t> to;
+    for (const auto &e : sends) {
+        CHECK(e.group == f.prs.group() && e.flags == 0, "entry of another group / unexpected flags");
+        to.insert(f.prs.id_of(e.peer_slot));
+        CHECK(e.next_idx == f.prs.get(f.prs.id_of(e.peer_slot))->next_idx, "entry carries the peer's next_idx");
+    }
+    CHECK(to == (std::set<uint64_t>{2, 3}), "MsgAppend goes to 2 and 3, never to the leader itself");
+    // a paused probe and a full inflight window are skipped (progress.rs:210-216)
+    f.prs.get_mut(3)->become_probe();
+    f.prs.get_mut(3)->pause();
+    f.log.set_log_bounds(2, 4);
+    drv.push_append_response(f.prs, 2, 4, 3);
+    drv.push_local_progress(f.prs, 1, 4, 4);
+    drv.step_tick();
+    sends = drv.send_list();
+    CHECK(f.log.committed() == 4 && sends.size() == 1 && f.prs.id_of(sends[0].peer_slot) == 2, "only the unpaused follower is sent to");
+    // nothing advanced -> nothing to broadcast
+    drv.push_append_response(f.prs, 2, 4, 4);
+    drv.step_tick();
+    CHECK(drv.send_list().empty(), "no commit, no bcast_append");
+}
+
 // check_quorum (raft.rs:1963-1973) -> quorum_recently_active / has_quorum (tracker.rs:346-372)
 static void test_quorum_activity() {
     Fixture f(3);
@@ -364,6 +407,7 @@ int main() {
     test_commit();
     test_group_commit();
     test_leader_append_response();
+    test_tick_batch_and_send_list();
     test_quorum_activity();
     test_errors();
     std::printf("%s: %d checks, %d failed\n", g_failed ? "FAILED" : "ok", g_checks, g_failed);

@@ -1050,11 +1050,12 @@ int32_t raftgpu_step_sorted_device(raftgpu_arena *a, void *stream, const void *d
     const uint32_t hint = simple5 ? 0x1fu : (a->voter_hint & 0xffu);
     const uint32_t H = static_cast<uint32_t>(__builtin_popcount(hint));
     // variant knobs (tuning): RAFTGPU_TILE_VARIANT = <threads per consumer group><groups>, e.g. 2562, 5122, 2563
-    static const int variant = getenv("RAFTGPU_TILE_VARIANT") ? atoi(getenv("RAFTGPU_TILE_VARIANT")) : 2562;
-    static const int cap_env = getenv("RAFTGPU_TILE_RECCAP") ? atoi(getenv("RAFTGPU_TILE_RECCAP")) : 1024;
+    static const int variant = getenv("RAFTGPU_TILE_VARIANT") ? atoi(getenv("RAFTGPU_TILE_VARIANT")) : 2563;
+    static const int cap_env = getenv("RAFTGPU_TILE_RECCAP") ? atoi(getenv("RAFTGPU_TILE_RECCAP")) : 0;
     const uint32_t rec_cap = static_cast<uint32_t>(cap_env) & ~3u;
     const uint32_t stage_bytes = tile_stage_bytes(H, rec_cap);
-    int stages = std::min<int>(kFMaxStages, static_cast<int>(a->tile_smem / stage_bytes));
+    static const int stages_env = getenv("RAFTGPU_TILE_STAGES") ? atoi(getenv("RAFTGPU_TILE_STAGES")) : kFMaxStages;
+    int stages = std::min<int>(std::min<int>(kFMaxStages, stages_env), static_cast<int>(a->tile_smem / stage_bytes));
     if (stages < 2 || H == 0) return fail(a, RAFTGPU_ERR_INVALID, "configuration too wide for the fused tile kernel");
     TileArgs t{};
     t.recs = static_cast<const PackedRec *>(d_packed_records);

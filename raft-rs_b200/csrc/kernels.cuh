@@ -1210,22 +1210,35 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             uint32_t *s_meta = reinterpret_cast<uint32_t *>(sb + o_meta);
             uint8_t *s_flags = sb + o_flags;
             const PackedRec *s_recs = reinterpret_cast<const PackedRec *>(sb + o_recs);
+            const ulonglong2 *g_recs = reinterpret_cast<const ulonglong2 *>(a.recs + rbeg);
+            ulonglong2 q_next = make_ulonglong2(kPkExt, 0ull);
+            if (staged == 0 && tid < cnt) q_next = g_recs[tid];  // direct records: in flight during the wait
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
             if (a.dbg && tid == 0) t0 = clock64();
             mbar_wait(&full_bar[st], ph);
             if (a.dbg && tid == 0) t1 = clock64();
 
             // ---- A: the tile's records against the shared-memory rows (raft.rs:1663-1743)
+            // Records come from the stage when they were staged (rec_cap > 0), else straight from HBM /
+            // L2 (rec_cap == 0: the stage holds rows only, which buys a fifth stage; the records of a
+            // tile were prefetched into L2 while the previous tile was processed, and the loop fetches
+            // record k + kCT while it works on record k).
+            auto rec_at = [&](uint32_t j) -> ulonglong2 {
+                if (j < staged) return reinterpret_cast<const ulonglong2 *>(s_recs)[j];
+                if (j < cnt) return g_recs[j];
+                return make_ulonglong2(kPkExt, 0ull);
+            };
+            if (staged != 0) q_next = rec_at(tid);
             for (uint32_t k = tid; k < cnt; k += kCT) {
                 // Fast path: a record for a staged cell of a peer in Replicate or Probe state -- accept,
                 // leader-local, or a rejection without a snapshot request -- straight on the packed
                 // words and the shared-memory cell.  Statement for statement the branches of apply_one
                 // (raft.rs:1674-1743, 1010-1014; progress.rs:95-114, 138-206); everything else (Snapshot
-                // state, request_snapshot, WIDE commits, learners, records near the staging boundary)
-                // takes the general path below.
-                const bool in_smem = staged == cnt || k + 4u <= staged;  // whole tile staged, or far from the cut
+                // state, request_snapshot, WIDE commits, learners) takes the general path below.
+                const ulonglong2 q = q_next;
+                q_next = rec_at(k + kCT);
+                const bool in_smem = true;
                 if (in_smem) {
-                    const ulonglong2 q = reinterpret_cast<const ulonglong2 *>(s_recs)[k];
                     const uint64_t w0 = q.x;
                     if (w0 & kPkExt) {
                         if (a.results) a.results[rbeg + k] = 0;
@@ -1243,10 +1256,9 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                                                             RAFTGPU_META_LEARN(s_meta[gl])) >> slot) & 1u);
                         bool simple = present && state != RAFTGPU_STATE_SNAPSHOT;
                         uint64_t hint_idx = 0;
-                        if (simple && (w0 & kPkReject) && k + 2u >= staged) simple = false;  // payloads at the very end
                         if (simple && (w0 & kPkReject)) {  // look at the EXT payloads: [kind 1 hint] [kind 2 snapshot request]
-                            const ulonglong2 e1 = reinterpret_cast<const ulonglong2 *>(s_recs)[k + 1];
-                            const ulonglong2 e2 = reinterpret_cast<const ulonglong2 *>(s_recs)[k + 2];
+                            const ulonglong2 e1 = rec_at(k + 1);   // (past the end: a padding EXT of kind 0)
+                            const ulonglong2 e2 = rec_at(k + 2);
                             const bool x1 = (e1.x & kPkExt) != 0, x2 = x1 && (e2.x & kPkExt) != 0;
                             if (x1 && (e1.x >> 40) == 1) hint_idx = e1.y;
                             if ((x1 && (e1.x >> 40) == 2) || (x2 && (e2.x >> 40) == 2)) simple = false;
@@ -1319,8 +1331,8 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                         }
                     }
                 }
-                // General path.  A record whose EXT payloads might straddle the staged prefix is read from HBM.
-                const bool from_smem = in_smem;
+                // General path: from the stage when the whole tile is staged, else from HBM.
+                const bool from_smem = staged == cnt;
                 const void *base = from_smem ? static_cast<const void *>(s_recs) : static_cast<const void *>(a.recs + rbeg);
                 const uint64_t nn = from_smem ? staged : cnt;
                 const RecRegs rec = load_rec<true>(base, k, nn);
@@ -1401,6 +1413,10 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             named_bar_sync(bar_id, kCT);
             if (a.dbg && tid == 0) t3 = clock64();
             if (tid == 0) mbar_arrive(&done_bar[st]);
+            if (kFRecCap == 0 && tile + tile_step < n_tiles) {  // direct records: next tile's range -> L2 (one line = 8 records)
+                const uint32_t nn = nx_end - nx_beg;
+                for (uint32_t k = tid * 8u; k < nn; k += kCT * 8u) prefetch_l2(a.recs + nx_beg + k);
+            }
             if (a.dbg && tid == 0) {
                 t4 = clock64();
                 atomicAdd(&a.dbg[0], static_cast<unsigned long long>(t1 - t0));  // waiting for the TMA loads

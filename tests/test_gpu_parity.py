@@ -916,6 +916,24 @@ def test_fused_compact_step_corner_cases():
     arena.close()
 
 
+def test_fused_kernels_in_their_other_configurations():
+    """The tuning knobs are read once per process, so the non-default forms of the fused kernels run in
+    a child process: records staged in shared memory by TMA (RAFTGPU_TILE_RECCAP=1024, the earlier
+    default -- including the tile with more records than the staging holds), two consumer groups,
+    and the compact kernel with two consumer groups and a small unit staging."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RAFTGPU_TILE_RECCAP="1024", RAFTGPU_TILE_VARIANT="2562", RAFTGPU_CTILE_GROUPS="2",
+               RAFTGPU_CTILE_UNITCAP="512")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "fused_tile_step_learners or (fused_tile_step_vs_oracle and 100003) or "
+                              "fused_compact_step_corner or (fused_compact_step_vs_oracle and 70001)"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_mci_and_properties_at_full_size():
     """1M x 7 joint: maximal_committed_index for every group vs the oracle, plus
     size-independent properties: idempotence, monotone commit, joint = min of halves."""

@@ -1,8 +1,9 @@
 #!/bin/bash
 OUT=gpurun_out/exp; mkdir -p $OUT
+timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused" > $OUT/pytest.txt 2>&1; tail -n 3 $OUT/pytest.txt
 run() {
-  echo "== $*"; env "$@" timeout 300 python bench.py --steps 40 --warmup 4 --no-cpu-baseline --e2e-steps 2 $EXTRA > $OUT/b.json 2> $OUT/b.err
-  python - <<PY
+  echo "== $*"; env "$@" RAFTGPU_TILE_DEBUG=1 timeout 300 python bench.py --steps 40 --warmup 4 --no-cpu-baseline --e2e-steps 2 $EXTRA > $OUT/b.json 2> $OUT/b.err
+  grep "tile debug" $OUT/b.err; python - <<PY
 import json
 try:
     d=json.loads(open("$OUT/b.json").read().strip().splitlines()[-1])
@@ -12,6 +13,6 @@ except Exception as e:
 PY
 }
 run A=1
+run RAFTGPU_TILE_STAGES=5
+run RAFTGPU_TILE_VARIANT=2562
 EXTRA="--workload cfg4" run A=1
-EXTRA="--workload cfg4" run RAFTGPU_TILE_VARIANT=2562 RAFTGPU_TILE_RECCAP=1024
-EXTRA="--workload cfg4" run RAFTGPU_TILE_VARIANT=2562

@@ -536,7 +536,8 @@ int32_t raftgpu_send_list_device(raftgpu_arena *arena, void *stream, uint32_t fi
                                  const uint32_t *d_adv_bitmap, raftgpu_send_entry *d_out, uint64_t capacity,
                                  uint64_t *d_count);
 /* The same for the last completed step (its advanced bitmap, all allocated groups), entries
- * copied to host memory; synchronous.  RAFTGPU_ERR_FULL (with *out_n = the number needed) when
+ * copied to host memory; synchronous.  The pause flags and next_idx are read when the kernel runs:
+ * call it before the NEXT step is submitted if the list has to reflect exactly this step.  RAFTGPU_ERR_FULL (with *out_n = the number needed) when
  * `capacity` is too small. */
 int32_t raftgpu_step_send_list(raftgpu_arena *arena, raftgpu_send_entry *out, uint64_t capacity, uint64_t *out_n);
 

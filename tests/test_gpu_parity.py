@@ -934,6 +934,151 @@ def test_fused_kernels_in_their_other_configurations():
     assert " passed" in r.stdout and "failed" not in r.stdout
 
 
+def _random_state(n, rng):
+    """Arbitrary configurations (joint, learners, group commit, no self) and per-peer states."""
+    c = O.new_columns(n, n)
+    for g in range(n):
+        inc = int(rng.integers(1, 256))
+        out = int(rng.integers(0, 256)) if rng.random() < 0.3 else 0
+        learners = int(rng.integers(0, 256)) & ~(inc | out) if rng.random() < 0.4 else 0
+        voters = [s_ for s_ in range(8) if (inc | out) >> s_ & 1]
+        self_slot = int(rng.choice(voters)) if rng.random() < 0.9 else None
+        c.meta[g] = O.make_meta(inc, out, learners, self_slot, group_commit=bool(rng.random() < 0.15))
+        base = int(rng.integers(100, 1 << 40))
+        c.last_index[g] = base + int(rng.integers(0, 10))
+        c.term_start[g] = (1 << 64) - 1 if rng.random() < 0.05 else max(1, base - int(rng.integers(0, 30)))
+        c.committed[g] = base - int(rng.integers(0, 40))
+        c.term[g] = int(rng.integers(1, 1000))
+        for s_ in range(8):
+            m = base - int(rng.integers(0, 50))
+            c.matched[s_, g] = m
+            c.next_idx[s_, g] = m + 1 + int(rng.integers(0, 5))
+            c.peer_committed[s_, g] = m - int(rng.integers(0, 5))
+            state = int(rng.choice([O.STATE_PROBE, O.STATE_REPLICATE, O.STATE_REPLICATE, O.STATE_SNAPSHOT]))
+            c.pflags[s_, g] = state | (O.PF_PAUSED if rng.random() < 0.3 else 0) | (O.PF_INS_FULL if rng.random() < 0.2 else 0) | \
+                (O.PF_RECENT_ACTIVE if rng.random() < 0.5 else 0)
+            c.pending_snapshot[s_, g] = m + int(rng.integers(0, 6)) if state == O.STATE_SNAPSHOT else 0
+            c.pending_request_snapshot[s_, g] = int(rng.integers(1, 100)) if rng.random() < 0.05 else 0
+            c.commit_group_id[s_, g] = int(rng.integers(0, 4))
+    return c
+
+
+def _random_batch(ref, n, rng, per_cell):
+    """Group-ordered batch; `per_cell` > 1 lets a (group, peer) cell receive several records."""
+    rows = []
+    for g in range(n):
+        if rng.random() < 0.3:
+            continue
+        meta = int(ref.meta[g])
+        has_self, self_slot = bool(meta & O.META_HAS_SELF), (meta >> 24) & 7
+        slots = rng.permutation(8)[: int(rng.integers(1, 6))]
+        for s_ in slots:
+            s_ = int(s_)
+            for _ in range(int(rng.integers(1, per_cell + 1))):
+                m, nx = int(ref.matched[s_, g]), int(ref.next_idx[s_, g])
+                kind = rng.random()
+                if has_self and s_ == self_slot:
+                    idx = m + int(rng.integers(0, 8))
+                    rows.append((g, s_, B.REC_LOCAL, 0, idx, 0 if rng.random() < 0.2 else idx + int(rng.integers(0, 5))))
+                elif kind < 0.7:
+                    idx = max(0, m + int(rng.integers(-6, 12)))
+                    commit = idx + 3 if rng.random() < 0.03 else max(0, idx - int(rng.integers(0, 300 if rng.random() < 0.05 else 6)))
+                    rows.append((g, s_, 0, 0, idx, commit))
+                else:
+                    idx = int(rng.choice([nx - 1, m, m + 1, m + 3, max(0, m - 2)]))
+                    rows.append((g, s_, B.REC_REJECT, 0, idx, max(0, m - int(rng.integers(0, 4)))))
+                    if rng.random() < 0.85:
+                        rows.append((g, s_, B.REC_EXT, 0, max(0, idx + int(rng.integers(-5, 3))),
+                                     int(rng.integers(1, 1 << 30)) if rng.random() < 0.2 else 0))
+    return np.array(rows, dtype=B.APPEND_RESP_DTYPE) if rows else np.zeros(0, dtype=B.APPEND_RESP_DTYPE)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_every_ingest_path_agrees_with_the_oracle_on_random_states(seed):
+    """Differential test: arbitrary configurations / peer states, random group-ordered batches (accepts,
+    stale acks, commits above the index, leader-local records, rejections with and without hint and
+    snapshot request, peers the group does not have), through EVERY way of handing a batch to the
+    engine -- rings + waves, bulk staging, zero-copy packed, zero-copy compact (fused), the records
+    API, the device-resident fused kernels -- each compared with the oracle column by column."""
+    rng = np.random.default_rng(seed)
+    n = 2500
+    init = _random_state(n, rng)
+    ref = O.copy_columns(init)
+    names = ["enqueue", "bulk", "packed", "compact", "records", "fused16", "fusedc"]
+    arenas = {}
+    for name in names:
+        # (the wave-splitting paths keep later waves in an overflow area sized from the arena capacity)
+        a = B.Arena(32 * n if name in ("enqueue", "bulk") else n)
+        a.group_alloc_range(n)
+        a.load_columns(init)
+        arenas[name] = a
+    pk_host = arenas["packed"].host_alloc_packed(40 * n)
+    blob_host = arenas["compact"].host_alloc_bytes(B.compact_bound(40 * n))
+    pk = np.zeros((40 * n, 2), dtype=np.uint64)
+    f16 = arenas["fused16"]
+    d16 = (f16.device_alloc(pk.nbytes), f16.device_alloc(4 * (n // B.tile_groups() + 2)))
+    blob, dc = _compact_bufs(arenas["fusedc"], n, 40)
+    for rnd in range(5):
+        per_cell = 3 if rnd >= 3 else 1          # the last rounds: several records per (group, peer)
+        recs = _random_batch(ref, n, rng, per_cell)
+        O.arena_apply(ref, recs, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        words = (n + 31) // 32
+        for name in names:
+            a = arenas[name]
+            if per_cell > 1 and name in ("packed", "fused16"):
+                continue                          # these promise one record per cell
+            if name == "enqueue":
+                a.enqueue(recs)
+                r = a.step(0)
+            elif name == "bulk":
+                a.enqueue_bulk(recs, sorted_by_group=True)
+                r = a.step(0)
+            elif name == "packed":
+                k = a.pack_records(recs, pk_host)
+                a.step_begin_packed(pk_host, k, 0)
+                r = a.step_wait()
+            elif name == "compact":
+                nb, _ = B.pack_compact(recs, blob_host)
+                a.step_begin_compact(blob_host, nb, 0)
+                r = a.step_wait()
+            elif name == "records":
+                a.step_begin_records(recs, 0)
+                r = a.step_wait()
+            elif name == "fused16":
+                k = a.pack_records(recs, pk)
+                a.h2d(d16[0], pk[:max(k, 1)])
+                a.h2d(d16[1], B.tile_index(pk, k, n))
+                a.step_sorted_device(d16[0], k, d16[1])
+                r = None
+            else:
+                _compact_round_nocheck(a, recs, blob, dc)
+                r = None
+            if r is not None:
+                assert r.n_advanced == want_adv and r.n_duplicates == 0, (name, rnd)
+                bm, _ = a.step_results(n)
+                assert np.array_equal(bm[:words], want_bm[:words]), (name, rnd)
+            assert_columns_equal(a.read_columns(n), ref, n, f"{name}, round {rnd}, seed {seed}")
+        if per_cell == 1:     # fused16 / packed skipped the multi-record rounds: keep them in step
+            continue
+        for name in ("packed", "fused16"):
+            arenas[name].load_columns(ref)
+    for a in arenas.values():
+        a.close()
+
+
+def _compact_round_nocheck(arena, recs, blob, d_bufs):
+    nb, _ = B.pack_compact(recs, blob)
+    d_blob, d_off, d_res, d_bm, d_com, d_bad = d_bufs
+    arena.h2d(d_blob, blob[:nb])
+    arena.h2d(d_bad, np.zeros(1, dtype=np.uint32))
+    arena.compact_tile_index_device(d_blob, blob, d_off, d_bad)
+    arena.step_compact_device(d_blob, blob, d_off, d_dup=d_bad)
+    bad = np.zeros(1, dtype=np.uint32)
+    arena.d2h(bad, d_bad)
+    assert bad[0] == 0
+
+
 def test_mci_and_properties_at_full_size():
     """1M x 7 joint: maximal_committed_index for every group vs the oracle, plus
     size-independent properties: idempotence, monotone commit, joint = min of halves."""

@@ -1248,86 +1248,92 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                     const uint32_t g = static_cast<uint32_t>(w0);
                     const uint32_t gl = g - g0;
                     if (!(w0 & kPkWide) && gl < ng && ((hint >> slot) & 1u)) {
-                        const uint32_t r = __popc(hint & ((1u << slot) - 1u));
+                        const uint32_t r = kSimple5 ? slot : static_cast<uint32_t>(__popc(hint & ((1u << slot) - 1u)));
                         const uint32_t ci = r * R64 + gl;
                         const uint32_t f0 = s_flags[r * kFRow8 + gl];
                         const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
                         const bool present = kSimple5 || (((RAFTGPU_META_IN(s_meta[gl]) | RAFTGPU_META_OUT(s_meta[gl]) |
                                                             RAFTGPU_META_LEARN(s_meta[gl])) >> slot) & 1u);
-                        bool simple = present && state != RAFTGPU_STATE_SNAPSHOT;
-                        uint64_t hint_idx = 0;
-                        if (simple && (w0 & kPkReject)) {  // look at the EXT payloads: [kind 1 hint] [kind 2 snapshot request]
+                        const bool simple = present && state != RAFTGPU_STATE_SNAPSHOT;
+                        if (simple && !(w0 & kPkReject)) {
+                            // accept / leader-local: maybe_update (progress.rs:138-150), shared by the accept path
+                            // (raft.rs:1674-1677, 1724-1730) and the leader-local path (raft.rs:974-991, 1010-1014);
+                            // only an accept looks at is_paused() and may move a probing peer to Replicate.
+                            // Written as straight-line selects: this is ~98 % of all records.
+                            const uint64_t index = q.y;
+                            const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
+                            const bool is_local = (w0 & kPkLocal) != 0;
+                            const uint64_t m = s_matched[ci], nx = s_next[ci], pcv = s_pc[ci];
+                            local[0]++;
+                            if (is_local && delta != kPkNoCommit) s_li[gl] = index + delta;   // raft.rs:974-991
+                            const uint64_t commit = index - delta;
+                            if (!is_local && commit > pcv) s_pc[ci] = commit;                 // raft.rs:1677
+                            const bool probe = state == RAFTGPU_STATE_PROBE;
+                            const bool need = m < index;
+                            const bool old_paused = !is_local && (f0 & (probe ? RAFTGPU_PF_PAUSED : RAFTGPU_PF_INS_FULL)) != 0;
+                            const bool trans = need && !is_local && probe;                    // raft.rs:1730 become_replicate
+                            uint32_t f = is_local ? f0 : (f0 | RAFTGPU_PF_RECENT_ACTIVE);     // raft.rs:1674
+                            if (need) f &= ~RAFTGPU_PF_PAUSED;
+                            if (trans)
+                                f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_REPLICATE;
+                            uint64_t nnx = nx < index + 1 ? index + 1 : nx;
+                            if (trans) {
+                                nnx = index + 1;                                              // next_idx = matched + 1
+                                c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
+                            }
+                            local[1] += need ? 1u : 0u;
+                            if (need) s_matched[ci] = index;
+                            if (nnx != nx) s_next[ci] = nnx;
+                            if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
+                            if (a.results)
+                                a.results[rbeg + k] = static_cast<uint8_t>(need ? (RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u)) : 0u);
+                            continue;
+                        }
+                        if (simple) {  // a rejection: look at its EXT payloads: [kind 1 hint] [kind 2 snapshot request]
+                            uint64_t hint_idx = 0;
+                            bool snapshot_req = false;
                             const ulonglong2 e1 = rec_at(k + 1);   // (past the end: a padding EXT of kind 0)
                             const ulonglong2 e2 = rec_at(k + 2);
                             const bool x1 = (e1.x & kPkExt) != 0, x2 = x1 && (e2.x & kPkExt) != 0;
                             if (x1 && (e1.x >> 40) == 1) hint_idx = e1.y;
-                            if ((x1 && (e1.x >> 40) == 2) || (x2 && (e2.x >> 40) == 2)) simple = false;
-                        }
-                        if (simple) {
-                            const uint64_t index = q.y;
-                            const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
-                            uint64_t m = s_matched[ci], nx = s_next[ci];
-                            const uint64_t m0 = m, nx0 = nx;
-                            uint32_t f = f0, res = 0;
-                            local[0]++;
-                            const bool is_local = (w0 & kPkLocal) != 0;
-                            if (is_local) {
-                                if (delta != kPkNoCommit) s_li[gl] = index + delta;  // raft.rs:974-991
-                            } else {
-                                f |= RAFTGPU_PF_RECENT_ACTIVE;                       // raft.rs:1674
-                                const uint64_t commit = index - delta;
-                                if (commit > s_pc[ci]) s_pc[ci] = commit;           // raft.rs:1677
-                            }
-                            if (w0 & kPkReject) {                                    // progress.rs:168-206, no snapshot request
+                            if ((x1 && (e1.x >> 40) == 2) || (x2 && (e2.x >> 40) == 2)) snapshot_req = true;
+                            if (!snapshot_req) {
+                                // maybe_decr_to without a snapshot request (progress.rs:168-206)
+                                const uint64_t index = q.y;
+                                const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
+                                uint64_t m = s_matched[ci], nx = s_next[ci];
+                                const uint64_t nx0 = nx;
+                                uint32_t f = f0 | RAFTGPU_PF_RECENT_ACTIVE, res = 0;         // raft.rs:1674
+                                local[0]++;
                                 local[2]++;
+                                const uint64_t commit = index - delta;
+                                if (commit > s_pc[ci]) s_pc[ci] = commit;                   // raft.rs:1677
                                 bool ok;
                                 if (state == RAFTGPU_STATE_REPLICATE) {
-                                    ok = index > m;                                  // :173-177 stale otherwise
-                                    if (ok) nx = m + 1;                              // :178-179
+                                    ok = index > m;                                          // :173-177 stale otherwise
+                                    if (ok) nx = m + 1;                                      // :178-179
                                 } else if (nx == 0 || nx - 1 != index) {
-                                    ok = false;                                      // :188-192 stale
+                                    ok = false;                                              // :188-192 stale
                                 } else {
-                                    nx = umin64(index, hint_idx + 1);                // :195-199
+                                    nx = umin64(index, hint_idx + 1);                        // :195-199
                                     if (nx < 1) nx = 1;
-                                    f &= ~RAFTGPU_PF_PAUSED;                         // :204
+                                    f &= ~RAFTGPU_PF_PAUSED;                                 // :204
                                     ok = true;
                                 }
                                 if (ok) {
                                     local[3]++;
                                     res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
-                                    if (state == RAFTGPU_STATE_REPLICATE) {          // raft.rs:1716-1718 become_probe
-                                        f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) |
-                                            RAFTGPU_STATE_PROBE;
+                                    if (state == RAFTGPU_STATE_REPLICATE) {                  // raft.rs:1716-1718 become_probe
+                                        f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_PROBE;
                                         c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
                                         nx = m + 1;
                                     }
                                 }
-                            } else {
-                                // maybe_update (progress.rs:138-150): shared by the accept path (raft.rs:1724-1730)
-                                // and the leader-local path (raft.rs:1010-1014); only an accept looks at
-                                // is_paused() and may move a probing peer to Replicate
-                                const bool old_paused = !is_local && (state == RAFTGPU_STATE_PROBE ? (f & RAFTGPU_PF_PAUSED) != 0
-                                                                                                   : (f & RAFTGPU_PF_INS_FULL) != 0);
-                                const bool need = m < index;
-                                if (need) {
-                                    m = index;
-                                    f &= ~RAFTGPU_PF_PAUSED;
-                                    local[1]++;
-                                    res = RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u);
-                                }
-                                if (nx < index + 1) nx = index + 1;
-                                if (need && !is_local && state == RAFTGPU_STATE_PROBE) {  // raft.rs:1730 become_replicate
-                                    f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) |
-                                        RAFTGPU_STATE_REPLICATE;
-                                    c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
-                                    nx = m + 1;
-                                }
+                                if (nx != nx0) s_next[ci] = nx;
+                                if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
+                                if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
+                                continue;
                             }
-                            if (m != m0) s_matched[ci] = m;
-                            if (nx != nx0) s_next[ci] = nx;
-                            if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
-                            if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
-                            continue;
                         }
                     }
                 }

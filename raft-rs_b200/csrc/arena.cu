@@ -494,7 +494,11 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
                               static_cast<int>(a->tile_smem)));                                              \
     TRYC(cudaFuncSetAttribute(step_tile_kernel<true, CT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                               static_cast<int>(a->tile_smem)))
-#if RAFTGPU_TILE_GROUPS == 128
+#if RAFTGPU_TILE_GROUPS == 192
+    RAFTGPU_TILE_ATTR(192, 3);
+    RAFTGPU_TILE_ATTR(192, 4);
+    RAFTGPU_TILE_ATTR(192, 5);
+#elif RAFTGPU_TILE_GROUPS == 128
     RAFTGPU_TILE_ATTR(128, 3);
     RAFTGPU_TILE_ATTR(128, 4);
     RAFTGPU_TILE_ATTR(128, 6);
@@ -1082,7 +1086,13 @@ int32_t raftgpu_step_sorted_device(raftgpu_arena *a, void *stream, const void *d
         else                                                                               \
             step_tile_kernel<false, CT, NG><<<blocks, CT * NG + 64, smem, st>>>(a->cols, t); \
     } while (0)
-#if RAFTGPU_TILE_GROUPS == 128
+#if RAFTGPU_TILE_GROUPS == 192
+    switch (variant) {
+    case 1923: RAFTGPU_LAUNCH_TILE(192, 3); break;
+    case 1925: RAFTGPU_LAUNCH_TILE(192, 5); break;
+    default: RAFTGPU_LAUNCH_TILE(192, 4); break;
+    }
+#elif RAFTGPU_TILE_GROUPS == 128
     switch (variant) {
     case 1283: RAFTGPU_LAUNCH_TILE(128, 3); break;
     case 1286: RAFTGPU_LAUNCH_TILE(128, 6); break;

@@ -1,0 +1,208 @@
+// k_common.cuh -- the arena columns, counters, the quorum selection (MajorityConfig / JointConfig::committed_index), block-level counter flush.
+// Part of kernels.cuh (included there, inside namespace raftgpu; not a standalone header).
+
+constexpr int kSlots = RAFTGPU_SLOTS;
+
+// Device view of the arena: per-peer columns are [kSlots][cap], per-group [cap].
+struct Columns {
+    uint32_t cap;
+    uint64_t *matched;
+    uint64_t *next_idx;
+    uint64_t *peer_committed;
+    uint64_t *pending_snapshot;
+    uint64_t *pending_req_snapshot;
+    uint64_t *commit_group_id;
+    uint8_t *pflags;
+    uint8_t *votes;
+    uint32_t *meta;
+    uint64_t *committed;
+    uint64_t *term_start;
+    uint64_t *last_index;
+};
+
+enum Counter : int {
+    kCntRecomputes = 0,
+    kCntAdvanced,
+    kCntRecords,
+    kCntUpdates,
+    kCntRejects,
+    kCntDecrements,
+    kCntNoProgress,
+    kCntVotes,
+    kCntCount
+};
+
+// Fire-and-forget L2 prefetch: costs no destination register, so it deepens the memory pipeline
+// beyond what registers x occupancy allow (the kernels here are long-scoreboard bound).
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------
+// MajorityConfig::committed_index without group commit (majority.rs:70-101):
+// the q-th largest acked index of the voters in `mask`, q = n/2 + 1
+// (util.rs:118-120); the empty config yields u64::MAX (majority.rs:71-75).
+
+// compare-exchange, larger value first
+__device__ __forceinline__ void cex(uint64_t &a, uint64_t &b) {
+    const bool lt = a < b;
+    const uint64_t hi = lt ? b : a, lo = lt ? a : b;
+    a = hi;
+    b = lo;
+}
+
+// General form.  Non-members are zeroed, which leaves the top-q ranks of the
+// members intact (q <= n); a 19-comparator network sorts the 8 slots in
+// descending order (the reference's stable sort_by, majority.rs:95 -- ties are
+// equal values, so any order of them selects the same index) and the q-th
+// element is picked.
+__device__ __forceinline__ uint64_t quorum_index(const uint64_t (&v)[kSlots], uint32_t mask) {
+    if (mask == 0) return UINT64_MAX;
+    const uint32_t q = (static_cast<uint32_t>(__popc(mask)) >> 1) + 1;
+    uint64_t w0 = (mask & 1u) ? v[0] : 0, w1 = (mask & 2u) ? v[1] : 0, w2 = (mask & 4u) ? v[2] : 0,
+             w3 = (mask & 8u) ? v[3] : 0, w4 = (mask & 16u) ? v[4] : 0, w5 = (mask & 32u) ? v[5] : 0,
+             w6 = (mask & 64u) ? v[6] : 0, w7 = (mask & 128u) ? v[7] : 0;
+    // Batcher / optimal 19-comparator network for 8 inputs
+    cex(w0, w1); cex(w2, w3); cex(w4, w5); cex(w6, w7);
+    cex(w0, w2); cex(w1, w3); cex(w4, w6); cex(w5, w7);
+    cex(w1, w2); cex(w5, w6); cex(w0, w4); cex(w3, w7);
+    cex(w1, w5); cex(w2, w6);
+    cex(w1, w4); cex(w3, w6);
+    cex(w2, w4); cex(w3, w5);
+    cex(w3, w4);
+    // q in 1..5 for up to 8 voters
+    uint64_t r = w0;
+    r = q == 2 ? w1 : r;
+    r = q == 3 ? w2 : r;
+    r = q == 4 ? w3 : r;
+    r = q == 5 ? w4 : r;
+    return r;
+}
+
+// The common 5-voter case (q = 3): the median, by the classic 10 min/max form
+// med5(a..e) = med3(e, max(min(a,b),min(c,d)), min(max(a,b),max(c,d))).
+__device__ __forceinline__ uint64_t median5(uint64_t a, uint64_t b, uint64_t c, uint64_t d,
+                                            uint64_t e) {
+    const uint64_t lo = umax64(umin64(a, b), umin64(c, d));
+    const uint64_t hi = umin64(umax64(a, b), umax64(c, d));
+    return umax64(umin64(lo, hi), umin64(umax64(lo, hi), e));
+}
+
+// MajorityConfig::committed_index WITH group commit (majority.rs:70-124), the
+// literal algorithm: gather, stable descending sort, then the scan of :102-123.
+// Rare path (ProgressTracker::group_commit is off by default), kept out of line
+// so its local arrays do not cost the common path registers.
+__device__ __noinline__ void majority_group_commit(const uint64_t *v, const uint64_t *gid,
+                                                   uint32_t mask, uint64_t *out_index,
+                                                   bool *out_use_gc) {
+    if (mask == 0) {  // :71-75
+        *out_index = UINT64_MAX;
+        *out_use_gc = true;
+        return;
+    }
+    uint64_t idx[kSlots], grp[kSlots];
+    int n = 0;
+    for (int s = 0; s < kSlots; s++) {
+        if ((mask >> s) & 1u) {  // :77-85 (voters without progress do not occur in a tracker)
+            idx[n] = v[s];
+            grp[n] = gid[s];
+            n++;
+        }
+    }
+    for (int i = 1; i < n; i++) {  // :95 stable sort, descending by index
+        uint64_t xi = idx[i], xg = grp[i];
+        int j = i;
+        while (j > 0 && idx[j - 1] < xi) {
+            idx[j] = idx[j - 1];
+            grp[j] = grp[j - 1];
+            j--;
+        }
+        idx[j] = xi;
+        grp[j] = xg;
+    }
+    const int quorum = n / 2 + 1;  // :97
+    const uint64_t quorum_commit_index = idx[quorum - 1];
+    uint64_t checked_group_id = grp[quorum - 1];
+    bool single_group = true;
+    for (int i = 0; i < n; i++) {  // :105-118
+        if (grp[i] == 0) {
+            single_group = false;
+            continue;
+        }
+        if (checked_group_id == 0) {
+            checked_group_id = grp[i];
+            continue;
+        }
+        if (checked_group_id == grp[i]) continue;
+        *out_index = umin64(idx[i], quorum_commit_index);
+        *out_use_gc = true;
+        return;
+    }
+    *out_index = single_group ? quorum_commit_index : idx[n - 1];  // :119-123
+    *out_use_gc = false;
+}
+
+// ProgressTracker::maximal_committed_index (tracker.rs:294-298) of group g:
+// JointConfig::committed_index (joint.rs:47-51) over both majority halves, reading
+// matched / commit_group_id through the ProgressMap AckedIndexer (tracker.rs:183-190).
+__device__ __forceinline__ void group_mci(const Columns &c, uint32_t g, uint32_t meta, uint64_t &mci,
+                                          bool &use_gc) {
+    const uint32_t in = RAFTGPU_META_IN(meta), out = RAFTGPU_META_OUT(meta);
+    const uint32_t voters = in | out;
+    uint64_t v[kSlots];
+#pragma unroll
+    for (int s = 0; s < kSlots; s++)
+        v[s] = ((voters >> s) & 1u) ? c.matched[static_cast<size_t>(s) * c.cap + g] : 0ull;
+    if (!(meta & RAFTGPU_META_GROUP_COMMIT)) {
+        const uint64_t i_idx = quorum_index(v, in);
+        const uint64_t o_idx = quorum_index(v, out);  // empty outgoing => u64::MAX
+        mci = umin64(i_idx, o_idx);                    // joint.rs:50
+        // a non-empty half reports false (majority.rs:99-101), an empty one true (:71-75)
+        use_gc = (in == 0) && (out == 0);
+    } else {
+        uint64_t gid[kSlots];
+        for (int s = 0; s < kSlots; s++)
+            gid[s] = ((voters >> s) & 1u) ? c.commit_group_id[static_cast<size_t>(s) * c.cap + g] : 0ull;
+        uint64_t i_idx, o_idx;
+        bool i_gc, o_gc;
+        majority_group_commit(v, gid, in, &i_idx, &i_gc);
+        majority_group_commit(v, gid, out, &o_idx, &o_gc);
+        mci = umin64(i_idx, o_idx);
+        use_gc = i_gc && o_gc;  // joint.rs:50
+    }
+}
+
+// Side-effect-free single-group query (thread 0 of one warp).
+__global__ void mci_kernel(Columns c, uint32_t g, uint64_t *out_mci, uint8_t *out_gc) {
+    if (threadIdx.x != 0) return;
+    uint64_t mci;
+    bool use_gc;
+    group_mci(c, g, c.meta[g], mci, use_gc);
+    *out_mci = mci;
+    *out_gc = use_gc ? 1 : 0;
+}
+
+// Block-level counter flush: per-thread tallies -> warp shuffle reduce -> shared
+// -> ONE global atomic per counter per block.  (v1 issued one atomic per warp per
+// counter; ~10^5 same-address atomics serialise in L2 and dominated both kernels.)
+template <int kN>
+__device__ __forceinline__ void block_flush_counts(const uint32_t (&local)[kN], const int (&which)[kN],
+                                                   unsigned long long *counters,
+                                                   uint32_t *extra_u32 /* nullable, gets local[1] */) {
+    __shared__ uint32_t s_cnt[kN];
+    if (threadIdx.x < kN) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kN; k++) {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, local[k]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt[k], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < kN && s_cnt[threadIdx.x]) {
+        atomicAdd(&counters[which[threadIdx.x]], static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+        if (extra_u32 && threadIdx.x == 1) atomicAdd(extra_u32, s_cnt[1]);
+    }
+}

@@ -414,7 +414,7 @@ int32_t raftgpu_step_begin_packed(raftgpu_arena *arena, const raftgpu_packed_rec
  *      unit & 3 == 3  ESC    [2,32) < 0x1fffffff: index into the side table; == 0x1fffffff: padding;
  *                            bit 31 set: the payload of the REJECT in front, [2,31) = hint - index (signed)
  * g_base[] holds one group id per block of RAFTGPU_COMPACT_BLOCK units.  Whatever does not fit
- * (a REJECT that asks for a snapshot, an index more than 16383 below the run's largest, a commit
+ * (a REJECT that asks for a snapshot, an index more than 8192 away from the run's first, a commit
  * delta above 254, a base above 2^48, a group more than 4095 above its block's g_base, flag bits
  * the format does not know) is an ESC unit pointing at the full 24-byte public record (and its
  * EXT) in the side table -- the format is lossless for ANY input, only less compact for hostile

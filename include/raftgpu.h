@@ -541,6 +541,17 @@ int32_t raftgpu_send_list_device(raftgpu_arena *arena, void *stream, uint32_t fi
  * `capacity` is too small. */
 int32_t raftgpu_step_send_list(raftgpu_arena *arena, raftgpu_send_entry *out, uint64_t capacity, uint64_t *out_n);
 
+/* ---- heartbeat commits (leader side) ------------------- */
+
+/* bcast_heartbeat (raft.rs:875-889) calls send_heartbeat for every peer but the leader itself, and
+ * send_heartbeat attaches commit = min(pr.matched, raft_log.committed) (raft.rs:826-848: the
+ * leader must not forward a follower's commit past what that follower has).  One dense pass
+ * over groups [first, first+n): d_out[slot * n + (g - first)] = that commit for every present
+ * peer (voter or learner) other than the group's own slot, RAFTGPU_NO_HEARTBEAT elsewhere. */
+#define RAFTGPU_NO_HEARTBEAT UINT64_MAX
+int32_t raftgpu_heartbeat_commits_device(raftgpu_arena *arena, void *stream, uint32_t first, uint32_t n,
+                                         uint64_t *d_out);
+
 /* ---- votes ----------------------------------------- */
 
 /* ProgressTracker::reset_votes / record_vote (tracker.rs:301-310). */

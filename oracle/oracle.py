@@ -147,6 +147,8 @@ def lib() -> C.CDLL:
         L.ro_arena_vote_result.restype = i32
         L.ro_arena_send_list.argtypes = [pv, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
         L.ro_arena_send_list.restype = C.c_uint64
+        L.ro_arena_heartbeat_commits.argtypes = [pv, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.ro_arena_heartbeat_commits.restype = None
         L.ro_bench_recompute.argtypes = [pv, i32, i32, p64]
         L.ro_bench_recompute.restype = C.c_double
         L.ro_bench_step.argtypes = [pv, C.c_void_p, sz, i32, p64]
@@ -302,6 +304,15 @@ def arena_send_list(c, adv_bitmap=None, first: int = 0, n: int | None = None):
     out = np.zeros(need, dtype=SEND_ENTRY_DTYPE)
     got = lib().ro_arena_send_list(C.byref(v), first, n, None if bm is None else bm.ctypes.data, out.ctypes.data, need)
     assert got == need
+    return out
+
+
+def arena_heartbeat_commits(c, first: int = 0, n: int | None = None) -> np.ndarray:
+    """send_heartbeat's commit = min(matched, committed) per peer (raft.rs:838-840); [SLOTS][n]."""
+    n = c.n_groups - first if n is None else n
+    out = np.zeros((SLOTS, n), dtype=np.uint64)
+    v = view(c)
+    lib().ro_arena_heartbeat_commits(C.byref(v), first, n, out.ctypes.data)
     return out
 
 

@@ -593,6 +593,23 @@ int ro_arena_vote_result(const ro_arena_view *a, const uint8_t *votes, uint32_t 
     return ro_joint_vote_result(in_ids, n_in, out_ids, n_out, &vm);
 }
 
+/* raft.rs:880-889 bcast_heartbeat_with_ctx + raft.rs:838-840 send_heartbeat */
+void ro_arena_heartbeat_commits(const ro_arena_view *a, uint32_t first, uint32_t n, uint64_t *out) {
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t g = first + i;
+        uint32_t meta = a->meta[g];
+        uint32_t peers = RO_META_IN(meta) | RO_META_OUT(meta) | RO_META_LEARN(meta);
+        for (uint32_t s = 0; s < RO_SLOTS; s++) {
+            uint64_t v = UINT64_MAX;
+            if ((peers & (1u << s)) && !((meta & RO_META_HAS_SELF) && RO_META_SELF(meta) == s)) { /* :887 */
+                uint64_t m = a->matched[cell(a, s, g)];
+                v = m < a->committed[g] ? m : a->committed[g];                                   /* :839 */
+            }
+            out[(size_t)s * n + i] = v;
+        }
+    }
+}
+
 /* progress.rs:210-216 */
 static int progress_is_paused(uint8_t flags) {
     switch (flags & RO_PF_STATE_MASK) {

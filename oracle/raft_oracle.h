@@ -251,6 +251,11 @@ typedef struct {
 uint64_t ro_arena_send_list(const ro_arena_view *a, uint32_t first, uint32_t n, const uint32_t *adv_bitmap,
                             ro_send_entry *out, uint64_t cap);
 
+/* bcast_heartbeat (raft.rs:875-889) -> send_heartbeat commit = min(pr.matched, committed)
+ * (raft.rs:838-840) for every present peer but the group's own slot; UINT64_MAX elsewhere.
+ * out[slot * n + (g - first)]. */
+void ro_arena_heartbeat_commits(const ro_arena_view *a, uint32_t first, uint32_t n, uint64_t *out);
+
 /* ---- CPU baseline timing (bench.py cpu_baseline / --impl reference) ----- */
 
 /* Runs `iters` recompute passes over the whole arena with n_threads pthreads

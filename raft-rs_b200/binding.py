@@ -253,6 +253,7 @@ def lib() -> C.CDLL:
             "raftgpu_record_vote": ([vp, u32, u32, i32], i32),
             "raftgpu_tally_votes": ([vp, vp, u32, u32, vp], i32),
             "raftgpu_send_list_device": ([vp, vp, u32, u32, vp, vp, u64, vp], i32),
+            "raftgpu_heartbeat_commits_device": ([vp, vp, u32, u32, vp], i32),
             "raftgpu_step_send_list": ([vp, vp, u64, C.POINTER(u64)], i32),
             "raftgpu_vote_result": ([vp, u32, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)], i32),
             "raftgpu_counters_read": ([vp, C.POINTER(Counters)], i32),
@@ -687,6 +688,9 @@ class Arena:
     def send_list_device(self, first, n, d_adv, d_out, capacity, d_count, stream=None):
         self._ck(self._L.raftgpu_send_list_device(self._h, stream, first, n, d_adv, d_out, capacity, d_count),
                  "send_list_device")
+
+    def heartbeat_commits_device(self, first, n, d_out, stream=None):
+        self._ck(self._L.raftgpu_heartbeat_commits_device(self._h, stream, first, n, d_out), "heartbeat_commits_device")
 
     def step_send_list(self, capacity: int) -> np.ndarray:
         """Post-commit send decisions of the last completed step (raftgpu_step_send_list)."""

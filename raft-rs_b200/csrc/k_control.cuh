@@ -74,6 +74,29 @@ send_list_kernel(Columns c, uint32_t first, uint32_t n, const uint32_t *__restri
 }
 
 // ---------------------------------------------------------------------------
+// heartbeat_commit_kernel: bcast_heartbeat (raft.rs:875-889) -> send_heartbeat's
+// commit = min(pr.matched, raft_log.committed) (raft.rs:838-840) for every peer but the group's own.
+// One thread per group, coalesced rows; algorithmic bytes per group: 4 (meta) + 8 (committed) +
+// 8K (matched) read, 8 x 8 written.
+__global__ void __launch_bounds__(256)
+heartbeat_commit_kernel(Columns c, uint32_t first, uint32_t n, uint64_t *__restrict__ out) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t g = first + i;
+        const uint32_t meta = c.meta[g];
+        uint32_t peers = RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
+        if (meta & RAFTGPU_META_HAS_SELF) peers &= ~(1u << RAFTGPU_META_SELF(meta));  // raft.rs:887 id != self_id
+        const uint64_t committed = c.committed[g];
+        uint64_t v[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; s++) v[s] = ((peers >> s) & 1u) ? c.matched[static_cast<size_t>(s) * c.cap + g] : 0ull;
+#pragma unroll
+        for (int s = 0; s < kSlots; s++)
+            out[static_cast<size_t>(s) * n + i] = ((peers >> s) & 1u) ? umin64(v[s], committed) : RAFTGPU_NO_HEARTBEAT;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // tally_kernel: ProgressTracker::tally_votes (tracker.rs:313-340) per group:
 // granted / rejected over voters, JointConfig::vote_result (joint.rs:56-67) over
 // MajorityConfig::vote_result (majority.rs:130-154).

@@ -1198,6 +1198,24 @@ def test_send_list_vs_oracle():
     arena.close()
 
 
+def test_heartbeat_commits_vs_oracle():
+    """SURVEY 8(f) rank 3, leader side: bcast_heartbeat's per-peer commit = min(matched, committed)
+    (raft.rs:838-840, 875-889) as one dense pass, on arbitrary configurations."""
+    rng = np.random.default_rng(21)
+    n = 5000
+    init = _random_state(n, rng)
+    arena = B.Arena(n)
+    arena.group_alloc_range(n)
+    arena.load_columns(init)
+    d_out = arena.device_alloc(8 * 8 * n)
+    for first, cnt in ((0, n), (37, 3001)):
+        arena.heartbeat_commits_device(first, cnt, d_out)
+        got = np.zeros((8, cnt), dtype=np.uint64)
+        arena.d2h(got, d_out)
+        assert np.array_equal(got, O.arena_heartbeat_commits(init, first, cnt))
+    arena.close()
+
+
 def test_vote_tally_batched_vs_oracle():
     n = 50_000
     rng = np.random.default_rng(7)

@@ -376,3 +376,20 @@ def test_send_list_arena_matches_progress_is_paused():
     # no bitmap = a plain bcast_append over every group of the range
     every = O.arena_send_list(c, None, 10, 100)
     assert set(every["group"].tolist()) <= set(range(10, 110)) and len(every) > len(got) // 4
+
+
+# ---- SURVEY 8(f) rank 3 (leader side): send_heartbeat attaches min(pr.matched, raft_log.committed)
+# (raft.rs:838-840); test_raft.rs:2713-2721 (test_bcast_beat) expects exactly that per follower ("want_commit =
+# min(committed, matched)") and nothing for the leader itself (raft.rs:887).
+def test_heartbeat_commits_arena():
+    c = O.new_columns(2, 2)
+    c.meta[0] = O.make_meta(0b0111, 0, 0b1000, 0)        # voters 0,1,2 + learner 3, self = slot 0
+    c.committed[0] = 1005
+    c.matched[:, 0] = [1011, 5, 1006, 1000, 9, 9, 9, 9]
+    c.meta[1] = O.make_meta(0b0011, 0b0110, 0, None)     # joint, no self slot known
+    c.committed[1] = 7
+    c.matched[:, 1] = [7, 9, 3, 0, 0, 0, 0, 0]
+    out = O.arena_heartbeat_commits(c)
+    none = (1 << 64) - 1
+    assert out[:, 0].tolist() == [none, 5, 1005, 1000, none, none, none, none]
+    assert out[:, 1].tolist() == [7, 7, 3, none, none, none, none, none]

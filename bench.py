@@ -3,14 +3,28 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # CPU baseline arm (the oracle port)
+    python bench.py --workload cfg4|cfg5 ...                 # the other BASELINE.json configs
 
 One "step" = one pass of the hot path over one batch: apply ONE round of synthetic
 AppendResponses (about 3.5 records per group) to a 1M-group x 5-peer arena and
-recompute the commit index of every group (Raft::maybe_commit).  `value` = groups recomputed
-per second over all GPUs with the records already resident in HBM; `e2e` = the same through
-raftgpu_enqueue_append_resp / raftgpu_step with HOST buffers (H2D + D2H inside the timed
-region).  Multi-GPU: groups shard across ranks, no data-path collective; NCCL only reduces
-the per-rank counters and times.
+recompute the commit index of every group (Raft::maybe_commit).
+
+  value            groups recomputed per second over all GPUs, records already resident in HBM
+                   (fused tile kernel, one launch per step; CUDA events on the launching stream)
+  e2e              the same step through the reference-facing C-ABI from what the reference's
+                   handle_append_response consumes: 24-byte records (raftgpu_append_resp) in pinned
+                   HOST memory -> raftgpu_step_begin_records (the library's staging threads pack
+                   them into the compact stream, H2D) -> kernels -> raftgpu_step_wait (D2H of the
+                   advanced bitmap + new commit indexes).  Everything after the records exist is
+                   inside the timed region.  This is the number to hold against the reference arm.
+  e2e_prepacked    the step for a caller that already holds its batch as the compact stream
+                   (raftgpu_step_begin_compact): the pack is NOT timed -- PCIe-bound floor
+  e2e_wire         the step from serialized eraftpb.Message bytes (raftgpu_step_begin_wire)
+  recompute_only   Raft::maybe_commit alone (BASELINE.md 3: rate x 74 B), back-to-back passes
+  scatter          the general two-kernel path (scatter apply + recompute) for unordered arrival
+
+Multi-GPU: groups shard across ranks, no data-path collective; NCCL only reduces the per-rank
+counters and times.
 """
 from __future__ import annotations
 
@@ -22,7 +36,6 @@ import statistics
 import subprocess
 import sys
 import time
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -32,12 +45,30 @@ if ROOT not in sys.path:
 
 METRIC = "commit_index_recomputes_per_s"
 UNIT = "recomputes/s"
-N_GROUPS = 1_000_000          # BASELINE configs[2]: the headline config, per GPU
 K_PEERS = 5
-SEED = 0x5EED0003
-B_ALG_RECOMPUTE = 8 * K_PEERS + 34   # 74 B per recompute at K = 5
 B_ALG_APPLY = 76                      # bytes per applied AppendResponse
 N_ARENAS = 4                          # rotated so consecutive steps never share L2 contents
+
+# BASELINE.json configs: groups per GPU, peer slots in the voter union, joint?, seed
+WORKLOADS = {
+    "cfg2": dict(groups=100_000, peers=5, joint=False, seed=0x5EED0002,
+                 text="cfg2: 100K raft groups x 5 peers per GPU"),
+    "cfg3": dict(groups=1_000_000, peers=5, joint=False, seed=0x5EED0003,
+                 text="cfg3: 1M raft groups x 5 peers per GPU"),
+    "cfg4": dict(groups=1_000_000, peers=7, joint=True, seed=0x5EED0004,
+                 text="cfg4: 1M raft groups x 7 peer slots per GPU under joint consensus (two 5-voter majorities)"),
+    "cfg5": dict(groups=1_250_000, peers=5, joint=False, seed=0x5EED0005,
+                 text="cfg5: 10M raft groups x 5 peers sharded over 8 GPUs = 1.25M groups per GPU"),
+}
+
+
+def config_of(args) -> dict:
+    """The workload description both arms print (identical for --impl reference)."""
+    w = WORKLOADS[args.workload]
+    return {"workload": w["text"] + ", one synthetic AppendResponse round per step (apply + recompute)",
+            "groups_per_gpu": args.groups or w["groups"], "peers": w["peers"], "seed": hex(w["seed"]),
+            "l2": f"inputs larger than L2: {N_ARENAS} arenas rotated, fresh records every step",
+            "parallelism": "groups sharded over the GPUs, no data-path collective"}
 
 
 def peaks():
@@ -122,53 +153,48 @@ def cpu_leg(n_groups, seed, rounds_wanted, threads, budget_s=20.0, joint=False):
     from oracle import oracle as O
     synth = B.Synth(n_groups, seed, k_peers=K_PEERS, joint=joint)
     cols = O.copy_columns(synth.initial)
-    total, done, times = 0.0, 0, []
+    total, done = 0.0, 0
     for _ in range(rounds_wanted):
         recs = synth.next_round()
         secs, _ = O.bench_step(cols, recs, threads, fast=True)
-        times.append(secs)
         total += secs
         done += 1
         if total > budget_s:
             break
-    return n_groups * done / total, done, times
+    return n_groups * done / total, done
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  raft-rs is Rust and
     this image has no rustc/cargo, so the arm runs the pinned C port (oracle/) with every host
-    thread, on the same config / metric as the GPU arm."""
+    thread, on the same config / metric as the GPU arm: it consumes the same 24-byte records the
+    GPU arm's `e2e` starts from."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     t0 = time.perf_counter()
-    # warmup rounds are part of the same stream; time exactly `steps` rounds after them
     B = importlib.import_module("raft-rs_b200").binding
     from oracle import oracle as O
-    joint = args.workload == "cfg4"
-    seed0 = 0x5EED0004 if joint else SEED
-    synth = B.Synth(N_GROUPS, seed0, k_peers=K_PEERS, joint=joint)
+    w = WORKLOADS[args.workload]
+    n = args.groups or w["groups"]
+    synth = B.Synth(n, w["seed"], k_peers=K_PEERS, joint=w["joint"])
     cols = O.copy_columns(synth.initial)
-    for _ in range(args.warmup):
+    for _ in range(args.warmup):   # warmup rounds are part of the same stream
         O.bench_step(cols, synth.next_round(), threads, fast=True)
     total = 0.0
     for _ in range(args.steps):
         secs, _ = O.bench_step(cols, synth.next_round(), threads, fast=True)
         total += secs
-    value = N_GROUPS * args.steps / total
+    value = n * args.steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic",
-        "config": {"workload": ("cfg4: 1M raft groups x 7 peer slots under joint consensus, one synthetic "
-                                "AppendResponse round per step (apply + recompute)") if joint else
-                               ("cfg3: 1M raft groups x 5 peers, one synthetic AppendResponse round "
-                                "per step (apply + recompute)"), "groups": N_GROUPS,
-                   "peers": 7 if joint else K_PEERS, "seed": hex(seed0)},
+        "data": "synthetic", "config": config_of(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} rounds of the {args.workload} stream, {threads} pthreads, "
-                                   "oracle/raft_oracle.c tuned path (ro_bench_step_fast, == the literal port)"},
+                         "sample": f"{args.steps} rounds of the {args.workload} stream ({n} groups), {threads} pthreads, "
+                                   "oracle/raft_oracle.c tuned path (ro_bench_step_fast, == the literal port), "
+                                   "input = 24-byte records in host memory"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
@@ -181,22 +207,16 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--groups", type=int, default=N_GROUPS, help=argparse.SUPPRESS)
-    ap.add_argument("--compact-device", action="store_true",
-                    help="device-resident leg on the compact stream + its fused kernel (raftgpu_step_compact_device) "
-                         "instead of the 16-byte packed records + per-record fused kernel (measured: 86 vs 75 us)")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
-                    help="cfg3 (default, the headline): 1M groups x 5 peers; cfg4: 1M groups x 7 peer slots under "
-                         "joint consensus (incoming {0..4}, outgoing {0,1,2,5,6}), 90 B per recompute")
-    ap.add_argument("--e2e-threads", type=int, default=0)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config: cfg3 (default, the headline) 1M groups x 5 peers per GPU; cfg4 1M groups "
+                         "x 7 peer slots under joint consensus (90 B per recompute); cfg5 10M groups over 8 GPUs "
+                         "(1.25M per GPU); cfg2 100K groups")
+    ap.add_argument("--groups", type=int, default=0, help="override the groups per GPU of the workload")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="library staging threads (default: from the GPU-local cores)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
     ap.add_argument("--e2e-chunk", type=int, default=8, help="pipelined e2e steps per timed chunk")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scatter", action="store_true",
-                    help="device-resident leg uses the general two-kernel path (scatter apply + recompute) "
-                         "instead of the fused tile kernel for group-ordered batches")
-    ap.add_argument("--public-records", action="store_true",
-                    help="device-resident leg reads 24-byte public records instead of the packed 16-byte form")
+    ap.add_argument("--no-sublegs", action="store_true", help="skip recompute_only / scatter / secondary e2e legs")
     ap.add_argument("--profile", action="store_true",
                     help="device-resident loop only (for ncu): no clock warm loop, no e2e, no CPU leg")
     args = ap.parse_args()
@@ -224,24 +244,25 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n = args.groups
+    wl = WORKLOADS[args.workload]
+    n = args.groups or wl["groups"]
     K, W = args.steps, args.warmup
-    joint = args.workload == "cfg4"
-    k_union = 7 if joint else K_PEERS
-    seed0 = 0x5EED0004 if joint else SEED
-    b_alg_recompute = 8 * k_union + 34
+    joint = wl["joint"]
+    k_union = wl["peers"]
+    seed0 = wl["seed"]
+    b_alg_recompute = 8 * k_union + 34    # 74 B per recompute at K = 5, 90 B at 7
     peak_gbs, peak_src = peaks()
+    sublegs = not (args.no_sublegs or args.profile)
+    rec_slots = (7 if joint else 5) * n + 64
 
-    # ---- synthetic inputs: N_ARENAS independent 1M-group stores, K+W rounds in total ----------
-    # Host memory is kept small and reused (one record buffer per generator): fresh host pages
-    # are slow on these VMs; HBM holds all K+W rounds.
-    per_arena = [(W + K + N_ARENAS - 1 - a) // N_ARENAS for a in range(N_ARENAS)]
+    # ---- synthetic inputs: N_ARENAS independent stores; W+K rounds for the fused leg and, after
+    # them in the same streams, W+K rounds for the scatter leg.  HBM holds all rounds; host memory
+    # is one reused record buffer per generator.
+    n_legs = 2 if sublegs else 1
+    total_rounds = n_legs * (W + K)
+    per_arena = [(total_rounds + N_ARENAS - 1 - a) // N_ARENAS for a in range(N_ARENAS)]
     arenas, round_len, d_recs, d_offs = [], [], [], []
-    fused = not (args.scatter or args.public_records)
-    compact = fused and args.compact_device    # compact stream + its fused kernel for the device-resident leg
     pack_buf = np.empty((7 * n + 64, 2), dtype=np.uint64)
-    blob_buf = np.empty(B.compact_bound(7 * n + 64), dtype=np.uint8) if compact else None
-    d_bad = None
     for a in range(N_ARENAS):
         seed = seed0 + 0x100 * a + 0x10000 * rank
         s = B.Synth(n, seed, k_peers=K_PEERS, joint=joint)
@@ -251,66 +272,55 @@ def main():
         ptrs, lens, offs = [], [], []
         for _ in range(per_arena[a]):
             recs = s.next_round()
-            if compact:                   # the compact stream (4-byte units) + its tile index, both in HBM
-                nb, _ = B.pack_compact(recs, blob_buf)
-                hdr = blob_buf[:64].copy()
-                assert hdr.view(B.COMPACT_HDR_DTYPE)[0]["flags"] & B.COMPACT_TILEABLE
-                p = ar.device_alloc(nb)
-                ar.h2d(p, blob_buf[:nb])
-                po = ar.device_alloc(4 * (3 * (ar.cap // B.tile_groups() + 2) + 2))
-                if d_bad is None:
-                    d_bad = ar.device_alloc(4)
-                    ar.h2d(d_bad, np.zeros(1, dtype=np.uint32))
-                ar.compact_tile_index_device(p, hdr, po, d_bad)
-                offs.append((po, hdr))
-                lens.append((nb, len(recs)))
-            elif args.public_records:     # the 24-byte public record layout in HBM
-                p = ar.device_alloc(recs.nbytes)
-                ar.h2d(p, recs)
-                lens.append((len(recs), len(recs)))
-            else:                         # the packed 16-byte wire form (what the staging path ships)
-                k = ar.pack_records(recs, pack_buf)
-                p = ar.device_alloc(16 * k)
-                ar.h2d(p, pack_buf[:k])
-                lens.append((k, len(recs)))
-                if fused:                 # the batch is in group order: its 256-group tile index
-                    off = B.tile_index(pack_buf, k, n)
-                    po = ar.device_alloc(off.nbytes)
-                    ar.h2d(po, off)
-                    offs.append(po)
+            k = ar.pack_records(recs, pack_buf)      # the packed 16-byte form, in group order
+            p = ar.device_alloc(16 * k)
+            ar.h2d(p, pack_buf[:k])
+            lens.append((k, len(recs)))
+            off = B.tile_index(pack_buf, k, n)       # first record of every 256-group tile
+            po = ar.device_alloc(off.nbytes)
+            ar.h2d(po, off)
+            offs.append(po)
             ptrs.append(p)
         arenas.append(ar)
         round_len.append(lens)
         d_recs.append(ptrs)
         d_offs.append(offs)
         del s
-    schedule = [(i % N_ARENAS, i // N_ARENAS) for i in range(W + K)]  # (arena, round) per step
+    schedule = [(i % N_ARENAS, i // N_ARENAS) for i in range(total_rounds)]  # (arena, round) per step
 
     stream = torch.cuda.Stream()
     sh = stream.cuda_stream
 
-    def run_step(i, ev=None):
+    def step_fused(i):
         a, r = schedule[i]
+        arenas[a].step_sorted_device(d_recs[a][r], round_len[a][r][0], d_offs[a][r], stream=sh)
+
+    def step_scatter(i, ev=None):
+        a, r = schedule[i]
+        arenas[a].apply_device_packed(d_recs[a][r], round_len[a][r][0], stream=sh)
         if ev:
-            ev[0].record(stream)
-        if fused:   # ONE kernel: apply + recompute on shared-memory tiles (group-ordered batch)
-            if compact:
-                arenas[a].step_compact_device(d_recs[a][r], d_offs[a][r][1], d_offs[a][r][0], stream=sh)
-            else:
-                arenas[a].step_sorted_device(d_recs[a][r], round_len[a][r][0], d_offs[a][r], stream=sh)
-            if ev:
-                ev[1].record(stream)
-                ev[2].record(stream)
-            return
-        if args.public_records:
-            arenas[a].apply_device(d_recs[a][r], round_len[a][r][0], stream=sh)
-        else:
-            arenas[a].apply_device_packed(d_recs[a][r], round_len[a][r][0], stream=sh)
-        if ev:
-            ev[1].record(stream)
+            ev.record(stream)
         arenas[a].recompute(0, n, stream=sh)
-        if ev:
-            ev[2].record(stream)
+
+    def timed(fn, first, count):
+        """count back-to-back steps under CUDA events on the launching stream; (ms total, per-step event pairs)."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for i in range(count):
+            evs[i][0].record(stream)
+            fn(first + i)
+            evs[i][1].record(stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), sum(a_.elapsed_time(b_) for a_, b_ in evs)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -322,33 +332,37 @@ def main():
                 a.recompute(0, n, stream=sh)
             stream.synchronize()
         for i in range(W):
-            run_step(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(K):
-            run_step(W + i, evs[i])
-        e1.record(stream)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
-    ms_apply = sum(e[0].elapsed_time(e[1]) for e in evs)
-    ms_recompute = sum(e[1].elapsed_time(e[2]) for e in evs)
-    n_records = sum(round_len[a][r][1] for a, r in schedule[W:])
+            step_fused(i)
+        ms_total, ms_kernel = timed(step_fused, W, K)
+        n_records = sum(round_len[a][r][1] for a, r in schedule[W:W + K])
+        sc = ro = None
+        if sublegs:
+            # scatter: the same streams continue through the general path (no group order needed)
+            base = W + K
+            for i in range(W):
+                step_scatter(base + i)
+            ev_mid = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(K):
+                evs[i][0].record(stream)
+                step_scatter(base + W + i, ev_mid[i])
+                evs[i][1].record(stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            sc_records = sum(round_len[a][r][1] for a, r in schedule[base + W:base + W + K])
+            sc = {"ms_total": e0.elapsed_time(e1),
+                  "ms_apply": sum(evs[i][0].elapsed_time(ev_mid[i]) for i in range(K)),
+                  "ms_recompute": sum(ev_mid[i].elapsed_time(evs[i][1]) for i in range(K)), "records": sc_records}
+            # recompute only: Raft::maybe_commit over every group, arenas rotated (4 x 74 MB > L2 hit window)
+            for i in range(W):
+                arenas[i % N_ARENAS].recompute(0, n, stream=sh)
+            ro_total, _ = timed(lambda i: arenas[i % N_ARENAS].recompute(0, n, stream=sh), 0, K)
+            ro = {"ms_total": ro_total}
 
-    # ---- e2e: host buffers -> enqueue -> step (H2D, kernels, D2H) on a fresh arena ------------
-    # The caller's records sit in ordinary host memory; raftgpu_enqueue_append_resp stages them
-    # into pinned rings (T caller threads, T rings), raftgpu_step_begin DMAs + launches,
-    # raftgpu_step_wait returns once the results are back in host memory.  Steps are timed in
-    # chunks of `chunk` pipelined steps (the next batch is staged while one is in flight); the
-    # records of the following chunk are regenerated between chunks, untimed, into the same few
-    # host buffers.
+    # ---- e2e: host buffers -> C-ABI -> results in host memory, on a fresh arena ------------------
     # staging threads per rank: one per physical GPU-local core, shared with the other ranks whose
     # GPU hangs off the same socket (two sockets per host)
     ranks_per_node = max(1, (world + 1) // 2)
@@ -360,212 +374,161 @@ def main():
     ea = B.Arena(n, device=local_rank, n_rings=e2e_threads)
     assert ea.group_alloc_range(n) == 0
     ea.load_columns(es.initial)
-    bufs = [np.empty((7 if joint else 5) * n + 64, dtype=B.APPEND_RESP_DTYPE) for _ in range(chunk)]
+    flags = B.STEP_READ_COMMITTED
+    # the caller's 24-byte records live in pinned, GPU-local host memory (raftgpu_host_alloc)
+    rec_bytes = rec_slots * B.APPEND_RESP_DTYPE.itemsize
+    bufs = [ea.host_alloc_bytes(rec_bytes).view(B.APPEND_RESP_DTYPE) for _ in range(chunk)] if e2e_steps else []
 
-    def split(recs):
-        return recs
-
-    def staged_leg(records_api):
-        """Timed: the caller's 24-byte records (ordinary host memory) -> library staging threads ->
-        H2D -> kernels -> D2H.  records_api: raftgpu_step_begin_records (compact stream, one call);
-        else the general path raftgpu_enqueue_bulk(SORTED) + raftgpu_step_begin (16-byte records)."""
-        def submit(recs):
-            if records_api:
-                ea.step_begin_records(recs, flags)
-                return time.perf_counter()
-            ea.enqueue_bulk(recs, sorted_by_group=True)
-            t_mid = time.perf_counter()
-            ea.step_begin(flags)
-            return t_mid
-
-        secs, timed, caller_b, first_chunk = 0.0, 0, 0, True
-        phase = [0.0, 0.0, 0.0]   # host seconds in staging / step_begin / step_wait
-        dma = [0, 0]              # bytes actually DMAed (h2d, d2h), as reported by the library
-        while timed < e2e_steps:
-            m = min(chunk, e2e_steps - timed)
-            parts = [es.next_round(bufs[j]) for j in range(m)]      # untimed generation
-            if first_chunk:                                           # untimed warm-up steps
+    def pipelined_leg(prepare, begin):
+        """`chunk` steps at a time: prepare(j) builds batch j (UNTIMED: the generation of the inputs);
+        then, timed: begin(batch 0); for each j: begin(batch j+1) while step j is in flight; wait(j).
+        Wall clock around the chunk, barrier + synchronize on both sides."""
+        secs, done, dma, first = 0.0, 0, [0, 0], True
+        phase = [0.0, 0.0]    # host seconds inside begin / inside wait
+        while done < e2e_steps:
+            m = min(chunk, e2e_steps - done)
+            batches = [prepare(j) for j in range(m)]
+            if first:                       # untimed warm-up steps (pool threads, first-touch, clocks)
                 for j in range(m):
-                    submit(parts[j])
+                    begin(batches[j])
                     ea.step_wait()
-                first_chunk = False
+                first = False
                 continue
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            t1 = submit(parts[0])
-            phase[0] += t1 - t0
-            phase[1] += time.perf_counter() - t1
+            begin(batches[0])
+            phase[0] += time.perf_counter() - t0
             for j in range(m):
                 ta = time.perf_counter()
-                if j + 1 < m:             # stage AND submit the next batch while this one is in flight:
-                    tb = submit(parts[j + 1])   # its H2D overlaps this step's kernels + D2H
-                else:
-                    tb = ta
-                tc = time.perf_counter()
+                if j + 1 < m:
+                    begin(batches[j + 1])
+                tb = time.perf_counter()
                 sr = ea.step_wait()
-                dma[0] += sr.h2d_bytes
-                dma[1] += sr.d2h_bytes
-                td = time.perf_counter()
+                tc = time.perf_counter()
                 phase[0] += tb - ta
                 phase[1] += tc - tb
-                phase[2] += td - tc
+                dma[0] += sr.h2d_bytes
+                dma[1] += sr.d2h_bytes
             secs += time.perf_counter() - t0
-            timed += m
-            caller_b += sum(pj.nbytes for pj in parts)
-        return {"seconds": secs, "steps": timed, "h2d": dma[0] / max(1, timed), "d2h": dma[1] / max(1, timed),
-                "caller_bytes": caller_b / max(1, timed), "phase": [1e3 * x / max(1, timed) for x in phase]}
+            done += m
+        d = max(1, done)
+        return {"seconds": secs, "steps": done, "h2d": dma[0] / d, "d2h": dma[1] / d,
+                "host_ms": {"begin": 1e3 * phase[0] / d, "wait": 1e3 * phase[1] / d}}
 
-    flags = B.STEP_READ_COMMITTED
-    sr_ = staged_leg(False) if e2e_steps else {"seconds": 0.0, "steps": 0}   # e2e_staged: the general staging path
-    sg = staged_leg(True) if e2e_steps else {"seconds": 0.0, "steps": 0}     # e2e_records_api: one-call compact staging
-    e2e_s, e2e_timed = sr_["seconds"], sr_["steps"]
-    # ---- e2e, zero-copy: the caller builds its batch (packed 16-byte records) directly in the
-    # arena's NUMA-local pinned memory (untimed, like the generation above); timed is
-    # raftgpu_step_begin_packed (H2D straight from that buffer, the GPU verifies the one-wave
-    # promise) + raftgpu_step_wait, two steps in flight.
-    def zero_copy_leg(compact):
-        if compact:
-            cap_b = B.compact_bound((7 if joint else 5) * n + 64)
-            pk = [ea.host_alloc_bytes(cap_b) for _ in range(chunk)]
-        else:
-            pk = [ea.host_alloc_packed((7 if joint else 5) * n + 64) for _ in range(chunk)]
-        zc_s, zc_timed, zc_dma = 0.0, 0, [0, 0]
-        while zc_timed < e2e_steps:
-            m = min(chunk, e2e_steps - zc_timed)
-            if compact:   # untimed, like the generation of the records themselves
-                ks = [B.pack_compact(es.next_round(bufs[j]), pk[j])[0] for j in range(m)]
-                begin = ea.step_begin_compact
-            else:
-                ks = [ea.pack_records(es.next_round(bufs[j]), pk[j]) for j in range(m)]
-                begin = ea.step_begin_packed
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            begin(pk[0], ks[0], flags)
-            for j in range(m):
-                if j + 1 < m:
-                    begin(pk[j + 1], ks[j + 1], flags)
-                sr = ea.step_wait()
-                zc_dma[0] += sr.h2d_bytes
-                zc_dma[1] += sr.d2h_bytes
-            zc_s += time.perf_counter() - t0
-            zc_timed += m
+    legs = {}
+    if e2e_steps:
+        # e2e: 24-byte records (pinned host memory) -> raftgpu_step_begin_records -> raftgpu_step_wait
+        legs["e2e"] = pipelined_leg(lambda j: es.next_round(bufs[j]), lambda recs: ea.step_begin_records(recs, flags))
+    if e2e_steps and sublegs:
+        # e2e_prepacked: the caller already holds the compact stream (pack untimed)
+        cap_b = B.compact_bound(rec_slots)
+        pk = [ea.host_alloc_bytes(cap_b) for _ in range(chunk)]
+        legs["e2e_prepacked"] = pipelined_leg(
+            lambda j: (pk[j], B.pack_compact(es.next_round(bufs[j]), pk[j])[0]),
+            lambda b: ea.step_begin_compact(b[0], b[1], flags))
         for b_ in pk:
             ea.host_free(b_)
-        return {"seconds": zc_s, "steps": zc_timed, "h2d": zc_dma[0] / zc_timed, "d2h": zc_dma[1] / zc_timed}
-
-    zc, zp = {"value": None}, {"value": None}
-    if e2e_steps:
-        zp = zero_copy_leg(False)
-        zc = zero_copy_leg(True)
+        if hasattr(ea, "step_begin_wire"):
+            # e2e_wire: serialized eraftpb.Message frames (pinned) -> device-side varint decode -> the same step
+            W_ = importlib.import_module("raft-rs_b200").wire
+            wb = [W_.WireBuffers(ea, rec_slots) for _ in range(chunk)]
+            legs["e2e_wire"] = pipelined_leg(
+                lambda j: wb[j].encode(es.next_round(bufs[j])),
+                lambda w_: ea.step_begin_wire(w_, flags))
+            for w_ in wb:
+                w_.free()
     clocks = sampler.stop()
 
     # ---- aggregate over ranks (NCCL: counters and times only) -----------------------------------
-    if os.environ.get("RAFTGPU_TILE_DEBUG") and rank == 0:
-        d = sum(a.debug_read().astype(np.float64) for a in arenas)
-        if d[4]:
-            print("[tile debug] cycles per tile: wait_loads %.0f  records %.0f  recompute %.0f  stores %.0f  (tiles %d)"
-                  % (d[0] / d[4], d[1] / d[4], d[2] / d[4], d[3] / d[4], d[4]), file=sys.stderr)
     cnt = [a.counters() for a in arenas]
     S = importlib.import_module("raft-rs_b200.shard")
+    times = {"ms_total": ms_total}
+    for name, lg in legs.items():
+        times[name] = lg["seconds"]
+    if sc:
+        times["sc_ms"] = sc["ms_total"]
+        times["ro_ms"] = ro["ms_total"]
     sums, maxes = S.aggregate(
         dist if world > 1 else None, torch,
-        {"groups_device": n * K, "groups_e2e": n * e2e_timed,
-         "recomputes": sum(c["recomputes"] for c in cnt), "advanced": sum(c["advanced"] for c in cnt),
+        {"recomputes": sum(c["recomputes"] for c in cnt), "advanced": sum(c["advanced"] for c in cnt),
          "records": sum(c["records"] for c in cnt)},
-        {"ms_total": ms_total, "e2e_s": e2e_s, "sg_s": sg.get("seconds", 0.0), "zc_s": zc.get("seconds", 0.0),
-         "zp_s": zp.get("seconds", 0.0)},
-        device="cuda")
-    ms_max, e2e_max = maxes["ms_total"], maxes["e2e_s"]
-    value = sums["groups_device"] / (ms_max * 1e-3)
-    e2e_value = sums["groups_e2e"] / e2e_max if e2e_max > 0 else None
+        times, device="cuda")
+    value = world * n * K / (maxes["ms_total"] * 1e-3)
 
     if rank == 0:
-        kernels = []
-        if fused:
-            klist = (("step_tile_compact_kernel" if compact else "step_tile_kernel", ms_apply, n_records * B_ALG_APPLY + n * K * b_alg_recompute),)
-        else:
-            klist = (("apply_kernel", ms_apply, n_records * B_ALG_APPLY),
-                     ("recompute_kernel", ms_recompute, n * K * b_alg_recompute))
-        for name, ms, alg_bytes in klist:
-            gbs = alg_bytes / (ms * 1e-3) / 1e9
-            kernels.append({"kernel": name, "avg_us": 1e3 * ms / K, "share": ms / ms_total,
-                            "alg_bytes_per_launch": alg_bytes / K, "achieved": gbs,
-                            "frac": gbs / peak_gbs})
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 traffic = json.load(f)
         except Exception:
             traffic = {}
-        for k in kernels:
-            k["traffic"] = traffic.get(k["kernel"])   # ncu dram bytes per launch (profiles/)
-        dom = max(kernels, key=lambda k: k["avg_us"])
+        alg_bytes = n_records * B_ALG_APPLY + n * K * b_alg_recompute
+        gbs = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        tkey = "step_tile_kernel" + ("" if args.workload in ("cfg3", "cfg5", "cfg2") else "_" + args.workload)
+        tr = traffic.get(tkey)
+        dom = {"kernel": "step_tile_kernel", "avg_us": 1e3 * ms_kernel / K, "share": ms_kernel / ms_total,
+               "alg_bytes_per_launch": alg_bytes / K, "achieved": gbs, "frac": gbs / peak_gbs, "traffic": tr}
+        if tr:   # the honest bandwidth fraction: DRAM bytes the kernel really moves (ncu) / its duration
+            dom["dram_gbs"] = tr / (dom["avg_us"] * 1e-6) / 1e9
+            dom["dram_frac"] = dom["dram_gbs"] / peak_gbs
+        cfg = config_of(args)    # identical to the reference arm's
+        details = {"records_per_step": n_records / K, "record_format": "16 B packed (raftgpu_pack_records), group order",
+                   "device_path": "fused tile kernel (raftgpu_step_sorted_device, group-ordered batch + tile index)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {
-                "workload": ("cfg4: 1M raft groups x 7 peer slots per GPU under joint consensus (two 5-voter "
-                             "majorities), one synthetic AppendResponse round per step (apply + recompute)")
-                if joint else ("cfg3: 1M raft groups x 5 peers per GPU, one synthetic AppendResponse "
-                               "round per step (apply + recompute)"),
-                "groups_per_gpu": n, "peers": k_union, "seed": hex(seed0),
-                "records_per_step": n_records / K,
-                "record_format": "24 B public" if args.public_records else
-                                 ("compact stream, 4 B units (raftgpu_pack_compact)" if compact else
-                                  "16 B packed (raftgpu_pack_records)"),
-                "device_path": "fused tile kernel (raftgpu_step_sorted_device, group-ordered batch + tile index)"
-                               if fused else "scatter apply + recompute (raftgpu_apply_device[_packed] + raftgpu_recompute)",
-                "l2": f"inputs larger than L2: {N_ARENAS} arenas rotated, fresh records every step",
-                "parallelism": f"groups sharded over {world} GPU(s), no data-path collective",
-            },
+            "ms_per_step": maxes["ms_total"] / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": cfg, "details": details,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"],
                          "peak": peak_gbs, "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],
-                         "peak_source": peak_src},
-            "kernels": kernels,
-            "e2e_staged": None if not e2e_timed else {
-                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sr_["h2d"], "d2h_bytes_per_step": sr_["d2h"],
-                "steps": e2e_timed, "ms_per_step": 1e3 * e2e_max / max(1, e2e_timed),
-                "caller_record_bytes_per_step": sr_["caller_bytes"],
-                "host_threads": e2e_threads, "pipelined_chunk": chunk, "host_cpus_bound": len(local_cpus) or None,
-                "host_ms_per_step": {"staging": sr_["phase"][0], "step_begin": sr_["phase"][1], "step_wait": sr_["phase"][2]},
-                "api": "raftgpu_enqueue_bulk(SORTED) + raftgpu_step_begin/_wait (READ_COMMITTED): 24-byte records in "
-                       "ordinary host memory, copied + packed to 16-byte records by the library's staging threads "
-                       "inside the timed region"},
-            "e2e_records_api": None if not sg.get("steps") else {
-                "value": world * n * sg["steps"] / maxes["sg_s"], "unit": UNIT,
-                "ms_per_step": 1e3 * maxes["sg_s"] / sg["steps"], "steps": sg["steps"],
-                "h2d_bytes_per_step": sg["h2d"], "d2h_bytes_per_step": sg["d2h"],
-                "host_ms_per_step": {"staging": sg["phase"][0], "step_begin": sg["phase"][1], "step_wait": sg["phase"][2]},
-                "api": "raftgpu_step_begin_records + raftgpu_step_wait: one call, the staging threads pack slices of "
-                       "the batch into the compact stream (host-bound: ~12 ns per record per thread)"},
-            "e2e": None if not zc.get("steps") else {
-                "value": world * n * zc["steps"] / maxes["zc_s"], "unit": UNIT,
-                "ms_per_step": 1e3 * maxes["zc_s"] / zc["steps"], "steps": zc["steps"],
-                "h2d_bytes_per_step": zc["h2d"], "d2h_bytes_per_step": zc["d2h"],
-                "api": "raftgpu_step_begin_compact + raftgpu_step_wait: the step's records sit in pinned host "
-                       "memory (raftgpu_host_alloc) as the compact stream the caller built them in "
-                       "(raftgpu_pack_compact, untimed like the generation of the records); timed: H2D of the "
-                       "stream, apply (device-side decode + one-wave check) + recompute kernels, D2H of the "
-                       "advanced bitmap and new commit indexes; two steps in flight.  e2e_packed16 is the same "
-                       "with the 16-byte packed form (raftgpu_step_begin_packed); e2e_staged goes through "
-                       "raftgpu_enqueue_bulk, i.e. with the library copying + packing 24-byte records from "
-                       "pageable memory first"},
-            "e2e_packed16": None if not zp.get("steps") else {
-                "value": world * n * zp["steps"] / maxes["zp_s"], "unit": UNIT,
-                "ms_per_step": 1e3 * maxes["zp_s"] / zp["steps"], "steps": zp["steps"],
-                "h2d_bytes_per_step": zp["h2d"], "d2h_bytes_per_step": zp["d2h"]},
-            "gpu_launches": (1 if fused else 2) * K,
+                         "dram_frac": dom.get("dram_frac"), "peak_source": peak_src,
+                         "note": "achieved = SURVEY 8(d) algorithmic bytes (76 B per record + 8K+34 B per group) / the kernel's "
+                                 "average duration (CUDA events); dram_frac = ncu DRAM bytes per launch (profiles/traffic.json) / "
+                                 "the same duration: the fused kernel reads `matched` once, so it moves fewer bytes than the "
+                                 "two-pass algorithmic count"},
+            "kernels": [dom],
+            "gpu_launches": K,
             "clocks": clocks,
             "counters": {"recomputes": sums["recomputes"], "advanced": sums["advanced"], "records": sums["records"]},
         }
+        if sc:
+            line["scatter"] = {
+                "value": world * n * K / (maxes["sc_ms"] * 1e-3), "unit": UNIT, "ms_per_step": maxes["sc_ms"] / K,
+                "apply_us": 1e3 * sc["ms_apply"] / K, "recompute_us": 1e3 * sc["ms_recompute"] / K,
+                "apply_frac": sc["records"] * B_ALG_APPLY / (sc["ms_apply"] * 1e-3) / 1e9 / peak_gbs,
+                "api": "raftgpu_apply_device_packed + raftgpu_recompute: the general path, any arrival order (one record per "
+                       "cell per call), no tile index"}
+            ro_gbs = world * n * K * b_alg_recompute / (maxes["ro_ms"] * 1e-3) / 1e9
+            line["recompute_only"] = {
+                "value": world * n * K / (maxes["ro_ms"] * 1e-3), "unit": UNIT, "us_per_pass": 1e3 * maxes["ro_ms"] / K,
+                "bytes_per_recompute": b_alg_recompute, "achieved_gbs_per_gpu": ro_gbs / world,
+                "frac": ro_gbs / world / peak_gbs, "traffic": traffic.get("recompute_kernel"),
+                "api": "raftgpu_recompute: Raft::maybe_commit for every group, nothing applied (BASELINE.md 3: rate x (8K+34) B)"}
+        apis = {
+            "e2e": "raftgpu_step_begin_records + raftgpu_step_wait (READ_COMMITTED): the step's 24-byte records "
+                   "(raftgpu_append_resp, what handle_append_response consumes) sit in pinned host memory "
+                   "(raftgpu_host_alloc); timed: the library's staging threads pack them into the compact stream, H2D "
+                   "slice by slice, tile index + fused apply/recompute kernel, D2H of the advanced bitmap and the new "
+                   "commit indexes; two steps in flight",
+            "e2e_prepacked": "raftgpu_step_begin_compact + raftgpu_step_wait: the caller already holds the batch as the "
+                             "compact stream (raftgpu_pack_compact NOT timed): the PCIe-bound floor of the step",
+            "e2e_wire": "raftgpu_step_begin_wire + raftgpu_step_wait: serialized eraftpb.Message frames in pinned host "
+                        "memory, varint decode on the GPU, then the same step",
+        }
+        for name, lg in legs.items():
+            if not lg["steps"]:
+                continue
+            line[name] = {"value": world * n * lg["steps"] / maxes[name], "unit": UNIT,
+                          "ms_per_step": 1e3 * maxes[name] / lg["steps"], "steps": lg["steps"],
+                          "h2d_bytes_per_step": lg["h2d"], "d2h_bytes_per_step": lg["d2h"],
+                          "host_ms_per_step": lg["host_ms"], "pipelined_chunk": chunk, "api": apis[name]}
+        if "e2e" in line:
+            line["e2e"].update({"caller_record_bytes_per_step": 24.0 * n_records / K, "host_threads": e2e_threads,
+                                "host_cpus_bound": len(local_cpus) or None})
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core
             threads = len(all_cpus)
-            v, done, _ = cpu_leg(n, seed0, 64, threads, budget_s=15.0, joint=joint)
+            v, done = cpu_leg(n, seed0, 64, threads, budget_s=15.0, joint=joint)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": f"{done} rounds of the same {args.workload} stream (apply + recompute), {threads} "

@@ -16,7 +16,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libraftgpu.so")
+SYNTH_LIB_PATH = os.path.join(_HERE, "libraftgpu_synth.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "raftgpu.h")
+SYNTH_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "raftgpu_synth.h")
 
 SLOTS = 8
 U64_MAX = (1 << 64) - 1
@@ -263,9 +265,6 @@ def lib() -> C.CDLL:
             "raftgpu_device_free": ([vp, vp], i32),
             "raftgpu_memcpy_h2d": ([vp, vp, vp, u64], i32),
             "raftgpu_memcpy_d2h": ([vp, vp, vp, u64], i32),
-            "raftgpu_synth_init": ([C.POINTER(SynthColumns), u64, u32, i32], i32),
-            "raftgpu_synth_round": ([C.POINTER(SynthColumns), u64, u32, u32, vp, u64,
-                                     C.POINTER(u64)], i32),
         }
         for name, (args, res) in sig.items():
             f = getattr(L, name)
@@ -273,6 +272,25 @@ def lib() -> C.CDLL:
         L._signatures = sig
         _lib = L
     return _lib
+
+
+_synth_lib = None
+
+
+def synth_lib() -> C.CDLL:
+    """libraftgpu_synth.so: the synthetic workload generator (include/raftgpu_synth.h), a
+    separate library so the product .so carries no bench infrastructure."""
+    global _synth_lib
+    if _synth_lib is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise RuntimeError(f"{SYNTH_LIB_PATH} is missing: run __graft_entry__.build() / make -C raft-rs_b200")
+        L = C.CDLL(SYNTH_LIB_PATH)
+        vp, u32, i32, u64 = C.c_void_p, C.c_uint32, C.c_int32, C.c_uint64
+        L.raftgpu_synth_init.argtypes, L.raftgpu_synth_init.restype = [C.POINTER(SynthColumns), u64, u32, i32], i32
+        L.raftgpu_synth_round.argtypes = [C.POINTER(SynthColumns), u64, u32, u32, vp, u64, C.POINTER(u64)]
+        L.raftgpu_synth_round.restype = i32
+        _synth_lib = L
+    return _synth_lib
 
 
 def strerror(status: int) -> str:
@@ -348,7 +366,7 @@ class Synth:
                           ("term", c.term), ("sim_acked", self.sim_acked),
                           ("sim_last", self.sim_last), ("sim_flags", self.sim_flags)]:
             setattr(self._sc, name, arr.ctypes.data)
-        rc = lib().raftgpu_synth_init(C.byref(self._sc), seed, k_peers, int(joint))
+        rc = synth_lib().raftgpu_synth_init(C.byref(self._sc), seed, k_peers, int(joint))
         if rc != OK:
             raise RaftGpuError(rc, "raftgpu_synth_init")
         # what an arena / the oracle is loaded with (rounds only advance the sim_* state)
@@ -368,7 +386,7 @@ class Synth:
                 self._buf = np.empty(cap, dtype=APPEND_RESP_DTYPE)
             out = self._buf
         n = C.c_uint64()
-        rc = lib().raftgpu_synth_round(C.byref(self._sc), self.seed, self.round_no, self.k_union,
+        rc = synth_lib().raftgpu_synth_round(C.byref(self._sc), self.seed, self.round_no, self.k_union,
                                        out.ctypes.data, len(out), C.byref(n))
         if rc != OK:
             raise RaftGpuError(rc, "raftgpu_synth_round")

@@ -26,6 +26,7 @@
 #endif
 
 #include "kernels.cuh"
+#include "pack_compact.h"
 
 using namespace raftgpu;
 
@@ -84,24 +85,47 @@ struct StagingSet {
     raftgpu_step_result result{};
 };
 
-// The library's own staging workers for raftgpu_enqueue_bulk: persistent threads, pinned to
-// the GPU-local CPUs, one staging ring each.
+// The library's own staging workers (raftgpu_enqueue_bulk, raftgpu_step_begin_records): persistent
+// threads, pinned to the GPU-local CPUs.  A step arrives every few hundred microseconds, so a worker
+// that has just finished a job SPINS on the generation counter for a while (RAFTGPU_SPIN_US, default
+// 400) before it goes to sleep on the condition variable: waking 32 sleepers through a futex costs
+// more than the job itself.  The submitter spins on `pending` likewise.
 struct HostPool {
     std::vector<std::thread> threads;
     std::mutex mu;
-    std::condition_variable cv_start, cv_done;
-    uint64_t generation = 0;
-    int pending = 0;
-    bool stop = false;
+    std::condition_variable cv_start;
+    std::atomic<uint64_t> generation{0};
+    std::atomic<int> pending{0};
+    std::atomic<int> sleepers{0};
+    std::atomic<bool> stop{false};
     std::function<void(int)> job;
+    int spin_us = 400;
 
-    void run(const std::function<void(int)> &fn) {
-        std::unique_lock<std::mutex> lk(mu);
+    static inline void cpu_relax() {
+#if defined(__x86_64__)
+        _mm_pause();
+#endif
+    }
+    // start `fn` on every worker and return at once; wait() blocks until all are done
+    void start(const std::function<void(int)> &fn) {
         job = fn;
-        pending = static_cast<int>(threads.size());
-        generation++;
-        cv_start.notify_all();
-        cv_done.wait(lk, [&] { return pending == 0; });
+        pending.store(static_cast<int>(threads.size()));
+        generation.fetch_add(1);
+        if (sleepers.load() > 0) {
+            std::lock_guard<std::mutex> lk(mu);
+            cv_start.notify_all();
+        }
+    }
+    void wait() {
+        uint32_t spins = 0;
+        while (pending.load(std::memory_order_acquire) != 0) {
+            cpu_relax();
+            if (++spins > (1u << 20)) std::this_thread::yield();
+        }
+    }
+    void run(const std::function<void(int)> &fn) {
+        start(fn);
+        wait();
     }
     void worker(int idx, cpu_set_t cpus, bool pin, int first_cpu) {
         if (pin) {
@@ -127,25 +151,29 @@ struct HostPool {
         }
         uint64_t seen = 0;
         for (;;) {
-            std::function<void(int)> fn;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv_start.wait(lk, [&] { return stop || generation != seen; });
-                if (stop) return;
-                seen = generation;
-                fn = job;
+            const auto t_idle = std::chrono::steady_clock::now();
+            uint32_t spins = 0;
+            while (generation.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed)) {
+                cpu_relax();
+                if ((++spins & 255u) == 0 &&
+                    std::chrono::steady_clock::now() - t_idle > std::chrono::microseconds(spin_us)) {
+                    std::unique_lock<std::mutex> lk(mu);
+                    sleepers.fetch_add(1);
+                    cv_start.wait(lk, [&] { return stop.load() || generation.load() != seen; });
+                    sleepers.fetch_sub(1);
+                    break;
+                }
             }
-            fn(idx);
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (--pending == 0) cv_done.notify_one();
-            }
+            if (stop.load()) return;
+            seen = generation.load(std::memory_order_acquire);
+            job(idx);
+            pending.fetch_sub(1, std::memory_order_release);
         }
     }
     ~HostPool() {
         {
             std::lock_guard<std::mutex> lk(mu);
-            stop = true;
+            stop.store(true);
             cv_start.notify_all();
         }
         for (auto &t : threads) t.join();
@@ -193,7 +221,12 @@ struct raftgpu_arena {
     std::string last_error;
     std::vector<void *> user_allocs;
     std::vector<void *> host_allocs;  // raftgpu_host_alloc
-    HostPool *pool = nullptr;  // created on first raftgpu_enqueue_bulk
+    HostPool *pool = nullptr;  // created on first raftgpu_enqueue_bulk / raftgpu_step_begin_records
+    // raftgpu_step_begin_records scratch, kept between steps (no allocation on the step path)
+    std::vector<uint64_t> rec_cut;
+    std::vector<PackState> rec_pack;
+    std::vector<uint32_t> rec_gbase;
+    std::vector<std::atomic<int32_t>> rec_done;
     cpu_set_t local_cpus;      // GPU-local CPUs (empty when unknown)
     bool have_local_cpus = false;
 };

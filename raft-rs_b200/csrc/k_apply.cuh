@@ -49,22 +49,7 @@ struct CellPtrs {
     uint8_t *pflags;
 };
 
-// Packed staging record, 16 bytes: what raftgpu_enqueue_* writes into the pinned rings and the
-// step path ships over PCIe (the public 24-byte raftgpu_append_resp stays the API; packing cuts
-// the H2D bytes -- the end-to-end bottleneck -- and the apply kernel's record traffic by a third).
-//   w0: [0,32) group  [32,35) slot  35 REJECT  36 LOCAL  37 EXT  38 WIDE  39 HAS_EXT  [40,64) delta
-//   w1: m.index   (EXT: the payload)
-// commit is carried as a 24-bit delta: index - commit for a message (a follower's commit never
-// exceeds what it acknowledges), commit - index for a LOCAL record (0xFFFFFF = "no new
-// last_index"); anything else sets WIDE and the exact value follows in an EXT record.
-// EXT kinds (in the delta field): 1 = next_probe_index, 2 = request_snapshot, 3 = wide commit,
-// 0 = padding.
-struct PackedRec {
-    uint64_t w0, w1;
-};
-constexpr uint64_t kPkReject = 1ull << 35, kPkLocal = 1ull << 36, kPkExt = 1ull << 37, kPkWide = 1ull << 38,
-                   kPkHasExt = 1ull << 39;
-constexpr uint32_t kPkNoCommit = 0xFFFFFFu;
+// PackedRec and the kPk* / kCu* bit layouts: wire_format.h
 
 template <bool kPacked>
 __device__ __forceinline__ RecRegs load_rec(const void *recs_v, uint64_t i, uint64_t n) {
@@ -342,10 +327,6 @@ apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__re
 
 // ---------------------------------------------------------------------------
 // The compact stream (raftgpu.h "compact stream"): 4-byte units, group runs with a header.
-constexpr uint32_t kCuRec = 0, kCuHdrA = 1, kCuHdrB = 2, kCuEsc = 3;
-constexpr uint32_t kCuLocal = 4u, kCuReject = 1u << 9, kCuNoCommit = 255u;
-constexpr uint32_t kCuPayload = 1u << 29;   // in the ESC field: a REJECT's hint rides here, not a side index
-constexpr uint32_t kCuPad = 0x1fffffffu;    // ESC field value of a padding unit (side indexes stay below it)
 struct CompactSrc {
     const uint32_t *units;
     const uint32_t *g_base;              // one per block of RAFTGPU_COMPACT_BLOCK units

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "raftgpu.h"
+#include "wire_format.h"
 
 namespace raftgpu {
 

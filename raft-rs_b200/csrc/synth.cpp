@@ -7,7 +7,7 @@
 #include <cstdint>
 #include <cstring>
 
-#include "raftgpu.h"
+#include "raftgpu_synth.h"
 
 namespace {
 

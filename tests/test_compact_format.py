@@ -62,8 +62,8 @@ def test_empty_batch():
     assert hdr["n_units"] == 0 and hdr["n_side"] == 0
 
 
-def test_round_trip_random_records():
-    rng = np.random.default_rng(5)
+def hostile_records(seed=5):
+    rng = np.random.default_rng(seed)
     edge = [0, 1, 2, 254, 255, 256, 0x3ffe, 0x3fff, 0x4000, 0x7ffe, 0x7fff, 0x8000, (1 << 28) - 1, 1 << 28, (1 << 28) + 1, (1 << 30) - 1, 1 << 30, (1 << 48) - 1, 1 << 48,
             (1 << 48) + 0x7fff, (1 << 48) + 0x8000, 1 << 63, M64 - 1, M64]
     rows = []
@@ -95,9 +95,43 @@ def test_round_trip_random_records():
                         int(rng.choice([-(1 << 28) - 1, -(1 << 28), (1 << 28) - 1, 1 << 28, 1 << 40]))
                     rows.append((g, slot, B.REC_EXT, 0, min(M64, max(0, index + hd)),
                                  0 if rng.random() < 0.7 else int(rng.integers(1, 1 << 40))))
-    recs = np.array(rows, dtype=B.APPEND_RESP_DTYPE)
-    hdr = check_round_trip(recs)
+    return np.array(rows, dtype=B.APPEND_RESP_DTYPE)
+
+
+def test_round_trip_random_records():
+    hdr = check_round_trip(hostile_records())
     assert hdr["n_side"] > 0
+
+
+def test_vector_packer_is_byte_identical_to_the_scalar_definition(tmp_path):
+    """pack_compact.cpp has an AVX-512 form (whole runs per step) and the scalar state machine that
+    defines the format; RAFTGPU_PACK_SCALAR=1 forces the latter.  Same bytes for hostile records,
+    for synthetic rounds, and when the batch is packed in slices (as the staging threads do)."""
+    import os
+    import subprocess
+    import sys
+    batches = [hostile_records(11), hostile_records(12), B.Synth(30000, 0xABCDE, k_peers=5).next_round().copy(),
+               B.Synth(9000, 3, k_peers=5, joint=True).next_round().copy()]
+    for k, recs in enumerate(batches):
+        np.save(tmp_path / f"recs{k}.npy", recs)
+        blob, units = pack(recs)
+        np.save(tmp_path / f"blob{k}.npy", blob)
+        np.save(tmp_path / f"units{k}.npy", units)
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r})
+from test_compact_format import pack
+for k in range({len(batches)}):
+    recs = np.load({str(tmp_path)!r} + f"/recs{{k}}.npy")
+    blob, units = pack(recs)
+    assert np.array_equal(blob, np.load({str(tmp_path)!r} + f"/blob{{k}}.npy")), k
+    assert np.array_equal(units, np.load({str(tmp_path)!r} + f"/units{{k}}.npy")), k
+print("same")
+"""
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RAFTGPU_PACK_SCALAR="1"),
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "same" in r.stdout, r.stderr
 
 
 def test_unsorted_and_stray_ext():

@@ -302,25 +302,46 @@ def main():
             ev.record(stream)
         arenas[a].recompute(0, n, stream=sh)
 
-    def timed(fn, first, count):
-        """count back-to-back steps under CUDA events on the launching stream; (ms total, per-step event pairs)."""
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
+    def timed(fn, first, count, per_launch=True):
+        """count back-to-back steps under CUDA events on the launching stream -> (ms total, ms in kernels).
+        per_launch: an event pair around every launch (the fused kernel: 70 us, the pair costs nothing
+        visible); without it the launches are captured into ONE CUDA graph and replayed, so that short
+        kernels (the 14 us recompute pass) run back to back instead of at the pace Python issues them."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        graph = None
+        if not per_launch:
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    for i in range(count):
+                        fn(first + i)
+            except Exception as e:   # capture refused: time the plain launches
+                print(f"[bench] CUDA graph capture failed ({e}); timing direct launches", file=sys.stderr)
+                graph = None
+                torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)] \
+            if per_launch else []
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0.record(stream)
-        for i in range(count):
-            evs[i][0].record(stream)
-            fn(first + i)
-            evs[i][1].record(stream)
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(count):
+                if per_launch:
+                    evs[i][0].record(stream)
+                fn(first + i)
+                if per_launch:
+                    evs[i][1].record(stream)
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        total = e0.elapsed_time(e1)
+        return total, (sum(a_.elapsed_time(b_) for a_, b_ in evs) if per_launch else total)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -359,7 +380,7 @@ def main():
             # recompute only: Raft::maybe_commit over every group, arenas rotated (4 x 74 MB > L2 hit window)
             for i in range(W):
                 arenas[i % N_ARENAS].recompute(0, n, stream=sh)
-            ro_total, _ = timed(lambda i: arenas[i % N_ARENAS].recompute(0, n, stream=sh), 0, K)
+            ro_total, _ = timed(lambda i: arenas[i % N_ARENAS].recompute(0, n, stream=sh), 0, K, per_launch=False)
             ro = {"ms_total": ro_total}
 
     # ---- e2e: host buffers -> C-ABI -> results in host memory, on a fresh arena ------------------

@@ -88,7 +88,7 @@ struct StagingSet {
 // The library's own staging workers (raftgpu_enqueue_bulk, raftgpu_step_begin_records): persistent
 // threads, pinned to the GPU-local CPUs.  A step arrives every few hundred microseconds, so a worker
 // that has just finished a job SPINS on the generation counter for a while (RAFTGPU_SPIN_US, default
-// 400) before it goes to sleep on the condition variable: waking 32 sleepers through a futex costs
+// 2000) before it goes to sleep on the condition variable: waking 32 sleepers through a futex costs
 // more than the job itself.  The submitter spins on `pending` likewise.
 struct HostPool {
     std::vector<std::thread> threads;
@@ -99,7 +99,7 @@ struct HostPool {
     std::atomic<int> sleepers{0};
     std::atomic<bool> stop{false};
     std::function<void(int)> job;
-    int spin_us = 400;
+    int spin_us = 2000;
 
     static inline void cpu_relax() {
 #if defined(__x86_64__)
@@ -120,34 +120,19 @@ struct HostPool {
         uint32_t spins = 0;
         while (pending.load(std::memory_order_acquire) != 0) {
             cpu_relax();
-            if (++spins > (1u << 20)) std::this_thread::yield();
+            if ((++spins & 63u) == 0) std::this_thread::yield();  // this thread may sit on a worker's CPU
         }
     }
     void run(const std::function<void(int)> &fn) {
         start(fn);
         wait();
     }
-    void worker(int idx, cpu_set_t cpus, bool pin, int first_cpu) {
-        if (pin) {
-            // one CPU per worker, taken in order from the GPU-local list (its first half are
-            // distinct physical cores on these hosts; SMT siblings come after), starting at an
-            // offset derived from the device index so that the arenas of several GPUs on the same
-            // socket (one process per GPU) do not pile onto the same cores
+    void worker(int idx, int cpu) {
+        if (cpu >= 0) {  // one CPU per worker (ensure_pool picks them: GPU-local physical cores first)
             cpu_set_t one;
             CPU_ZERO(&one);
-            int seen = 0, chosen = -1;
-            const int want = (first_cpu + idx) % std::max(1, CPU_COUNT(&cpus));
-            for (int c = 0; c < CPU_SETSIZE; c++)
-                if (CPU_ISSET(c, &cpus) && seen++ == want) {
-                    chosen = c;
-                    break;
-                }
-            if (chosen >= 0) {
-                CPU_SET(chosen, &one);
-                sched_setaffinity(0, sizeof(one), &one);
-            } else {
-                sched_setaffinity(0, sizeof(cpus), &cpus);
-            }
+            CPU_SET(cpu, &one);
+            sched_setaffinity(0, sizeof(one), &one);
         }
         uint64_t seen = 0;
         for (;;) {

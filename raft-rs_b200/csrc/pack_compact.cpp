@@ -5,11 +5,9 @@
 //
 // Two implementations with byte-identical output:
 //   pack_range_scalar  one record at a time (the definition of the format);
-//   pack_range         AVX-512: run boundaries for 64 records at a time from one pass over the group
-//                      words, then ONE 8-lane pass per run -- no data-dependent branch per record, and
-//                      no loop-carried dependency between runs except the output position.  Runs the
-//                      vector form cannot take (a REJECT / EXT inside, values out of the compact
-//                      ranges, more than 8 records) go through the scalar state machine.
+//   pack_range         AVX-512: eight records per step as lane arithmetic, whatever runs they belong
+//                      to (see pack_range_avx512); blocks the lanes cannot express go through the
+//                      scalar state machine.
 #include "pack_compact.h"
 
 #include <algorithm>
@@ -158,7 +156,7 @@ int32_t pack_range_scalar(const raftgpu_append_resp *records, uint64_t lo, uint6
 }
 
 #if defined(__x86_64__)
-#define RAFTGPU_AVX512 __attribute__((target("avx512f,avx512bw,avx512dq,avx512vl,bmi,bmi2,lzcnt,popcnt")))
+#define RAFTGPU_AVX512 __attribute__((target("avx512f,avx512bw,avx512dq,avx512vl,avx512cd,avx512vpopcntdq,bmi,bmi2,lzcnt,popcnt")))
 
 // records[i, i+8) as three vectors of their 64-bit words: W = {group, peer_slot, flags}, I = index, C = commit
 RAFTGPU_AVX512 static inline void load8(const raftgpu_append_resp *p, __m512i &W, __m512i &I, __m512i &C) {
@@ -174,116 +172,180 @@ RAFTGPU_AVX512 static inline void load8(const raftgpu_append_resp *p, __m512i &W
     C = _mm512_mask_permutexvar_epi64(_mm512_permutex2var_epi64(z0, c01, z1), 0xE0, c2, z2);
 }
 
+// T_first[ks][k]: the lane (<= k) at which the run of lane k starts, for the 8-bit run-start mask ks
+// (bit j = lane j opens a run); 8 = the run was opened before this block (carry).
+struct FirstTable {
+    alignas(64) uint8_t t[256][8];
+    FirstTable() {
+        for (int ks = 0; ks < 256; ks++) {
+            int cur = 8;
+            for (int k = 0; k < 8; k++) {
+                if ((ks >> k) & 1) cur = k;
+                t[ks][k] = static_cast<uint8_t>(cur);
+            }
+        }
+    }
+};
+static const FirstTable kFirst;
+
+// The vector form: EIGHT records per step, whatever runs they belong to.  All per-record work (run
+// starts, the run's base index, position inside the run, the delta fits, the unit words, the headers
+// and REJECT payloads) is lane arithmetic; the units of the block -- [HDR_A HDR_B] rec [payload] per
+// lane -- are laid out as 32 candidates and squeezed together with two vpcompressd.  Between blocks only
+// a handful of scalars carry over (output position, the open run's group / base / length / slots), so
+// consecutive blocks overlap in the pipeline.  Whatever the lanes cannot express (an unknown flag
+// combination, a delta that does not fit, a run reaching 8 units, a header that needs a new g_base
+// word, ...) sends that block through the scalar state machine, which also defines the result.
 RAFTGPU_AVX512 static int32_t pack_range_avx512(const raftgpu_append_resp *records, uint64_t lo, uint64_t hi, uint64_t n_total,
                                                 PackState &st, uint32_t *unit_of_record, uint32_t unit_base) {
     static_assert(sizeof(raftgpu_append_resp) == 24, "record layout");
-    uint64_t i = lo;
-    const __m512i gather_idx = _mm512_setr_epi64(0, 3, 6, 9, 12, 15, 18, 21);  // record j's first word, in 8-byte units
-    const __m512i lane3 = _mm512_setr_epi64(0 << 3, 1 << 3, 2 << 3, 3 << 3, 4 << 3, 5 << 3, 6 << 3, 7 << 3);
-    // a record the vector form may take: flags in {0, LOCAL}, peer_slot < 8 (reserved bits ignored)
-    const __m512i dirty_bits = _mm512_set1_epi64(0x0000fdf800000000ll);
+    if (unit_of_record) return pack_range_scalar(records, lo, hi, n_total, st, unit_of_record, unit_base);  // tests only
+    const __m512i zero = _mm512_setzero_si512();
     const __m512i lo32 = _mm512_set1_epi64(0xffffffffll);
-    // Window of 64 records starting at c0: bit k of `starts` = record c0+k opens a new stretch of equal
-    // groups, bit k of `clean` = record c0+k is vector material.  A run's end is searched at most 9
-    // records ahead, so a window serves starts up to c0+54 and is then re-based.
-    while (i < hi && i + 64 + 8 <= n_total) {
-        const uint64_t c0 = i;
-        uint64_t starts = 0, clean = 0;
-        {
-            const long long *w = reinterpret_cast<const long long *>(records + c0);
-            // the group before the window: a real record, or (at the very start) anything that differs
-            long long before = c0 > 0 ? reinterpret_cast<const long long *>(records + c0 - 1)[0] : ~w[0];
-            __m512i prev = _mm512_set1_epi64(before);
-            for (int j = 0; j < 8; j++) {
-                const __m512i W = _mm512_i64gather_epi64(gather_idx, w + 24 * j, 8);
-                const __m512i P = _mm512_alignr_epi64(W, prev, 7);  // lane k = word of record c0 + 8j + k - 1
-                const __mmask8 ks = _mm512_cmpneq_epu64_mask(_mm512_and_si512(W, lo32), _mm512_and_si512(P, lo32));
-                const __mmask8 kc = _mm512_testn_epi64_mask(W, dirty_bits);
-                starts |= static_cast<uint64_t>(ks) << (8 * j);
-                clean |= static_cast<uint64_t>(kc) << (8 * j);
-                prev = W;
+    const __m512i c255 = _mm512_set1_epi64(255), c8 = _mm512_set1_epi64(8), one = _mm512_set1_epi64(1);
+    const __m512i idx0 = _mm512_setr_epi64(0, 8, 1, 9, 2, 10, 3, 11), idx1 = _mm512_setr_epi64(4, 12, 5, 13, 6, 14, 7, 15);
+    uint64_t i = lo;
+    while (i + 8 <= hi) {
+        const raftgpu_append_resp *p = records + i;
+        __m512i W, I, C;
+        load8(p, W, I, C);
+        const __m512i F = _mm512_and_si512(_mm512_srli_epi64(W, 40), c255);  // flags
+        const __m512i S = _mm512_and_si512(_mm512_srli_epi64(W, 32), c255);  // peer slot
+        const __mmask8 kext = _mm512_cmpeq_epu64_mask(F, _mm512_set1_epi64(RAFTGPU_REC_EXT));
+        const __mmask8 kloc = _mm512_cmpeq_epu64_mask(F, _mm512_set1_epi64(RAFTGPU_REC_LOCAL));
+        const __mmask8 krej_all = _mm512_cmpeq_epu64_mask(F, one);  // RAFTGPU_REC_REJECT
+        const __mmask8 kacc = _mm512_testn_epi64_mask(F, F);
+        const __mmask8 kslot = _mm512_cmplt_epu64_mask(S, c8) | kext;
+        bool vec = ((kext | kloc | krej_all | kacc) & kslot) == 0xff;
+        // a REJECT in the last lane has its EXT in the next block: leave it for the next step
+        const uint32_t nproc = (krej_all & 0x80) ? 7u : 8u;
+        const __mmask8 live = static_cast<__mmask8>((1u << nproc) - 1u);
+        const __mmask8 krej = krej_all & live, kmain = static_cast<__mmask8>(~kext) & live;
+        const __m512i G = _mm512_and_si512(W, lo32);
+        const __m512i Gprev = _mm512_alignr_epi64(G, _mm512_set1_epi64(st.cur_g), 7);
+        __mmask8 ks = _mm512_cmpneq_epu64_mask(G, Gprev) & live;
+        if (!st.in_run) ks |= 1;
+        vec = vec && !(ks & kext);  // an EXT whose group differs from its predecessor's: the scalar form sorts it out
+        const uint64_t nu = st.nu, b = nu / RAFTGPU_COMPACT_BLOCK;
+        vec = vec && nu + 32 <= st.unit_cap && (nu + 31) / RAFTGPU_COMPACT_BLOCK == b && st.blocks_set > b;
+        const __mmask8 kc = ks ? static_cast<__mmask8>((ks & (0u - ks)) - 1u) : 0xff;  // lanes of the run carried in
+        vec = vec && !((kc & kmain) && !(st.in_run && st.header));
+        if (vec) {
+            // units per lane (0 EXT, 1 record, 2 REJECT + payload) and their running sum
+            const __m512i CNT = _mm512_mask_add_epi64(_mm512_maskz_mov_epi64(kmain, one), krej, one, one);
+            __m512i x = _mm512_add_epi64(CNT, _mm512_alignr_epi64(CNT, zero, 7));
+            x = _mm512_add_epi64(x, _mm512_alignr_epi64(x, zero, 6));
+            x = _mm512_add_epi64(x, _mm512_alignr_epi64(x, zero, 4));
+            const __m512i E = _mm512_sub_epi64(x, CNT);  // exclusive
+            const __m512i idxFirst = _mm512_cvtepu8_epi64(_mm_loadl_epi64(reinterpret_cast<const __m128i *>(kFirst.t[ks])));
+            // units of the lane's run in front of it (the `back` field): E - E[first], carried run: + st.back
+            const __m512i BACK = _mm512_sub_epi64(
+                E, _mm512_permutex2var_epi64(E, idxFirst, _mm512_set1_epi64(-static_cast<long long>(st.back))));
+            // the scalar form opens a new run when run_units + need > 8; run_units counts 2 for every REJECT, also
+            // one that went to the side table as ONE unit, so the carried run may be ahead of its `back`
+            const __m512i RU = _mm512_mask_add_epi64(BACK, kc, BACK, _mm512_set1_epi64(st.run_units - st.back));
+            const __mmask8 kover = _mm512_cmpgt_epu64_mask(_mm512_add_epi64(RU, CNT), c8) & live;
+            // the run's base: its first record's index - 8192 (saturating)
+            const __m512i c2000 = _mm512_set1_epi64(0x2000);
+            const __m512i baseRec = _mm512_sub_epi64(_mm512_max_epu64(I, c2000), c2000);
+            const __m512i BASE = _mm512_permutex2var_epi64(baseRec, idxFirst, _mm512_set1_epi64(static_cast<long long>(st.base)));
+            const __m512i D = _mm512_sub_epi64(I, BASE);
+            const __mmask8 kd = _mm512_cmple_epu64_mask(D, _mm512_set1_epi64(0x3fff));
+            // headers: base < 2^48, group within 4095 of the block's g_base
+            const uint32_t gb = st.g_base[b];
+            const __m512i GD = _mm512_sub_epi64(G, _mm512_set1_epi64(gb));
+            const __mmask8 khdr = _mm512_cmple_epu64_mask(GD, _mm512_set1_epi64(0xfff)) &
+                                  _mm512_cmplt_epu64_mask(BASE, _mm512_set1_epi64(1ll << 48));
+            // commit deltas
+            const __m512i CDM = _mm512_sub_epi64(I, C);  // message (accept / reject): index - commit
+            const __mmask8 kcm = _mm512_cmple_epu64_mask(CDM, c255);
+            const __m512i CDL = _mm512_sub_epi64(C, I);  // LOCAL: commit - index, or 255 for "no new last_index"
+            const __mmask8 kzero = _mm512_testn_epi64_mask(C, C);
+            const __mmask8 kcl = _mm512_cmplt_epu64_mask(CDL, c255) | kzero;
+            const __m512i CD = _mm512_mask_blend_epi64(kloc, CDM, _mm512_mask_mov_epi64(CDL, kzero, c255));
+            const __mmask8 kcok = (kloc & kcl) | (static_cast<__mmask8>(~kloc) & kcm);
+            // REJECT payload: the EXT behind it gives next_probe_index (hint) and request_snapshot
+            __m512i DH = zero;
+            __mmask8 krejok = 0xff;
+            if (krej) {
+                const __mmask8 kextnext = static_cast<__mmask8>(kext >> 1);
+                const __m512i HINT = _mm512_maskz_mov_epi64(kextnext, _mm512_alignr_epi64(zero, I, 1));
+                const __m512i SNAP = _mm512_maskz_mov_epi64(kextnext, _mm512_alignr_epi64(zero, C, 1));
+                DH = _mm512_sub_epi64(HINT, I);
+                krejok = _mm512_cmplt_epu64_mask(_mm512_add_epi64(DH, _mm512_set1_epi64(1ll << 28)), _mm512_set1_epi64(1ll << 29)) &
+                         _mm512_testn_epi64_mask(SNAP, SNAP);
+            }
+            const __mmask8 good = (static_cast<__mmask8>(~kmain) | (kd & kcok)) & (static_cast<__mmask8>(~krej) | krejok) &
+                                  (static_cast<__mmask8>(~ks) | khdr);
+            vec = !kover && (good & live) == live;
+            if (vec) {
+                // ---- the unit words
+                __m512i U = _mm512_or_si512(_mm512_slli_epi64(S, 6), _mm512_slli_epi64(D, 10));
+                U = _mm512_or_si512(U, _mm512_slli_epi64(CD, 24));
+                U = _mm512_or_si512(U, _mm512_slli_epi64(BACK, 3));
+                U = _mm512_mask_or_epi64(U, kloc, U, _mm512_set1_epi64(kCuLocal));
+                U = _mm512_mask_or_epi64(U, krej, U, _mm512_set1_epi64(kCuReject));
+                const __m512i P = _mm512_or_si512(
+                    _mm512_set1_epi64(kCuEsc | (static_cast<uint64_t>(kCuPayload) << 2)),
+                    _mm512_slli_epi64(_mm512_and_si512(DH, _mm512_set1_epi64(kCuPayload - 1u)), 2));
+                const __m512i HA = _mm512_or_si512(_mm512_set1_epi64(kCuHdrA),
+                                                   _mm512_slli_epi64(_mm512_and_si512(BASE, _mm512_set1_epi64(0x3fffffff)), 2));
+                const __m512i HB = _mm512_or_si512(_mm512_or_si512(_mm512_set1_epi64(kCuHdrB), _mm512_slli_epi64(GD, 2)),
+                                                   _mm512_slli_epi64(_mm512_srli_epi64(BASE, 30), 14));
+                // lane k's four candidates [HDR_A HDR_B rec payload] side by side: two 64-bit words per lane
+                const __m512i V1 = _mm512_or_si512(HA, _mm512_slli_epi64(HB, 32)), V2 = _mm512_or_si512(U, _mm512_slli_epi64(P, 32));
+                const __m512i X0 = _mm512_permutex2var_epi64(V1, idx0, V2), X1 = _mm512_permutex2var_epi64(V1, idx1, V2);
+                const uint32_t m32 = static_cast<uint32_t>(_pdep_u32(ks, 0x11111111u)) * 3u | static_cast<uint32_t>(_pdep_u32(kmain, 0x44444444u)) |
+                                     static_cast<uint32_t>(_pdep_u32(krej, 0x88888888u));
+                uint32_t *out = st.units + nu;
+                const uint32_t n0 = static_cast<uint32_t>(__builtin_popcount(m32 & 0xffffu));
+                _mm512_storeu_si512(out, _mm512_maskz_compress_epi32(static_cast<__mmask16>(m32 & 0xffffu), X0));
+                _mm512_storeu_si512(out + n0, _mm512_maskz_compress_epi32(static_cast<__mmask16>(m32 >> 16), X1));
+                // ---- one record per (group, peer) cell?  Every main lane sets bit (8 * run ordinal + slot) of a
+                // 64-bit word (at most 8 runs touch a block): a cell hit twice leaves fewer bits than lanes.
+                const __m512i RI = _mm512_popcnt_epi64(_mm512_and_si512(_mm512_set1_epi64(ks), _mm512_setr_epi64(1, 3, 7, 15, 31, 63, 127, 255)));
+                const __m512i sh = _mm512_add_epi64(S, _mm512_slli_epi64(_mm512_and_si512(RI, _mm512_set1_epi64(7)), 3));
+                const uint64_t cells = static_cast<uint64_t>(_mm512_reduce_or_epi64(_mm512_maskz_sllv_epi64(kmain, one, sh)));
+                if (__builtin_popcountll(cells) != __builtin_popcount(kmain) || (!(ks & 1) && (cells & 0xffu & st.seen_slots)))
+                    st.one_wave = false;
+                if (kmain) {
+                    const uint32_t last = nproc - 1;
+                    const uint32_t g_last = p[last].group;
+                    if (_mm512_cmplt_epu64_mask(G, Gprev) & ks & (st.have_prev_group ? 0xff : 0xfe)) st.tileable = false;
+                    if (!st.any) {
+                        st.any = true;
+                        st.first_group = p[_tzcnt_u32(kmain)].group;
+                    }
+                    if (ks) {
+                        const uint32_t ls = 31u - static_cast<uint32_t>(__builtin_clz(static_cast<uint32_t>(ks)));
+                        const __mmask8 tail = static_cast<__mmask8>(0xffu << ls);
+                        st.back = st.run_units = static_cast<uint32_t>(__builtin_popcount(kmain & tail) + __builtin_popcount(krej & tail));
+                        const uint64_t idx = p[ls].index;
+                        st.base = idx > 0x2000u ? idx - 0x2000u : 0;
+                        st.header = true;
+                        st.seen_slots = static_cast<uint32_t>(cells >> (8 * (__builtin_popcount(ks) & 7))) & 0xffu;
+                    } else {
+                        const uint32_t added = static_cast<uint32_t>(__builtin_popcount(kmain) + __builtin_popcount(krej));
+                        st.back += added;
+                        st.run_units += added;
+                        st.seen_slots |= static_cast<uint32_t>(cells & 0xffu);
+                    }
+                    st.in_run = true;
+                    st.have_prev_group = true;
+                    st.cur_g = st.prev_group = st.last_group = g_last;
+                }
+                st.nu = nu + static_cast<uint32_t>(__builtin_popcount(m32));
+                st.n_rec += static_cast<uint32_t>(__builtin_popcount(kmain));
+                i += nproc;
             }
         }
-        while (i < hi && i - c0 < 55) {
-            const uint32_t off = static_cast<uint32_t>(i - c0);
-            // length of the stretch of equal groups that starts at i: 1..8, or 9 = "more than 8"
-            uint32_t len = static_cast<uint32_t>(_tzcnt_u64((starts >> (off + 1)) | 0x100u)) + 1u;
-            const bool too_long = len > 8;
-            if (too_long) len = 8;
-            if (i + len > hi) len = static_cast<uint32_t>(hi - i);
-            const uint32_t lenmask = (1u << len) - 1u;
-            const raftgpu_append_resp *p = records + i;
-            const uint32_t g = p->group;
-            bool vec = !too_long && ((clean >> off) & lenmask) == lenmask && !(st.in_run && st.cur_g == g);
-            if (vec) {
-                const uint64_t idx0 = p->index;
-                const uint64_t base = idx0 > 0x2000u ? idx0 - 0x2000u : 0;
-                const uint64_t b = st.nu / RAFTGPU_COMPACT_BLOCK;
-                if (st.nu + 2 + 8 > st.unit_cap) return RAFTGPU_ERR_FULL;  // what the scalar form answers at a run start
-                const uint32_t gb = (st.blocks_set <= b || b >= st.gbase_cap) ? g : st.g_base[b];
-                vec = b < st.gbase_cap && base < (1ull << 48) && g >= gb && g - gb <= 0xfffu;
-                if (vec) {
-                    __m512i W, I, C;
-                    load8(p, W, I, C);
-                    const __mmask8 kloc = _mm512_test_epi64_mask(W, _mm512_set1_epi64(1ll << 41));  // flags & LOCAL
-                    const __m512i D = _mm512_sub_epi64(I, _mm512_set1_epi64(static_cast<long long>(base)));
-                    const __mmask8 kd = _mm512_cmple_epu64_mask(D, _mm512_set1_epi64(0x3fff));
-                    const __m512i CDM = _mm512_sub_epi64(I, C);  // message: index - commit
-                    const __mmask8 kcm = _mm512_cmple_epu64_mask(CDM, _mm512_set1_epi64(255));
-                    const __m512i CDL = _mm512_sub_epi64(C, I);  // LOCAL: commit - index, or 255 for "no new last_index"
-                    const __mmask8 kzero = _mm512_testn_epi64_mask(C, C);
-                    const __mmask8 kcl = _mm512_cmplt_epu64_mask(CDL, _mm512_set1_epi64(255)) | kzero;
-                    const __m512i CDLv = _mm512_mask_mov_epi64(CDL, kzero, _mm512_set1_epi64(255));
-                    const __m512i CD = _mm512_mask_blend_epi64(kloc, CDM, CDLv);
-                    const __mmask8 ok = kd & ((kloc & kcl) | (~kloc & kcm));
-                    vec = (ok & lenmask) == lenmask;
-                    if (vec) {
-                        // ---- commit the run: g_base, header, 8 units (lanes >= len are overwritten by the next run)
-                        uint32_t *units = st.units;
-                        uint64_t nu = st.nu;
-                        while (st.blocks_set <= b) st.g_base[st.blocks_set++] = g;
-                        units[nu] = kCuHdrA | (static_cast<uint32_t>(base & 0x3fffffffu) << 2);
-                        units[nu + 1] = kCuHdrB | ((g - gb) << 2) | (static_cast<uint32_t>(base >> 30) << 14);
-                        const __m512i slot = _mm512_and_si512(_mm512_srli_epi64(W, 32), _mm512_set1_epi64(7));
-                        __m512i U = _mm512_or_si512(_mm512_slli_epi64(slot, 6), _mm512_slli_epi64(D, 10));
-                        U = _mm512_or_si512(U, _mm512_slli_epi64(CD, 24));
-                        U = _mm512_or_si512(U, lane3);
-                        U = _mm512_mask_or_epi64(U, kloc, U, _mm512_set1_epi64(kCuLocal));
-                        _mm256_storeu_si256(reinterpret_cast<__m256i *>(units + nu + 2), _mm512_cvtepi64_epi32(U));
-                        if (unit_of_record)
-                            for (uint32_t k = 0; k < len; k++) unit_of_record[i + k] = unit_base + static_cast<uint32_t>(nu + 2 + k);
-                        // one record per (group, peer) cell?
-                        const __m512i bits = _mm512_sllv_epi64(_mm512_set1_epi64(1), slot);
-                        const uint32_t seen = static_cast<uint32_t>(_mm512_mask_reduce_or_epi64(static_cast<__mmask8>(lenmask), bits));
-                        if (static_cast<uint32_t>(__builtin_popcount(seen)) != len) st.one_wave = false;
-                        if (st.have_prev_group && g < st.prev_group) st.tileable = false;
-                        if (!st.any) {
-                            st.any = true;
-                            st.first_group = g;
-                        }
-                        st.last_group = g;
-                        st.prev_group = g;
-                        st.have_prev_group = true;
-                        st.seen_slots = seen;
-                        st.in_run = true;
-                        st.header = true;
-                        st.cur_g = g;
-                        st.run_units = len;
-                        st.back = len;
-                        st.base = base;
-                        st.nu = nu + 2 + len;
-                        st.n_rec += len;
-                    }
-                }
-            }
-            if (!vec) {
-                const int32_t rc = pack_range_scalar(records, i, i + len, n_total, st, unit_of_record, unit_base);
-                if (rc != RAFTGPU_OK) return rc;
-            }
-            i += len;
+        if (!vec) {
+            const int32_t rc = pack_range_scalar(records, i, i + 8, n_total, st, nullptr, unit_base);
+            if (rc != RAFTGPU_OK) return rc;
+            i += 8;
         }
     }
-    if (i < hi) return pack_range_scalar(records, i, hi, n_total, st, unit_of_record, unit_base);
+    if (i < hi) return pack_range_scalar(records, i, hi, n_total, st, nullptr, unit_base);
     return RAFTGPU_OK;
 }
 
@@ -292,7 +354,7 @@ static bool use_avx512() {
         const char *e = getenv("RAFTGPU_PACK_SCALAR");
         if (e && e[0] == '1') return false;
         return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512dq") &&
-               __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("bmi");
+               __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512vpopcntdq") && __builtin_cpu_supports("bmi2");
     }();
     return on;
 }

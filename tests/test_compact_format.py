@@ -188,3 +188,19 @@ def test_capacity_errors():
     out = np.zeros(128, dtype=np.uint8)
     with pytest.raises(RuntimeError):
         B.pack_compact(recs, out)
+
+
+def test_packer_differential_fuzz(tmp_path):
+    """scripts/micro/pack_fuzz.cpp: pack_range (the vector form on this CPU) against pack_range_scalar on
+    random traffic -- clean rounds, many REJECTs, hostile values, unsorted groups and stray EXT records --
+    packed as a sequence of arbitrary [lo, hi) ranges on one PackState.  Units, g_base words, side
+    records, ESC positions and the tileable / one-wave verdicts must be identical."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "pack_fuzz")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "raft-rs_b200", "csrc"),
+                    os.path.join(root, "scripts", "micro", "pack_fuzz.cpp"), os.path.join(root, "raft-rs_b200", "csrc", "pack_compact.cpp"),
+                    "-o", exe], check=True)
+    r = subprocess.run([exe, "800"], capture_output=True, text=True)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout + r.stderr

@@ -162,7 +162,8 @@ enum {
     RAFTGPU_COL_COMMITTED = 9,            /* u64 [cap] */
     RAFTGPU_COL_TERM_START = 10,          /* u64 [cap] */
     RAFTGPU_COL_LAST_INDEX = 11,          /* u64 [cap] */
-    RAFTGPU_COL__COUNT = 12
+    RAFTGPU_COL_TERM = 12,                /* u64 [cap]  Raft::term (raft.rs:227), 0 = unknown; only the wire path reads it */
+    RAFTGPU_COL__COUNT = 13
 };
 
 typedef struct {
@@ -551,6 +552,49 @@ int32_t raftgpu_step_send_list(raftgpu_arena *arena, raftgpu_send_entry *out, ui
 #define RAFTGPU_NO_HEARTBEAT UINT64_MAX
 int32_t raftgpu_heartbeat_commits_device(raftgpu_arena *arena, void *stream, uint32_t first, uint32_t n,
                                          uint64_t *d_out);
+
+/* ---- wire decode ------------------------------------- */
+
+/* The step from what a transport holds: serialized eraftpb.Message frames (proto/proto/eraftpb.proto:71-92;
+ * the reference decodes them with rust-protobuf / prost before RawNode::step, raw_node.rs:402-411).  The host
+ * appends frames and their end offsets and parses NOTHING; the GPU decodes the varints and runs the same
+ * per-message prefix of handle_append_response (raft.rs:1663-1743) + Raft::maybe_commit.
+ *      frame i = bytes[offsets[i], offsets[i+1]) = u32 little-endian (group << 4 | peer_slot), then the Message
+ * offsets[0..n] ascend.  Per frame one status byte comes back: RAFTGPU_WIRE_* << 4 | RAFTGPU_RES_* (the latter
+ * for applied frames).  Frames the device cannot decide are NOT applied and are the host's to handle: */
+#define RAFTGPU_WIRE_OK 0u         /* a MsgAppendResponse, applied (low nibble: RAFTGPU_RES_*) */
+#define RAFTGPU_WIRE_SKIP_TYPE 1u  /* any other MessageType: Raft::step on the host */
+#define RAFTGPU_WIRE_TERM 2u       /* m.term != the group's term (raftgpu_group_set_term; 0 = not checked): Raft::step's term rules */
+#define RAFTGPU_WIRE_NEEDS_LOG 3u  /* reject with log_term > 0: next_probe_index = find_conflict_by_term(..) needs the leader's
+                                      log (raft.rs:1562-1661); the host computes it and submits the 24-byte REJECT + EXT records */
+#define RAFTGPU_WIRE_MALFORMED 4u  /* not a protobuf message, a bad frame, or a group that is not allocated */
+#define RAFTGPU_WIRE_DUP 5u        /* a later frame of a (group, peer) cell that already has one in this batch: cells are
+                                      applied in arrival order, one message per step -- resubmit it with the next batch */
+typedef struct raftgpu_wire_batch {
+    const uint8_t *bytes;    /* the frames, back to back */
+    uint64_t n_bytes;
+    const uint32_t *offsets; /* [n + 1] */
+    uint64_t n;              /* frames */
+    /* 24-byte records that travel with the batch and are applied BEFORE the frames: the leader's own
+     * RAFTGPU_REC_LOCAL events (append_entry / on_persist_entries are calls, not messages) and REJECTs whose
+     * next_probe_index the host has resolved (RAFTGPU_WIRE_NEEDS_LOG of an earlier step).  At most one
+     * record per (group, peer) cell, verified on the GPU like raftgpu_step_begin_packed.  May be NULL / 0. */
+    const raftgpu_append_resp *records;
+    uint64_t n_records;
+} raftgpu_wire_batch;
+/* Raft::term (raft.rs:227) of a group, for the wire path's term test; 0 (the initial value) = the caller filters. */
+int32_t raftgpu_group_set_term(raftgpu_arena *arena, uint32_t group, uint64_t term);
+/* Decode + apply for a batch that already sits in device memory (d_bytes 16-byte aligned, d_offsets [n + 1]);
+ * d_status [n] is required.  Two kernels (scan: classify + first frame of every cell; apply), asynchronous on
+ * `stream`; run raftgpu_recompute afterwards for Raft::maybe_commit. */
+int32_t raftgpu_wire_apply_device(raftgpu_arena *arena, void *stream, const void *d_bytes, uint64_t n_bytes,
+                                  const uint32_t *d_offsets, uint64_t n, uint8_t *d_status);
+/* One step from a wire batch in host memory (pinned -- raftgpu_host_alloc -- for an asynchronous copy): H2D of
+ * bytes + offsets, decode + apply, the recompute pass, D2H of the results and the status bytes.  Same
+ * begin / wait protocol and result accessors as raftgpu_step_begin; the buffers must stay untouched until
+ * raftgpu_step_wait returns.  raftgpu_step_wire_status: the status bytes of the last completed wire step. */
+int32_t raftgpu_step_begin_wire(raftgpu_arena *arena, const raftgpu_wire_batch *batch, uint32_t flags);
+int32_t raftgpu_step_wire_status(raftgpu_arena *arena, const uint8_t **status, uint64_t *n);
 
 /* ---- votes ----------------------------------------- */
 

@@ -40,6 +40,14 @@ int32_t raftgpu_synth_round(const raftgpu_synth_columns *cols, uint64_t seed, ui
                             uint32_t k_peers, raftgpu_append_resp *out, uint64_t max_records,
                             uint64_t *out_n);
 
+/* The records of one round as a transport holds them: follower records -> frames of
+ * serialized eraftpb.Message (u32 header group << 4 | peer_slot, then the protobuf bytes; a REJECT's EXT
+ * becomes reject_hint / request_snapshot), leader-local records -> out_local as they are.  term: [cap] the
+ * groups' terms (NULL = 1).  out_offsets has room for n + 1 entries, out_local for n records. */
+int32_t raftgpu_synth_wire_encode(const raftgpu_append_resp *recs, uint64_t n, const uint64_t *term, uint8_t *out_bytes,
+                                  uint64_t bytes_cap, uint32_t *out_offsets, uint64_t *out_n_frames, uint64_t *out_n_bytes,
+                                  raftgpu_append_resp *out_local, uint64_t *out_n_local);
+
 #ifdef __cplusplus
 }
 #endif

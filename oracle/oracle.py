@@ -81,10 +81,18 @@ class ArenaView(C.Structure):
         [(n, C.POINTER(C.c_uint64)) for n in GROUP_COLUMNS]
 
 
+class WireMessage(C.Structure):
+    """wo_message (wire_oracle.h): the scalar fields of eraftpb.Message."""
+    _fields_ = [("msg_type", C.c_uint32), ("reject", C.c_uint32)] + \
+               [(n, C.c_uint64) for n in ("to", "from_", "term", "log_term", "index", "commit", "commit_term",
+                                          "request_snapshot", "reject_hint", "priority")]
+
+
 def build(force: bool = False) -> str:
     """Compile oracle/libraft_oracle.so with the committed Makefile."""
     if force or not os.path.exists(_LIB_PATH) or \
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "raft_oracle.c")):
+            os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f))
+                                              for f in ("raft_oracle.c", "wire_oracle.c", "raft_oracle.h", "wire_oracle.h")):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _LIB_PATH
 
@@ -155,6 +163,11 @@ def lib() -> C.CDLL:
         L.ro_bench_step.restype = C.c_double
         L.ro_bench_step_fast.argtypes = [pv, C.c_void_p, sz, i32, p64]
         L.ro_bench_step_fast.restype = C.c_double
+        L.wo_decode_message.argtypes = [C.c_void_p, sz, C.POINTER(WireMessage)]
+        L.wo_decode_message.restype = i32
+        L.wo_decode_batch.argtypes = [C.c_void_p, C.c_void_p, sz, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
+        L.wo_decode_batch.restype = None
         _lib = L
     return _lib
 
@@ -329,3 +342,36 @@ def bench_step(c, recs: np.ndarray, n_threads: int, fast: bool = False):
     f = lib().ro_bench_step_fast if fast else lib().ro_bench_step
     secs = f(C.byref(v), recs.ctypes.data, len(recs), n_threads, C.byref(adv))
     return secs, adv.value
+
+
+# --------------------------------------------------------------------------- wire decode
+
+WIRE_OK, WIRE_SKIP_TYPE, WIRE_TERM, WIRE_NEEDS_LOG, WIRE_MALFORMED, WIRE_DUP = range(6)
+
+
+def wire_decode_message(raw: bytes):
+    """wo_decode_message: dict of the scalar fields, or None when the bytes are not a protobuf message."""
+    m = WireMessage()
+    buf = (C.c_uint8 * max(1, len(raw))).from_buffer_copy(raw or b"\0")
+    if not lib().wo_decode_message(buf, len(raw), C.byref(m)):
+        return None
+    return {"msg_type": m.msg_type, "reject": m.reject, "to": m.to, "from": m.from_, "term": m.term,
+            "log_term": m.log_term, "index": m.index, "commit": m.commit, "commit_term": m.commit_term,
+            "request_snapshot": m.request_snapshot, "reject_hint": m.reject_hint, "priority": m.priority}
+
+
+def wire_decode_batch(blob: np.ndarray, offsets: np.ndarray, n_groups: int, group_term: np.ndarray | None = None):
+    """wo_decode_batch -> (status u8[n], records (24-byte dtype)[n], hint u64[n], request_snapshot u64[n])."""
+    n = len(offsets) - 1
+    rec_dtype = np.dtype([("group", "<u4"), ("peer_slot", "u1"), ("flags", "u1"), ("reserved", "<u2"),
+                          ("index", "<u8"), ("commit", "<u8")])
+    status = np.zeros(n, dtype=np.uint8)
+    recs = np.zeros(n, dtype=rec_dtype)
+    hint = np.zeros(n, dtype=np.uint64)
+    snap = np.zeros(n, dtype=np.uint64)
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    gt = None if group_term is None else np.ascontiguousarray(group_term, dtype=np.uint64)
+    lib().wo_decode_batch(blob.ctypes.data, offsets.ctypes.data, n, None if gt is None else gt.ctypes.data, n_groups,
+                          status.ctypes.data, recs.ctypes.data, hint.ctypes.data, snap.ctypes.data)
+    return status, recs, hint, snap

@@ -41,7 +41,8 @@ BULK_SORTED = 0x1
 
 (COL_MATCHED, COL_NEXT_IDX, COL_PEER_COMMITTED, COL_PENDING_SNAPSHOT, COL_PENDING_REQ_SNAPSHOT,
  COL_COMMIT_GROUP_ID, COL_PFLAGS, COL_VOTES, COL_META, COL_COMMITTED, COL_TERM_START,
- COL_LAST_INDEX) = range(12)
+ COL_LAST_INDEX, COL_TERM) = range(13)
+WIRE_OK, WIRE_SKIP_TYPE, WIRE_TERM, WIRE_NEEDS_LOG, WIRE_MALFORMED, WIRE_DUP = range(6)
 
 APPEND_RESP_DTYPE = np.dtype(
     [("group", "<u4"), ("peer_slot", "u1"), ("flags", "u1"), ("reserved", "<u2"),
@@ -67,6 +68,7 @@ COLUMNS = {
     "term_start": (COL_TERM_START, np.uint64, False),
     "last_index": (COL_LAST_INDEX, np.uint64, False),
 }
+# (the term column, COL_TERM, is written separately: only the wire path reads it)
 
 
 class RaftGpuError(RuntimeError):
@@ -107,6 +109,11 @@ class StepResult(C.Structure):
     _fields_ = [("n_records", C.c_uint64), ("n_waves", C.c_uint32), ("n_groups", C.c_uint32),
                 ("n_advanced", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("n_duplicates", C.c_uint64)]
+
+
+class WireBatch(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("offsets", C.c_void_p), ("n", C.c_uint64),
+                ("records", C.c_void_p), ("n_records", C.c_uint64)]
 
 
 class SynthColumns(C.Structure):
@@ -258,6 +265,10 @@ def lib() -> C.CDLL:
             "raftgpu_heartbeat_commits_device": ([vp, vp, u32, u32, vp], i32),
             "raftgpu_step_send_list": ([vp, vp, u64, C.POINTER(u64)], i32),
             "raftgpu_vote_result": ([vp, u32, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)], i32),
+            "raftgpu_group_set_term": ([vp, u32, u64], i32),
+            "raftgpu_wire_apply_device": ([vp, vp, vp, u64, vp, u64, vp], i32),
+            "raftgpu_step_begin_wire": ([vp, C.POINTER(WireBatch), u32], i32),
+            "raftgpu_step_wire_status": ([vp, C.POINTER(vp), C.POINTER(u64)], i32),
             "raftgpu_counters_read": ([vp, C.POINTER(Counters)], i32),
             "raftgpu_synchronize": ([vp], i32),
             "raftgpu_debug_read": ([vp, vp], i32),
@@ -289,6 +300,8 @@ def synth_lib() -> C.CDLL:
         L.raftgpu_synth_init.argtypes, L.raftgpu_synth_init.restype = [C.POINTER(SynthColumns), u64, u32, i32], i32
         L.raftgpu_synth_round.argtypes = [C.POINTER(SynthColumns), u64, u32, u32, vp, u64, C.POINTER(u64)]
         L.raftgpu_synth_round.restype = i32
+        L.raftgpu_synth_wire_encode.argtypes = [vp, u64, vp, vp, u64, vp, C.POINTER(u64), C.POINTER(u64), vp, C.POINTER(u64)]
+        L.raftgpu_synth_wire_encode.restype = i32
         _synth_lib = L
     return _synth_lib
 
@@ -654,6 +667,28 @@ class Arena:
 
     def step_begin(self, flags=0):
         self._ck(self._L.raftgpu_step_begin(self._h, flags), "step_begin")
+
+    # -- wire path
+    def group_set_term(self, g, term):
+        self._ck(self._L.raftgpu_group_set_term(self._h, g, term), "group_set_term")
+
+    def step_begin_wire(self, batch, flags=0):
+        """batch: anything with .bytes (u8 array), .n_bytes, .offsets (u32 array), .n, .records (24-byte records or
+        None), .n_records -- e.g. wire.WireBuffers.  The arrays must stay alive and untouched until step_wait."""
+        wb = WireBatch(batch.bytes.ctypes.data, batch.n_bytes, batch.offsets.ctypes.data, batch.n,
+                       batch.records.ctypes.data if batch.n_records else None, batch.n_records)
+        self._ck(self._L.raftgpu_step_begin_wire(self._h, C.byref(wb), flags), "step_begin_wire")
+
+    def wire_status(self) -> np.ndarray:
+        """Status bytes (RAFTGPU_WIRE_* << 4 | RAFTGPU_RES_*) of the last completed wire step (a view)."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self._L.raftgpu_step_wire_status(self._h, C.byref(p), C.byref(n)), "step_wire_status")
+        if n.value == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,))
+
+    def wire_apply_device(self, d_bytes, n_bytes, d_offsets, n, d_status, stream=None):
+        self._ck(self._L.raftgpu_wire_apply_device(self._h, stream, d_bytes, n_bytes, d_offsets, n, d_status), "wire_apply_device")
 
     def step_wait(self, check: bool = True) -> StepResult:
         r = StepResult()

@@ -76,6 +76,10 @@ struct StagingSet {
     uint32_t *d_tile_off = nullptr;  // [cap / kFTile + 2]: tile index of a tileable compact stream
     uint32_t *d_step_adv = nullptr;  // [0] advanced groups of the step, [1] duplicate records (zero-copy)
     uint32_t *d_touched = nullptr;   // [cap/4] zero-copy steps: one bit per (group, slot)
+    // wire steps (grown on demand): the frames and their offsets on the device
+    uint8_t *d_wire = nullptr;
+    uint64_t d_wire_cap = 0;
+    uint64_t wire_n = 0;             // frames of the wire step this set carried (0 = not a wire step)
     // sync
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
     bool in_flight = false;
@@ -183,6 +187,7 @@ struct raftgpu_arena {
     uint32_t tile_smem = 0;                  // dynamic shared memory for the fused tile kernel
     int tma_stages_cap = 0;                  // RAFTGPU_TMA_STAGES (tuning knob)
     Columns cols{};
+    uint32_t *d_wire_first = nullptr;  // [kSlots][cap] wire steps: first frame of every cell (allocated on first use)
     unsigned long long *d_counters = nullptr;
     void *d_scratch = nullptr;  // 256 B for single-group queries
     void *h_scratch = nullptr;  // pinned mirror
@@ -412,6 +417,7 @@ void free_set(StagingSet &s) {
     cudaFree(s.d_tile_off);
     cudaFree(s.d_step_adv);
     cudaFree(s.d_touched);
+    cudaFree(s.d_wire);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_compute) cudaEventDestroy(s.ev_compute);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -434,6 +440,8 @@ void destroy(raftgpu_arena *a) {
     cudaFree(c.committed);
     cudaFree(c.term_start);
     cudaFree(c.last_index);
+    cudaFree(c.term);
+    cudaFree(a->d_wire_first);
     cudaFree(a->d_counters);
     cudaFree(a->d_scratch);
     cudaFreeHost(a->h_scratch);
@@ -571,6 +579,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
     TRY(dev_alloc(a, &c.committed, a->cap));
     TRY(dev_alloc(a, &c.term_start, a->cap));
     TRY(dev_alloc(a, &c.last_index, a->cap));
+    TRY(dev_alloc(a, &c.term, a->cap));
     TRYC(cudaMemset(c.term_start, 0xff, sizeof(uint64_t) * a->cap));  // RAFTGPU_NO_TERM_START
     TRY(dev_alloc(a, &a->d_counters, kCntCount + 8));  // + 8 diagnostic slots (fused kernel phase cycles)
     TRY(dev_alloc(a, reinterpret_cast<uint8_t **>(&a->d_scratch), 256));
@@ -645,6 +654,7 @@ bool column_desc(raftgpu_arena *a, int32_t col, ColumnDesc *d) {
     case RAFTGPU_COL_COMMITTED: *d = {c.committed, 8, false}; return true;
     case RAFTGPU_COL_TERM_START: *d = {c.term_start, 8, false}; return true;
     case RAFTGPU_COL_LAST_INDEX: *d = {c.last_index, 8, false}; return true;
+    case RAFTGPU_COL_TERM: *d = {c.term, 8, false}; return true;
     default: return false;
     }
 }
@@ -676,6 +686,7 @@ int32_t reclaim_set(raftgpu_arena *a, StagingSet &s) {
         r.overflow_seq.clear();
     }
     s.next_chunk.store(0);
+    s.wire_n = 0;
     s.overflow_depth.clear();
     s.overflow_waves.clear();
     return RAFTGPU_OK;
@@ -690,6 +701,7 @@ extern "C" {
 #include "abi_device.inc"
 #include "abi_staging.inc"
 #include "abi_compact.inc"
+#include "abi_wire.inc"
 #include "abi_results.inc"
 
 }  // extern "C"

@@ -18,6 +18,7 @@ struct Columns {
     uint64_t *committed;
     uint64_t *term_start;
     uint64_t *last_index;
+    uint64_t *term;  // Raft::term, 0 = unknown (wire path only)
 };
 
 enum Counter : int {

@@ -20,5 +20,6 @@ namespace raftgpu {
 #include "k_tile.cuh"
 #include "k_tile_compact.cuh"
 #include "k_control.cuh"
+#include "k_wire.cuh"
 
 }  // namespace raftgpu

@@ -158,4 +158,64 @@ int32_t raftgpu_synth_round(const raftgpu_synth_columns *c, uint64_t seed, uint3
     return RAFTGPU_OK;
 }
 
+
+// One synthetic round as a TRANSPORT would hold it: every follower record becomes a
+// serialized eraftpb.Message (proto/proto/eraftpb.proto:71-92; proto3: zero fields are not written) behind
+// a 4-byte frame header (group << 4 | peer_slot); a REJECT's EXT record folds into reject_hint /
+// request_snapshot.  Leader-local records are not messages and are returned as they are.
+static inline uint8_t *put_varint(uint8_t *p, uint64_t v) {
+    while (v >= 0x80) {
+        *p++ = static_cast<uint8_t>(v) | 0x80;
+        v >>= 7;
+    }
+    *p++ = static_cast<uint8_t>(v);
+    return p;
+}
+static inline uint8_t *put_field(uint8_t *p, uint32_t field, uint64_t v) {
+    if (v == 0) return p;
+    p = put_varint(p, static_cast<uint64_t>(field) << 3);
+    return put_varint(p, v);
+}
+
+int32_t raftgpu_synth_wire_encode(const raftgpu_append_resp *recs, uint64_t n, const uint64_t *term, uint8_t *out_bytes,
+                                  uint64_t bytes_cap, uint32_t *out_offsets, uint64_t *out_n_frames, uint64_t *out_n_bytes,
+                                  raftgpu_append_resp *out_local, uint64_t *out_n_local) {
+    if ((!recs && n) || !out_bytes || !out_offsets || !out_n_frames || !out_n_bytes || !out_local || !out_n_local)
+        return RAFTGPU_ERR_INVALID;
+    uint64_t nf = 0, nl = 0;
+    uint8_t *p = out_bytes;
+    out_offsets[0] = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const raftgpu_append_resp &r = recs[i];
+        if (r.flags & RAFTGPU_REC_EXT) continue;
+        if (r.flags & RAFTGPU_REC_LOCAL) {
+            out_local[nl++] = r;
+            continue;
+        }
+        if (static_cast<uint64_t>(p - out_bytes) + 80 > bytes_cap) return RAFTGPU_ERR_FULL;
+        const bool has_ext = (r.flags & RAFTGPU_REC_REJECT) && i + 1 < n && (recs[i + 1].flags & RAFTGPU_REC_EXT);
+        const uint32_t hdr = (r.group << 4) | (r.peer_slot & 15u);
+        memcpy(p, &hdr, 4);
+        p += 4;
+        p = put_field(p, 1, 4);                                     // msg_type = MsgAppendResponse
+        p = put_field(p, 2, 1);                                     // to: the leader
+        p = put_field(p, 3, static_cast<uint64_t>(r.peer_slot) + 1); // from
+        p = put_field(p, 4, term ? term[r.group] : 1);              // term
+        p = put_field(p, 6, r.index);
+        p = put_field(p, 8, r.commit);
+        if (r.flags & RAFTGPU_REC_REJECT) {
+            p = put_field(p, 10, 1);
+            if (has_ext) {
+                p = put_field(p, 11, recs[i + 1].index);   // reject_hint
+                p = put_field(p, 13, recs[i + 1].commit);  // request_snapshot
+            }
+        }
+        out_offsets[++nf] = static_cast<uint32_t>(p - out_bytes);
+    }
+    *out_n_frames = nf;
+    *out_n_bytes = static_cast<uint64_t>(p - out_bytes);
+    *out_n_local = nl;
+    return RAFTGPU_OK;
+}
+
 }  // extern "C"

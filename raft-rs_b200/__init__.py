@@ -7,3 +7,4 @@ The product is ``libraftgpu.so`` (hand-written sm_100a CUDA behind the C-ABI in
 """
 from .binding import *  # noqa: F401,F403
 from . import binding  # noqa: F401
+from . import wire  # noqa: F401

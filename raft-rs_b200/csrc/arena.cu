@@ -83,7 +83,7 @@ struct StagingSet {
     // sync
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
     bool in_flight = false;
-    bool dirty = false;  // touched[] has bits set
+    std::atomic<bool> dirty{false};  // touched[] has bits set (set by any enqueueing thread)
     uint32_t flags = 0;
     uint64_t wave0_slots = 0;  // staged wave-0 slots (chunks used * kChunk)
     raftgpu_step_result result{};
@@ -675,9 +675,9 @@ void push_overflow(StagingSet &s, uint64_t cell, const PackedRec *pk, int n_pk, 
 // make a finished set reusable for filling
 int32_t reclaim_set(raftgpu_arena *a, StagingSet &s) {
     if (s.in_flight) return RAFTGPU_ERR_BUSY;
-    if (s.dirty) {
+    if (s.dirty.load(std::memory_order_relaxed)) {
         memset(s.touched, 0, a->cap);
-        s.dirty = false;
+        s.dirty.store(false, std::memory_order_relaxed);
     }
     for (auto &r : s.rings) {
         r.chunks.clear();

@@ -12,7 +12,9 @@ namespace raftgpu {
 
 // Where one packer pass writes, what it has produced so far, and the state of the run it is in.
 // A pass may be continued by another call with the same PackState (the run state carries over).
-struct PackState {
+// Cache-line aligned: the staging threads keep one PackState per slice in an array and update it for
+// every block of records -- unaligned neighbours would share lines and ping-pong between cores.
+struct alignas(128) PackState {
     // outputs
     uint32_t *units = nullptr;  // unit positions (and g_base blocks) are relative to this pointer
     uint64_t unit_cap = 0;

@@ -1233,7 +1233,66 @@ def test_vote_tally_batched_vs_oracle():
     arena.tally_votes(0, n, d_out)
     got = np.zeros(arena.cap, dtype=np.uint32)
     arena.d2h(got, d_out)
-    for g in rng.integers(0, n, 3000):
-        gr, rj, r = O.arena_vote_result(c, votes, int(g))
-        assert int(got[g]) == r | (gr << 8) | (rj << 16)
+    for g in range(n):      # every group
+        gr, rj, r = O.arena_vote_result(c, votes, g)
+        assert int(got[g]) == r | (gr << 8) | (rj << 16), g
+    arena.close()
+
+
+def test_concurrent_enqueue_from_eight_threads():
+    """The threading contract of SURVEY 8(b): raftgpu_enqueue_append_resp from several caller threads at once,
+    one ring each, different groups on different threads (raw_node.rs:284 / raft.rs:292-294).  Eight threads
+    enqueue TWO rounds each in small, ragged calls (so every cell gets two records -> two waves); columns,
+    advanced bitmap, commit indexes and the per-ring results against the oracle, three steps in a row."""
+    import threading
+    n, T = 40_000, 8
+    synth = B.Synth(n, 0x7E57, k_peers=5)
+    arena = B.Arena(n, n_rings=T)
+    assert arena.group_alloc_range(n) == 0
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    rng = np.random.default_rng(99)
+    for step in range(3):
+        r1, r2 = synth.next_round().copy(), synth.next_round().copy()
+        per_thread = []
+        for t in range(T):
+            # thread t owns the groups g % T == t; its records keep their arrival order: round 1, then round 2
+            mine = np.concatenate([r1[r1["group"] % T == t], r2[r2["group"] % T == t]])
+            per_thread.append(mine)
+        errors = []
+        start = threading.Barrier(T)
+
+        def work(t):
+            try:
+                recs = per_thread[t]
+                start.wait()
+                i = 0
+                while i < len(recs):
+                    k = int(rng.integers(1, 700))
+                    j = min(len(recs), i + k)
+                    while j < len(recs) and (recs[j]["flags"] & B.REC_EXT):   # never separate a REJECT from its EXT
+                        j += 1
+                    arena.enqueue(recs[i:j], ring=t)      # ctypes releases the GIL: the calls really overlap
+                    i = j
+            except Exception as e:   # noqa: BLE001
+                errors.append(e)
+
+        th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        assert not errors, errors
+        r = arena.step(B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS)
+        assert r.n_waves == 2 and r.n_records == len(r1) + len(r2)
+        want_adv = None
+        for t in range(T):   # cells of different threads are disjoint: any interleaving of the threads is the same
+            want_res = O.arena_apply(ref, per_thread[t], mode=0)
+            assert np.array_equal(arena.record_results(t), want_res), (step, t)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        bm, com = arena.step_results(n)
+        assert r.n_advanced == want_adv and np.array_equal(bm, want_bm[: len(bm)])
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+        assert_columns_equal(arena.read_columns(n), ref, n, f"concurrent enqueue step {step}")
     arena.close()

@@ -136,6 +136,9 @@ typedef struct {
  * prs[self].maybe_update(index); peer_slot is the leader's own slot. */
 #define RAFTGPU_REC_LOCAL 0x02u
 #define RAFTGPU_REC_EXT 0x80u    /* extension record of the preceding REJECT */
+/* A MsgHeartbeatResponse (raft.rs:1777-1819): `commit` = m.commit, `index` unused.  Only
+ * raftgpu_heartbeat_resp[_device] takes such records; the append-response paths ignore them. */
+#define RAFTGPU_REC_HEARTBEAT 0x04u
 
 /* The packed 16-byte wire form of a record (raftgpu_pack_records); layout in DESIGN.md 2. */
 typedef struct {
@@ -595,6 +598,32 @@ int32_t raftgpu_wire_apply_device(raftgpu_arena *arena, void *stream, const void
  * raftgpu_step_wait returns.  raftgpu_step_wire_status: the status bytes of the last completed wire step. */
 int32_t raftgpu_step_begin_wire(raftgpu_arena *arena, const raftgpu_wire_batch *batch, uint32_t flags);
 int32_t raftgpu_step_wire_status(raftgpu_arena *arena, const uint8_t **status, uint64_t *n);
+
+/* ---- heartbeat responses (response side) ---------------- */
+
+/* The tracker part of Raft::handle_heartbeat_response (raft.rs:1777-1804) for a batch of RAFTGPU_REC_HEARTBEAT
+ * records: pr.update_committed(m.commit), recent_active = true, resume(), a full inflights window of a
+ * Replicate peer frees its first entry (INS_FULL clears), and the result byte says whether the reference would
+ * call send_append: RAFTGPU_RES_OK | RAFTGPU_RES_SEND when pr.matched < last_index or a snapshot was requested
+ * (raft.rs:1800-1803); RAFTGPU_RES_NO_PROGRESS for an unknown peer.  The read-index tail (:1806-1818) is not
+ * on this path.  A heartbeat batch is its own pass, ordered by the caller between steps (it reads last_index,
+ * which a step's LOCAL records write): "all heartbeat responses of the tick after its append responses" is
+ * one of the delivery orders raft allows.  One record per (group, peer) cell; a second one is not applied,
+ * gets result 0 and -- in the host form -- makes the call return RAFTGPU_ERR_INVALID.
+ * _device: records and results in device memory, asynchronous on `stream` (d_dup_count nullable, u32, zeroed by
+ * the caller); the host form copies, runs and waits. */
+int32_t raftgpu_heartbeat_resp_device(raftgpu_arena *arena, void *stream, const raftgpu_append_resp *d_records,
+                                      uint64_t n, uint8_t *d_results, uint32_t *d_dup_count);
+int32_t raftgpu_heartbeat_resp(raftgpu_arena *arena, const raftgpu_append_resp *records, uint64_t n, uint8_t *results);
+
+/* Progress::update_state(last) (progress.rs:231-243) for a list of MsgAppends the host has just built -- the
+ * follow-up of every send-list entry (raft.rs:753-760): a Replicate peer's next_idx jumps to last + 1
+ * (optimistic_update; the matching ins.add(last) is the host's Inflights), a Probe peer is paused until its
+ * next response.  entries[i].next_idx carries `last`, the index of the last entry sent to that peer.
+ * results[i] (nullable): 1 done, 0xff where the reference panics (a Snapshot-state peer), RAFTGPU_RES_NO_PROGRESS. */
+int32_t raftgpu_update_state_device(raftgpu_arena *arena, void *stream, const raftgpu_send_entry *d_entries, uint64_t n,
+                                    uint8_t *d_results);
+int32_t raftgpu_update_state(raftgpu_arena *arena, const raftgpu_send_entry *entries, uint64_t n, uint8_t *results);
 
 /* ---- votes ----------------------------------------- */
 

@@ -157,6 +157,10 @@ def lib() -> C.CDLL:
         L.ro_arena_send_list.restype = C.c_uint64
         L.ro_arena_heartbeat_commits.argtypes = [pv, C.c_uint32, C.c_uint32, C.c_void_p]
         L.ro_arena_heartbeat_commits.restype = None
+        L.ro_arena_apply_heartbeat.argtypes = [pv, C.c_void_p, sz, C.c_void_p]
+        L.ro_arena_apply_heartbeat.restype = None
+        L.ro_arena_update_state.argtypes = [pv, C.c_void_p, sz, C.c_void_p]
+        L.ro_arena_update_state.restype = None
         L.ro_bench_recompute.argtypes = [pv, i32, i32, p64]
         L.ro_bench_recompute.restype = C.c_double
         L.ro_bench_step.argtypes = [pv, C.c_void_p, sz, i32, p64]
@@ -318,6 +322,24 @@ def arena_send_list(c, adv_bitmap=None, first: int = 0, n: int | None = None):
     got = lib().ro_arena_send_list(C.byref(v), first, n, None if bm is None else bm.ctypes.data, out.ctypes.data, need)
     assert got == need
     return out
+
+
+def arena_apply_heartbeat(c, recs: np.ndarray) -> np.ndarray:
+    """handle_heartbeat_response (raft.rs:1777-1819) for every REC_HEARTBEAT record, in order."""
+    assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous
+    res = np.zeros(len(recs), dtype=np.uint8)
+    v = view(c)
+    lib().ro_arena_apply_heartbeat(C.byref(v), recs.ctypes.data, len(recs), res.ctypes.data)
+    return res
+
+
+def arena_update_state(c, entries: np.ndarray) -> np.ndarray:
+    """Progress::update_state(last) for every {group, peer_slot, next_idx = last} entry (16-byte send entries)."""
+    assert entries.dtype.itemsize == 16 and entries.flags.c_contiguous
+    res = np.zeros(len(entries), dtype=np.uint8)
+    v = view(c)
+    lib().ro_arena_update_state(C.byref(v), entries.ctypes.data, len(entries), res.ctypes.data)
+    return res
 
 
 def arena_heartbeat_commits(c, first: int = 0, n: int | None = None) -> np.ndarray:

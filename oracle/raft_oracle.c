@@ -539,6 +539,50 @@ void ro_arena_apply(ro_arena_view *a, const ro_append_resp *recs, size_t n, int 
     }
 }
 
+/* raft.rs:1777-1819 */
+uint8_t ro_arena_handle_heartbeat_response(ro_arena_view *a, const ro_append_resp *rec) {
+    uint32_t g = rec->group, slot = rec->peer_slot;
+    uint32_t meta = a->meta[g];
+    uint32_t present = RO_META_IN(meta) | RO_META_OUT(meta) | RO_META_LEARN(meta);
+    if (slot >= RO_SLOTS || !(present & (1u << slot))) return RO_RES_NO_PROGRESS; /* :1779-1789 */
+    ro_progress pr;
+    load_progress(a, slot, g, &pr);
+    ro_progress_update_committed(&pr, rec->commit); /* :1791 */
+    pr.recent_active = 1;                           /* :1792 */
+    ro_progress_resume(&pr);                        /* :1793 */
+    if (pr.state == RO_STATE_REPLICATE && pr.ins_full) pr.ins_full = 0; /* :1796-1798 free_first_one */
+    uint8_t res = RO_RES_OK;
+    if (pr.matched < a->last_index[g] || pr.pending_request_snapshot != RO_INVALID_INDEX) res |= RO_RES_SEND; /* :1800-1803 */
+    store_progress(a, slot, g, &pr);
+    return res;
+}
+
+void ro_arena_apply_heartbeat(ro_arena_view *a, const ro_append_resp *recs, size_t n, uint8_t *results) {
+    for (size_t i = 0; i < n; i++) {
+        uint8_t res = (recs[i].flags & RO_REC_HEARTBEAT) ? ro_arena_handle_heartbeat_response(a, &recs[i]) : 0;
+        if (results) results[i] = res;
+    }
+}
+
+/* progress.rs:231-243 over a send list */
+void ro_arena_update_state(ro_arena_view *a, const ro_send_entry *e, size_t n, uint8_t *results) {
+    for (size_t i = 0; i < n; i++) {
+        uint32_t g = e[i].group, slot = e[i].peer_slot;
+        uint32_t meta = a->meta[g];
+        uint32_t present = RO_META_IN(meta) | RO_META_OUT(meta) | RO_META_LEARN(meta);
+        uint8_t res;
+        if (slot >= RO_SLOTS || !(present & (1u << slot))) {
+            res = RO_RES_NO_PROGRESS;
+        } else {
+            ro_progress pr;
+            load_progress(a, slot, g, &pr);
+            res = ro_progress_update_state(&pr, e[i].next_idx) == 0 ? 1 : 0xff;
+            store_progress(a, slot, g, &pr);
+        }
+        if (results) results[i] = res;
+    }
+}
+
 uint64_t ro_arena_recompute(ro_arena_view *a, uint32_t first, uint32_t n, uint32_t *adv_bitmap,
                             uint64_t *mci_out, uint8_t *gc_out) {
     uint64_t advanced = 0;

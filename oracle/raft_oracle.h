@@ -256,6 +256,22 @@ uint64_t ro_arena_send_list(const ro_arena_view *a, uint32_t first, uint32_t n, 
  * out[slot * n + (g - first)]. */
 void ro_arena_heartbeat_commits(const ro_arena_view *a, uint32_t first, uint32_t n, uint64_t *out);
 
+/* handle_heartbeat_response for ONE record (raft.rs:1777-1819, the tracker part: the read-index tail
+ * :1806-1818 is outside the path): rec->commit = m.commit.  update_committed, recent_active = true,
+ * resume(); a Replicate peer whose inflights window is full frees its first entry (:1797-1799 -- a full
+ * window that loses an entry is no longer full, so the carried ins_full bit clears); RO_RES_SEND when the
+ * reference calls send_append: pr.matched < last_index || pending_request_snapshot != INVALID_INDEX
+ * (:1801-1804).  RO_RES_OK marks a record that found its Progress. */
+#define RO_REC_HEARTBEAT 0x04u
+uint8_t ro_arena_handle_heartbeat_response(ro_arena_view *a, const ro_append_resp *rec);
+void ro_arena_apply_heartbeat(ro_arena_view *a, const ro_append_resp *recs, size_t n, uint8_t *results);
+
+/* Progress::update_state(last) (progress.rs:231-243) for every entry {group, peer_slot, next_idx = last}:
+ * what send_append does after it built a MsgAppend (raft.rs:753-760): Replicate -> optimistic_update(last)
+ * (+ ins.add(last), host side), Probe -> pause().  results[i]: 1 done, 0xff where the reference panics
+ * (Snapshot state), RO_RES_NO_PROGRESS for an unknown peer. */
+void ro_arena_update_state(ro_arena_view *a, const ro_send_entry *entries, size_t n, uint8_t *results);
+
 /* ---- CPU baseline timing (bench.py cpu_baseline / --impl reference) ----- */
 
 /* Runs `iters` recompute passes over the whole arena with n_threads pthreads

@@ -31,7 +31,7 @@ STATE_PROBE, STATE_REPLICATE, STATE_SNAPSHOT = 0, 1, 2
 VOTE_PENDING, VOTE_LOST, VOTE_WON = 0, 1, 2
 PF_STATE_MASK, PF_PAUSED, PF_RECENT_ACTIVE, PF_INS_FULL = 0x03, 0x04, 0x08, 0x10
 META_HAS_SELF, META_GROUP_COMMIT = 0x08000000, 0x10000000
-REC_REJECT, REC_LOCAL, REC_EXT = 0x01, 0x02, 0x80
+REC_REJECT, REC_LOCAL, REC_HEARTBEAT, REC_EXT = 0x01, 0x02, 0x04, 0x80
 RES_OK, RES_OLD_PAUSED, RES_NO_PROGRESS, RES_SEND = 0x01, 0x02, 0x04, 0x08
 STEP_READ_COMMITTED, STEP_READ_RESULTS = 0x1, 0x2
 BULK_SORTED = 0x1
@@ -266,6 +266,10 @@ def lib() -> C.CDLL:
             "raftgpu_step_send_list": ([vp, vp, u64, C.POINTER(u64)], i32),
             "raftgpu_vote_result": ([vp, u32, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)], i32),
             "raftgpu_group_set_term": ([vp, u32, u64], i32),
+            "raftgpu_heartbeat_resp_device": ([vp, vp, vp, u64, vp, vp], i32),
+            "raftgpu_heartbeat_resp": ([vp, vp, u64, vp], i32),
+            "raftgpu_update_state_device": ([vp, vp, vp, u64, vp], i32),
+            "raftgpu_update_state": ([vp, vp, u64, vp], i32),
             "raftgpu_wire_apply_device": ([vp, vp, vp, u64, vp, u64, vp], i32),
             "raftgpu_step_begin_wire": ([vp, C.POINTER(WireBatch), u32], i32),
             "raftgpu_step_wire_status": ([vp, C.POINTER(vp), C.POINTER(u64)], i32),
@@ -667,6 +671,21 @@ class Arena:
 
     def step_begin(self, flags=0):
         self._ck(self._L.raftgpu_step_begin(self._h, flags), "step_begin")
+
+    # -- heartbeat responses / update_state
+    def heartbeat_resp(self, recs: np.ndarray) -> np.ndarray:
+        """raftgpu_heartbeat_resp: REC_HEARTBEAT records -> result bytes (RES_OK | RES_SEND | RES_NO_PROGRESS)."""
+        assert recs.dtype == APPEND_RESP_DTYPE and recs.flags.c_contiguous
+        res = np.zeros(len(recs), dtype=np.uint8)
+        self._ck(self._L.raftgpu_heartbeat_resp(self._h, recs.ctypes.data, len(recs), res.ctypes.data), "heartbeat_resp")
+        return res
+
+    def update_state(self, entries: np.ndarray) -> np.ndarray:
+        """raftgpu_update_state: send entries with next_idx = last -> result bytes."""
+        assert entries.dtype == SEND_ENTRY_DTYPE and entries.flags.c_contiguous
+        res = np.zeros(len(entries), dtype=np.uint8)
+        self._ck(self._L.raftgpu_update_state(self._h, entries.ctypes.data, len(entries), res.ctypes.data), "update_state")
+        return res
 
     # -- wire path (SURVEY 8(f4))
     def group_set_term(self, g, term):

@@ -514,7 +514,7 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
                               static_cast<int>(a->tma_smem)));
     TRYC(cudaFuncSetAttribute(recompute_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               static_cast<int>(a->tma_smem)));
-    a->tile_smem = 227u * 1024u - 512u;  // 227 KB per CTA minus the kernels' static shared memory
+    a->tile_smem = 227u * 1024u - 5u * 1024u;  // 227 KB per CTA minus the kernels' static shared memory (barriers, deferred lists)
 #define RAFTGPU_TILE_ATTR(CT, NG)                                                                             \
     TRYC(cudaFuncSetAttribute(step_tile_kernel<false, CT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                               static_cast<int>(a->tile_smem)));                                              \
@@ -689,6 +689,25 @@ int32_t reclaim_set(raftgpu_arena *a, StagingSet &s) {
     s.wire_n = 0;
     s.overflow_depth.clear();
     s.overflow_waves.clear();
+    return RAFTGPU_OK;
+}
+
+// host batch -> device scratch (the fill set's record staging, idle between steps) -> kernel -> results
+template <typename T, typename F>
+int32_t host_batch_op(raftgpu_arena *a, const T *in, uint64_t n, uint8_t *results, F &&launch, uint32_t *out_dups) {
+    StagingSet &s = a->sets[a->fill];
+    if (s.in_flight || s.next_chunk.load() != 0) return fail(a, RAFTGPU_ERR_BUSY, "records are staged for a step: step first");
+    const uint64_t room = (static_cast<uint64_t>(a->n_chunks) * kChunk + a->overflow_records) * sizeof(PackedRec);
+    if (n * sizeof(T) > room || n > 4 * (room / sizeof(PackedRec))) return fail(a, RAFTGPU_ERR_FULL, "batch larger than the staging buffer");
+    CK(a, cudaSetDevice(a->device));
+    CK(a, cudaMemcpyAsync(s.d_recs, in, n * sizeof(T), cudaMemcpyHostToDevice, a->s_compute));
+    CK(a, cudaMemsetAsync(s.d_step_adv, 0, 8, a->s_compute));
+    const int32_t rc = launch(reinterpret_cast<const T *>(s.d_recs), s.d_results, s.d_step_adv + 1);
+    if (rc != RAFTGPU_OK) return rc;
+    if (results) CK(a, cudaMemcpyAsync(results, s.d_results, n, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaMemcpyAsync(s.h_step_adv, s.d_step_adv, 8, cudaMemcpyDeviceToHost, a->s_compute));
+    CK(a, cudaStreamSynchronize(a->s_compute));
+    if (out_dups) *out_dups = s.h_step_adv[1];
     return RAFTGPU_OK;
 }
 

@@ -97,6 +97,86 @@ heartbeat_commit_kernel(Columns c, uint32_t first, uint32_t n, uint64_t *__restr
 }
 
 // ---------------------------------------------------------------------------
+// heartbeat_resp_kernel: the tracker part of Raft::handle_heartbeat_response (raft.rs:1777-1804), one
+// thread per RAFTGPU_REC_HEARTBEAT record (commit = m.commit): update_committed, recent_active = true,
+// resume(); a Replicate peer whose inflights window is full frees its first entry (:1796-1798 -- the
+// window is then no longer full: INS_FULL clears); RAFTGPU_RES_SEND where the reference calls send_append:
+// pr.matched < last_index || pending_request_snapshot != INVALID_INDEX (:1800-1803).  A scatter pass by
+// nature (the records name the cells); one record per cell, verified through `touched` like the other
+// zero-copy paths (a second record for a cell is not applied and bumps *dup_count).
+__global__ void __launch_bounds__(256)
+heartbeat_resp_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, uint64_t n, uint8_t *__restrict__ results,
+                      uint32_t *__restrict__ touched, uint32_t *__restrict__ dup_count) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t *p = reinterpret_cast<const uint64_t *>(recs + i);
+        const uint64_t w0 = p[0], commit = p[2];
+        const uint32_t g = static_cast<uint32_t>(w0), slot = static_cast<uint32_t>(w0 >> 32) & 0xffu;
+        const uint32_t rflags = static_cast<uint32_t>(w0 >> 40) & 0xffu;
+        uint32_t res = 0;
+        if (rflags & RAFTGPU_REC_HEARTBEAT) {
+            const bool in_range = g < c.cap && slot < kSlots;
+            const uint32_t meta = in_range ? c.meta[g] : 0u;
+            const uint32_t present = RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
+            if (!in_range || !((present >> slot) & 1u)) {
+                res = RAFTGPU_RES_NO_PROGRESS;  // raft.rs:1779-1789
+            } else {
+                const uint32_t bit = 1u << (8 * (g & 3u) + slot);
+                if (touched && (atomicOr(&touched[g >> 2], bit) & bit)) {
+                    if (dup_count) atomicAdd(dup_count, 1u);
+                } else {
+                    const size_t cell = static_cast<size_t>(slot) * c.cap + g;
+                    const uint32_t f0 = c.pflags[cell];
+                    uint32_t f = (f0 | RAFTGPU_PF_RECENT_ACTIVE) & ~RAFTGPU_PF_PAUSED;          // :1792-1793
+                    if ((f0 & RAFTGPU_PF_STATE_MASK) == RAFTGPU_STATE_REPLICATE) f &= ~RAFTGPU_PF_INS_FULL;  // :1796-1798
+                    if (commit > c.peer_committed[cell]) c.peer_committed[cell] = commit;      // :1791
+                    if (f != f0) c.pflags[cell] = static_cast<uint8_t>(f);
+                    res = RAFTGPU_RES_OK;
+                    if (c.matched[cell] < c.last_index[g] || c.pending_req_snapshot[cell] != RAFTGPU_INVALID_INDEX)
+                        res |= RAFTGPU_RES_SEND;                                                // :1800-1803
+                }
+            }
+        }
+        if (results) results[i] = static_cast<uint8_t>(res);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// update_state_kernel: Progress::update_state(last) (progress.rs:231-243) for a list of sends, i.e. what
+// send_append does once it has built a MsgAppend for the entry (raft.rs:753-760): Replicate ->
+// optimistic_update(last): next_idx = last + 1 (the ins.add(last) that goes with it is the host's Inflights);
+// Probe -> pause().  Without it a probing peer is never paused and every later send list names it again.
+// entries: raftgpu_send_entry with next_idx = `last` (the index of the last entry sent).  results[i]: 1 done,
+// 0xff where the reference panics (Snapshot state), RAFTGPU_RES_NO_PROGRESS for an unknown peer.
+__global__ void __launch_bounds__(256)
+update_state_kernel(Columns c, const raftgpu_send_entry *__restrict__ e, uint64_t n, uint8_t *__restrict__ results) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t g = e[i].group, slot = e[i].peer_slot;
+        const uint64_t last = e[i].next_idx;
+        uint32_t res;
+        const bool in_range = g < c.cap && slot < kSlots;
+        const uint32_t meta = in_range ? c.meta[g] : 0u;
+        const uint32_t present = RAFTGPU_META_IN(meta) | RAFTGPU_META_OUT(meta) | RAFTGPU_META_LEARN(meta);
+        if (!in_range || !((present >> slot) & 1u)) {
+            res = RAFTGPU_RES_NO_PROGRESS;
+        } else {
+            const size_t cell = static_cast<size_t>(slot) * c.cap + g;
+            const uint32_t f0 = c.pflags[cell];
+            const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
+            res = 1;
+            if (state == RAFTGPU_STATE_REPLICATE)
+                c.next_idx[cell] = last + 1;                                      // :233-236 optimistic_update
+            else if (state == RAFTGPU_STATE_PROBE)
+                c.pflags[cell] = static_cast<uint8_t>(f0 | RAFTGPU_PF_PAUSED);    // :237 pause()
+            else
+                res = 0xffu;                                                      // :238-241 panic!
+        }
+        if (results) results[i] = static_cast<uint8_t>(res);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // tally_kernel: ProgressTracker::tally_votes (tracker.rs:313-340) per group:
 // granted / rejected over voters, JointConfig::vote_result (joint.rs:56-67) over
 // MajorityConfig::vote_result (majority.rs:130-154).

@@ -28,6 +28,7 @@ constexpr int kFMaxStages = 8;
 // 258 u64 (= 2064 B, still 16-byte aligned for TMA) shifts consecutive rows by 4 banks.
 constexpr uint32_t kFRow64 = (kFTile + 2) * 8;   // bytes per u64 row
 constexpr uint32_t kFRow8 = kFTile + 16;         // bytes per u8 (pflags) row
+constexpr uint32_t kFDefer = 32;                 // deferred (rare-path) records per warp per tile; more are handled inline
 
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
@@ -67,6 +68,8 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
     __shared__ __align__(8) uint64_t full_bar[kFMaxStages];   // loads landed            (load warp -> consumers)
     __shared__ __align__(8) uint64_t done_bar[kFMaxStages];   // rows final in smem      (consumers -> store warp)
     __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];  // rows read by the stores (store warp -> load warp)
+    __shared__ uint32_t s_defer[32][kFDefer];                 // per warp: tile-relative indexes of its rare-path records
+    __shared__ uint32_t s_ndefer[32];
 
     const uint32_t hint = kSimple5 ? 0x1fu : (a.hint & 0xffu);
     const uint32_t H = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint));
@@ -222,118 +225,84 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             // Records come from the stage when they were staged (rec_cap > 0), else straight from HBM /
             // L2 (rec_cap == 0: the stage holds rows only, which buys a fifth stage; the records of a
             // tile were prefetched into L2 while the previous tile was processed, and the loop fetches
-            // record k + kCT while it works on record k).
+            // the records two iterations ahead).
             auto rec_at = [&](uint32_t j) -> ulonglong2 {
                 if (j < staged) return reinterpret_cast<const ulonglong2 *>(s_recs)[j];
                 if (j < cnt) return g_recs[j];
                 return make_ulonglong2(kPkExt, 0ull);
             };
-            if (staged != 0) q_next = rec_at(tid);
-            for (uint32_t k = tid; k < cnt; k += kCT) {
-                // Fast path: a record for a staged cell of a peer in Replicate or Probe state -- accept,
-                // leader-local, or a rejection without a snapshot request -- straight on the packed
-                // words and the shared-memory cell.  Statement for statement the branches of apply_one
-                // (raft.rs:1674-1743, 1010-1014; progress.rs:95-114, 138-206); everything else (Snapshot
-                // state, request_snapshot, WIDE commits, learners) takes the general path below.
-                const ulonglong2 q = q_next;
-                q_next = rec_at(k + kCT);
-                const bool in_smem = true;
-                if (in_smem) {
-                    const uint64_t w0 = q.x;
-                    if (w0 & kPkExt) {
-                        if (a.results) a.results[rbeg + k] = 0;
-                        continue;
-                    }
-                    const uint32_t slot = static_cast<uint32_t>(w0 >> 32) & 7u;
-                    const uint32_t g = static_cast<uint32_t>(w0);
-                    const uint32_t gl = g - g0;
-                    if (!(w0 & kPkWide) && gl < ng && ((hint >> slot) & 1u)) {
-                        const uint32_t r = kSimple5 ? slot : static_cast<uint32_t>(__popc(hint & ((1u << slot) - 1u)));
-                        const uint32_t ci = r * R64 + gl;
-                        const uint32_t f0 = s_flags[r * kFRow8 + gl];
-                        const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
-                        const bool present = kSimple5 || (((RAFTGPU_META_IN(s_meta[gl]) | RAFTGPU_META_OUT(s_meta[gl]) |
-                                                            RAFTGPU_META_LEARN(s_meta[gl])) >> slot) & 1u);
-                        const bool simple = present && state != RAFTGPU_STATE_SNAPSHOT;
-                        if (simple && !(w0 & kPkReject)) {
-                            // accept / leader-local: maybe_update (progress.rs:138-150), shared by the accept path
-                            // (raft.rs:1674-1677, 1724-1730) and the leader-local path (raft.rs:974-991, 1010-1014);
-                            // only an accept looks at is_paused() and may move a probing peer to Replicate.
-                            // Written as straight-line selects: this is ~98 % of all records.
+            // The main loop is STRAIGHT-LINE code for the records that make up ~98 % of the traffic -- an accept
+            // or a leader-local record for a staged cell of a peer in Replicate or Probe state: maybe_update
+            // (progress.rs:138-150), shared by the accept path (raft.rs:1674-1677, 1724-1730) and the leader-local
+            // path (raft.rs:974-991, 1010-1014); only an accept looks at is_paused() and may move a probing peer
+            // to Replicate.  Every load is issued unconditionally on a clamped address and every store is
+            // predicated, so two records per thread are in flight per iteration and nothing diverges.  Whatever
+            // else turns up (a rejection, a WIDE commit, a Snapshot-state peer, a learner outside the hint, a
+            // record that is not this tile's) is put on the WARP's deferred list and handled after the loop with
+            // all the warp's lanes working on such records at once, instead of one lane at a time in the loop:
+            // a wave has at most one record per cell, so the order between the two passes does not matter.
+            uint32_t *my_defer = s_defer[warp];
+            if (lane == 0) s_ndefer[warp] = 0;
+            __syncwarp();
+            // A record the straight-line form does not take: a rejection without a snapshot request on a staged
+            // Replicate / Probe cell directly (maybe_decr_to, progress.rs:168-206), the rest through apply_one.
+            auto slow_record = [&](const uint32_t k) {
+                const ulonglong2 q = rec_at(k);
+                const uint64_t w0 = q.x;
+                const uint32_t slot = static_cast<uint32_t>(w0 >> 32) & 7u;
+                const uint32_t g = static_cast<uint32_t>(w0);
+                const uint32_t gl = g - g0;
+                if (!(w0 & kPkWide) && (w0 & kPkReject) && gl < ng && ((hint >> slot) & 1u)) {
+                    const uint32_t r = kSimple5 ? slot : static_cast<uint32_t>(__popc(hint & ((1u << slot) - 1u)));
+                    const uint32_t ci = r * R64 + gl;
+                    const uint32_t f0 = s_flags[r * kFRow8 + gl];
+                    const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
+                    const bool present = kSimple5 || (((RAFTGPU_META_IN(s_meta[gl]) | RAFTGPU_META_OUT(s_meta[gl]) |
+                                                        RAFTGPU_META_LEARN(s_meta[gl])) >> slot) & 1u);
+                    if (present && state != RAFTGPU_STATE_SNAPSHOT) {
+                        // its EXT payloads: [kind 1 hint] [kind 2 snapshot request]
+                        uint64_t hint_idx = 0;
+                        bool snapshot_req = false;
+                        const ulonglong2 e1 = rec_at(k + 1);   // (past the end: a padding EXT of kind 0)
+                        const ulonglong2 e2 = rec_at(k + 2);
+                        const bool x1 = (e1.x & kPkExt) != 0, x2 = x1 && (e2.x & kPkExt) != 0;
+                        if (x1 && (e1.x >> 40) == 1) hint_idx = e1.y;
+                        if ((x1 && (e1.x >> 40) == 2) || (x2 && (e2.x >> 40) == 2)) snapshot_req = true;
+                        if (!snapshot_req) {
                             const uint64_t index = q.y;
                             const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
-                            const bool is_local = (w0 & kPkLocal) != 0;
-                            const uint64_t m = s_matched[ci], nx = s_next[ci], pcv = s_pc[ci];
+                            uint64_t m = s_matched[ci], nx = s_next[ci];
+                            const uint64_t nx0 = nx;
+                            uint32_t f = f0 | RAFTGPU_PF_RECENT_ACTIVE, res = 0;         // raft.rs:1674
                             local[0]++;
-                            if (is_local && delta != kPkNoCommit) s_li[gl] = index + delta;   // raft.rs:974-991
+                            local[2]++;
                             const uint64_t commit = index - delta;
-                            if (!is_local && commit > pcv) s_pc[ci] = commit;                 // raft.rs:1677
-                            const bool probe = state == RAFTGPU_STATE_PROBE;
-                            const bool need = m < index;
-                            const bool old_paused = !is_local && (f0 & (probe ? RAFTGPU_PF_PAUSED : RAFTGPU_PF_INS_FULL)) != 0;
-                            const bool trans = need && !is_local && probe;                    // raft.rs:1730 become_replicate
-                            uint32_t f = is_local ? f0 : (f0 | RAFTGPU_PF_RECENT_ACTIVE);     // raft.rs:1674
-                            if (need) f &= ~RAFTGPU_PF_PAUSED;
-                            if (trans)
-                                f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_REPLICATE;
-                            uint64_t nnx = nx < index + 1 ? index + 1 : nx;
-                            if (trans) {
-                                nnx = index + 1;                                              // next_idx = matched + 1
-                                c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
+                            if (commit > s_pc[ci]) s_pc[ci] = commit;                   // raft.rs:1677
+                            bool ok;
+                            if (state == RAFTGPU_STATE_REPLICATE) {
+                                ok = index > m;                                          // :173-177 stale otherwise
+                                if (ok) nx = m + 1;                                      // :178-179
+                            } else if (nx == 0 || nx - 1 != index) {
+                                ok = false;                                              // :188-192 stale
+                            } else {
+                                nx = umin64(index, hint_idx + 1);                        // :195-199
+                                if (nx < 1) nx = 1;
+                                f &= ~RAFTGPU_PF_PAUSED;                                 // :204
+                                ok = true;
                             }
-                            local[1] += need ? 1u : 0u;
-                            if (need) s_matched[ci] = index;
-                            if (nnx != nx) s_next[ci] = nnx;
+                            if (ok) {
+                                local[3]++;
+                                res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
+                                if (state == RAFTGPU_STATE_REPLICATE) {                  // raft.rs:1716-1718 become_probe
+                                    f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_PROBE;
+                                    c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
+                                    nx = m + 1;
+                                }
+                            }
+                            if (nx != nx0) s_next[ci] = nx;
                             if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
-                            if (a.results)
-                                a.results[rbeg + k] = static_cast<uint8_t>(need ? (RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u)) : 0u);
-                            continue;
-                        }
-                        if (simple) {  // a rejection: look at its EXT payloads: [kind 1 hint] [kind 2 snapshot request]
-                            uint64_t hint_idx = 0;
-                            bool snapshot_req = false;
-                            const ulonglong2 e1 = rec_at(k + 1);   // (past the end: a padding EXT of kind 0)
-                            const ulonglong2 e2 = rec_at(k + 2);
-                            const bool x1 = (e1.x & kPkExt) != 0, x2 = x1 && (e2.x & kPkExt) != 0;
-                            if (x1 && (e1.x >> 40) == 1) hint_idx = e1.y;
-                            if ((x1 && (e1.x >> 40) == 2) || (x2 && (e2.x >> 40) == 2)) snapshot_req = true;
-                            if (!snapshot_req) {
-                                // maybe_decr_to without a snapshot request (progress.rs:168-206)
-                                const uint64_t index = q.y;
-                                const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
-                                uint64_t m = s_matched[ci], nx = s_next[ci];
-                                const uint64_t nx0 = nx;
-                                uint32_t f = f0 | RAFTGPU_PF_RECENT_ACTIVE, res = 0;         // raft.rs:1674
-                                local[0]++;
-                                local[2]++;
-                                const uint64_t commit = index - delta;
-                                if (commit > s_pc[ci]) s_pc[ci] = commit;                   // raft.rs:1677
-                                bool ok;
-                                if (state == RAFTGPU_STATE_REPLICATE) {
-                                    ok = index > m;                                          // :173-177 stale otherwise
-                                    if (ok) nx = m + 1;                                      // :178-179
-                                } else if (nx == 0 || nx - 1 != index) {
-                                    ok = false;                                              // :188-192 stale
-                                } else {
-                                    nx = umin64(index, hint_idx + 1);                        // :195-199
-                                    if (nx < 1) nx = 1;
-                                    f &= ~RAFTGPU_PF_PAUSED;                                 // :204
-                                    ok = true;
-                                }
-                                if (ok) {
-                                    local[3]++;
-                                    res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
-                                    if (state == RAFTGPU_STATE_REPLICATE) {                  // raft.rs:1716-1718 become_probe
-                                        f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_PROBE;
-                                        c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
-                                        nx = m + 1;
-                                    }
-                                }
-                                if (nx != nx0) s_next[ci] = nx;
-                                if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
-                                if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
-                                continue;
-                            }
+                            if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
+                            return;
                         }
                     }
                 }
@@ -344,32 +313,100 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                 const RecRegs rec = load_rec<true>(base, k, nn);
                 uint32_t res = 0;
                 if (!((rec.w0 >> 40) & RAFTGPU_REC_EXT)) {
-                    const uint32_t g = static_cast<uint32_t>(rec.w0), slot = static_cast<uint32_t>(rec.w0 >> 32) & 0xffu;
-                    const uint32_t gl = g - g0;
-                    if (gl >= ng) {  // not this tile's group: the batch is not in group order / bad index
+                    const uint32_t g2 = static_cast<uint32_t>(rec.w0), slot2 = static_cast<uint32_t>(rec.w0 >> 32) & 0xffu;
+                    const uint32_t gl2 = g2 - g0;
+                    if (gl2 >= ng) {  // not this tile's group: the batch is not in group order / bad index
                         local[0]++;
                         local[4]++;
                         res = RAFTGPU_RES_NO_PROGRESS;
-                    } else if (slot < kSlots && ((hint >> slot) & 1u)) {
-                        const uint32_t r = __popc(hint & ((1u << slot) - 1u));
+                    } else if (slot2 < kSlots && ((hint >> slot2) & 1u)) {
+                        const uint32_t r = __popc(hint & ((1u << slot2) - 1u));
                         CellRegs cd;
-                        cd.meta = s_meta[gl];
-                        cd.matched = s_matched[r * R64 + gl];
-                        cd.next_idx = s_next[r * R64 + gl];
-                        cd.flags = s_flags[r * kFRow8 + gl];
-                        cd.peer_committed = s_pc[r * R64 + gl];
-                        const CellPtrs sp{&s_matched[r * R64 + gl], &s_next[r * R64 + gl], &s_pc[r * R64 + gl], &s_li[gl],
-                                          &s_flags[r * kFRow8 + gl]};
+                        cd.meta = s_meta[gl2];
+                        cd.matched = s_matched[r * R64 + gl2];
+                        cd.next_idx = s_next[r * R64 + gl2];
+                        cd.flags = s_flags[r * kFRow8 + gl2];
+                        cd.peer_committed = s_pc[r * R64 + gl2];
+                        const CellPtrs sp{&s_matched[r * R64 + gl2], &s_next[r * R64 + gl2], &s_pc[r * R64 + gl2], &s_li[gl2],
+                                          &s_flags[r * kFRow8 + gl2]};
                         res = apply_one<1>(c, base, nn, k, rec, cd, sp, local);
                     } else {  // a peer slot outside the hint (a learner): its cell lives in HBM
                         CellRegs cd = load_cell(c, rec);
-                        cd.meta = s_meta[gl];
+                        cd.meta = s_meta[gl2];
                         CellPtrs gp = global_cell_ptrs(c, rec);
-                        gp.last_index = &s_li[gl];
+                        gp.last_index = &s_li[gl2];
                         res = apply_one<1>(c, base, nn, k, rec, cd, gp, local);
                     }
                 }
                 if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
+            };
+            auto fast_record = [&](const ulonglong2 q, const uint32_t k) {
+                const uint64_t w0 = q.x;
+                const bool is_ext = (w0 & kPkExt) != 0;
+                const uint32_t slot = static_cast<uint32_t>(w0 >> 32) & 7u;
+                const uint32_t g = static_cast<uint32_t>(w0);
+                const uint32_t gl = g - g0;
+                const bool cell_ok = gl < ng && ((hint >> slot) & 1u);
+                const uint32_t gl_s = cell_ok ? gl : 0u;
+                const uint32_t r = cell_ok ? (kSimple5 ? slot : static_cast<uint32_t>(__popc(hint & ((1u << slot) - 1u)))) : 0u;
+                const uint32_t ci = r * R64 + gl_s, fi = r * kFRow8 + gl_s;
+                const uint32_t f0 = s_flags[fi];
+                const uint64_t m = s_matched[ci], nx = s_next[ci], pcv = s_pc[ci];
+                const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
+                bool present = true;
+                if constexpr (!kSimple5) {
+                    const uint32_t mt = s_meta[gl_s];
+                    present = ((RAFTGPU_META_IN(mt) | RAFTGPU_META_OUT(mt) | RAFTGPU_META_LEARN(mt)) >> slot) & 1u;
+                }
+                const bool fast = !(w0 & (kPkExt | kPkWide | kPkReject)) && cell_ok && present && state != RAFTGPU_STATE_SNAPSHOT;
+                const uint64_t index = q.y;
+                const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
+                const bool is_local = (w0 & kPkLocal) != 0;
+                const uint64_t commit = index - delta;
+                const bool probe = state == RAFTGPU_STATE_PROBE;
+                const bool need = m < index;
+                const bool old_paused = !is_local && (f0 & (probe ? RAFTGPU_PF_PAUSED : RAFTGPU_PF_INS_FULL)) != 0;
+                const bool trans = need && !is_local && probe;                    // raft.rs:1730 become_replicate
+                uint32_t f = is_local ? f0 : (f0 | RAFTGPU_PF_RECENT_ACTIVE);     // raft.rs:1674
+                if (need) f &= ~RAFTGPU_PF_PAUSED;
+                if (trans)
+                    f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_REPLICATE;
+                uint64_t nnx = nx < index + 1 ? index + 1 : nx;
+                if (trans) nnx = index + 1;                                       // next_idx = matched + 1
+                if (fast) {
+                    if (is_local && delta != kPkNoCommit) s_li[gl_s] = index + delta;   // raft.rs:974-991
+                    if (!is_local && commit > pcv) s_pc[ci] = commit;                   // raft.rs:1677
+                    if (need) s_matched[ci] = index;
+                    if (nnx != nx) s_next[ci] = nnx;
+                    if (f != f0) s_flags[fi] = static_cast<uint8_t>(f);
+                    if (trans) c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
+                    local[0]++;
+                    local[1] += need ? 1u : 0u;
+                } else if (!is_ext) {
+                    const uint32_t at = atomicAdd(&s_ndefer[warp], 1u);
+                    if (at < kFDefer)
+                        my_defer[at] = k;
+                    else
+                        slow_record(k);  // the list is full: here and now (correct, only slower)
+                }
+                if (a.results && (fast || is_ext) && k < cnt)
+                    a.results[rbeg + k] = static_cast<uint8_t>((fast && need) ? (RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u)) : 0u);
+            };
+            {
+                ulonglong2 qa = staged != 0 ? rec_at(tid) : q_next;
+                ulonglong2 qb = rec_at(tid + kCT);
+                for (uint32_t k = tid; k < cnt; k += 2u * kCT) {
+                    const ulonglong2 q0 = qa, q1 = qb;
+                    qa = rec_at(k + 2u * kCT);
+                    qb = rec_at(k + 3u * kCT);
+                    fast_record(q0, k);
+                    fast_record(q1, k + kCT);   // past the end: a padding EXT, nothing happens
+                }
+            }
+            __syncwarp();
+            {
+                const uint32_t nd = s_ndefer[warp] < kFDefer ? s_ndefer[warp] : kFDefer;
+                for (uint32_t j = lane; j < nd; j += 32) slow_record(my_defer[j]);
             }
             named_bar_sync(bar_id, kCT);
             if (a.dbg && tid == 0) t2 = clock64();

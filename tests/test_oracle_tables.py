@@ -393,3 +393,55 @@ def test_heartbeat_commits_arena():
     none = (1 << 64) - 1
     assert out[:, 0].tolist() == [none, 5, 1005, 1000, none, none, none, none]
     assert out[:, 1].tolist() == [7, 7, 3, none, none, none, none, none]
+
+
+# ---- SURVEY 8(f) rank 3 (response side): handle_heartbeat_response, raft.rs:1777-1804.
+def hb(group, slot, commit=0):
+    r = np.zeros(1, dtype=O.APPEND_RESP_DTYPE)
+    r[0] = (group, slot, 0x04, 0, 0, commit)
+    return r
+
+
+def test_heartbeat_response_resumes_and_frees_one_inflight():
+    # test_raft.rs:329-347 test_progress_resume_by_heartbeat_resp: a paused peer in Replicate state is resumed
+    c = one_group([11, 5], last_index=11)
+    c.pflags[1, 0] = REPL | O.PF_PAUSED
+    res = O.arena_apply_heartbeat(c, hb(0, 1))
+    assert not (c.pflags[1, 0] & O.PF_PAUSED) and (c.pflags[1, 0] & O.PF_RECENT_ACTIVE)
+    assert res[0] == O.RES_OK | O.RES_SEND            # matched 5 < last_index 11: send_append (raft.rs:1800-1803)
+    # test_raft_flow_control.rs:100-187 test_msg_app_flow_control_recv_heartbeat: a full window is not full
+    # any more after ONE heartbeat response (free_first_one), and stays so for further ones
+    c.pflags[1, 0] = REPL | O.PF_INS_FULL
+    for _ in range(3):
+        O.arena_apply_heartbeat(c, hb(0, 1))
+        assert not (c.pflags[1, 0] & O.PF_INS_FULL)
+    # a Probe peer's "full" bit is not looked at (raft.rs:1796: only in Replicate); paused clears
+    # (test_raft.rs:2855-2880: the heartbeat response lets ONE more append go out to a paused probing peer)
+    c.pflags[1, 0] = PROBE | O.PF_PAUSED | O.PF_INS_FULL
+    res = O.arena_apply_heartbeat(c, hb(0, 1))
+    assert c.pflags[1, 0] & O.PF_INS_FULL and not (c.pflags[1, 0] & O.PF_PAUSED) and res[0] & O.RES_SEND
+    # update_committed (raft.rs:1791) never decreases; a caught-up peer with no snapshot request gets no append
+    c.matched[1, 0], c.peer_committed[1, 0] = 11, 9
+    assert O.arena_apply_heartbeat(c, hb(0, 1, commit=7))[0] == O.RES_OK and c.peer_committed[1, 0] == 9
+    assert O.arena_apply_heartbeat(c, hb(0, 1, commit=10))[0] == O.RES_OK and c.peer_committed[1, 0] == 10
+    c.pending_request_snapshot[1, 0] = 4
+    assert O.arena_apply_heartbeat(c, hb(0, 1))[0] == O.RES_OK | O.RES_SEND
+    # unknown responder (raft.rs:1779-1789); a record without the HEARTBEAT flag is not this path's
+    assert O.arena_apply_heartbeat(c, hb(0, 5))[0] == O.RES_NO_PROGRESS
+    plain = hb(0, 1)
+    plain["flags"] = 0
+    assert O.arena_apply_heartbeat(c, plain)[0] == 0
+
+
+def test_update_state_over_a_send_list():
+    # progress.rs:231-243 (pinned Progress-level by test_progress_update_state above): the arena form
+    c = one_group([20, 4, 7, 9], last_index=20)
+    c.pflags[1, 0], c.pflags[2, 0], c.pflags[3, 0] = REPL, PROBE, SNAP
+    e = np.zeros(5, dtype=[("group", "<u4"), ("peer_slot", "u1"), ("flags", "u1"), ("reserved", "<u2"), ("next_idx", "<u8")])
+    e["peer_slot"] = [1, 2, 3, 6, 1]
+    e["next_idx"] = [15, 12, 9, 1, 18]       # `last` of every MsgAppend built
+    res = O.arena_update_state(c, e)
+    assert res.tolist() == [1, 1, 0xFF, O.RES_NO_PROGRESS, 1]
+    assert c.next_idx[1, 0] == 19             # optimistic_update of the second send to peer 1: last + 1
+    assert c.pflags[2, 0] & O.PF_PAUSED and c.next_idx[2, 0] == 8     # Probe: paused, next_idx untouched
+    assert c.next_idx[3, 0] == 10 and not (c.pflags[3, 0] & O.PF_PAUSED)

@@ -441,7 +441,10 @@ def main():
     legs = {}
     if e2e_steps:
         # e2e: 24-byte records (pinned host memory) -> raftgpu_step_begin_records -> raftgpu_step_wait
-        legs["e2e"] = pipelined_leg(lambda j: es.next_round(bufs[j]), lambda recs: ea.step_begin_records(recs, flags))
+        # (RAFTGPU_STEP_ASYNC: the call returns once the staging threads have the batch; the records stay untouched
+        # in their pinned buffer until the step's raftgpu_step_wait, which is what this loop does anyway)
+        legs["e2e"] = pipelined_leg(lambda j: es.next_round(bufs[j]),
+                                    lambda recs: ea.step_begin_records(recs, flags | B.STEP_ASYNC))
     if e2e_steps and sublegs:
         # e2e_prepacked: the caller already holds the compact stream (pack untimed)
         cap_b = B.compact_bound(rec_slots)
@@ -526,7 +529,7 @@ def main():
                 "frac": ro_gbs / world / peak_gbs, "traffic": traffic.get("recompute_kernel"),
                 "api": "raftgpu_recompute: Raft::maybe_commit for every group, nothing applied (BASELINE.md 3: rate x (8K+34) B)"}
         apis = {
-            "e2e": "raftgpu_step_begin_records + raftgpu_step_wait (READ_COMMITTED): the step's 24-byte records "
+            "e2e": "raftgpu_step_begin_records(READ_COMMITTED | ASYNC) + raftgpu_step_wait: the step's 24-byte records "
                    "(raftgpu_append_resp, what handle_append_response consumes) sit in pinned host memory "
                    "(raftgpu_host_alloc); timed: the library's staging threads pack them into the compact stream, H2D "
                    "slice by slice, tile index + fused apply/recompute kernel, D2H of the advanced bitmap and the new "

@@ -497,6 +497,12 @@ int32_t raftgpu_step_slot_results(raftgpu_arena *arena, const uint8_t **results,
  * j+1 overlaps the kernels and D2H of step j.  raftgpu_step_wait completes the oldest. */
 #define RAFTGPU_STEP_READ_COMMITTED 0x1u /* also copy back the new committed index of advanced groups */
 #define RAFTGPU_STEP_READ_RESULTS 0x2u   /* also copy back the per-record result bytes */
+/* raftgpu_step_begin_records only: return as soon as the staging threads have the batch; packing, the H2D copies
+ * and the kernel launches are queued by the arena's submitter thread.  `records` must then stay untouched until
+ * this step's raftgpu_step_wait returns, a submission error is reported by that raftgpu_step_wait, and until
+ * then the only arena calls allowed are raftgpu_step_wait and the next raftgpu_step_begin_* (which first waits
+ * for the pending submission).  This overlaps ALL host work of tick j+1 with the GPU work of tick j. */
+#define RAFTGPU_STEP_ASYNC 0x4u
 int32_t raftgpu_step_begin(raftgpu_arena *arena, uint32_t flags);
 int32_t raftgpu_step_wait(raftgpu_arena *arena, raftgpu_step_result *out);
 int32_t raftgpu_step(raftgpu_arena *arena, uint32_t flags, raftgpu_step_result *out);

@@ -1394,3 +1394,41 @@ def test_update_state_vs_oracle_and_probe_peers_are_sent_to_once():
     snap["peer_slot"], snap["group"], snap["next_idx"] = gs[0][0], gs[0][1], 5
     assert a.update_state(snap).tolist() == [0xFF] == O.arena_update_state(ref, snap).tolist()
     a.close()
+
+
+def test_async_record_steps_keep_two_ticks_in_flight():
+    """RAFTGPU_STEP_ASYNC: raftgpu_step_begin_records returns once the staging threads have the batch; the submitter
+    thread packs / copies / launches.  Tick j+1 is begun before tick j is waited for, six ticks in a row: every
+    step's advanced bitmap and commit indexes and the final columns against the oracle."""
+    n = 300_000
+    synth = B.Synth(n, 0xA51C, k_peers=5)
+    os.environ.setdefault("RAFTGPU_HOST_THREADS", "8")
+    arena = B.Arena(n, n_rings=8)
+    assert arena.group_alloc_range(n) == 0
+    arena.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    rounds = [synth.next_round().copy() for _ in range(6)]
+    flags = B.STEP_READ_COMMITTED | B.STEP_ASYNC
+    arena.step_begin_records(rounds[0], flags)
+    for j in range(len(rounds)):
+        if j + 1 < len(rounds):
+            arena.step_begin_records(rounds[j + 1], flags)      # waits for submission j, then returns at once
+        r = arena.step_wait()
+        O.arena_apply(ref, rounds[j], mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        bm, com = arena.step_results(n)
+        assert r.n_advanced == want_adv and r.n_records == int(np.count_nonzero((rounds[j]["flags"] & B.REC_EXT) == 0))
+        assert np.array_equal(bm, want_bm[: len(bm)]), j
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+    assert_columns_equal(arena.read_columns(n), ref, n, "async steps")
+    # an ordinary call right after an asynchronous one first lets the submission finish
+    e1, e2 = synth.next_round().copy(), synth.next_round().copy()
+    arena.step_begin_records(e1, flags)
+    arena.step_begin_records(e2, B.STEP_READ_COMMITTED)      # synchronous form: two steps in flight, in order
+    for e in (e1, e2):
+        arena.step_wait()
+        O.arena_apply(ref, e, mode=0)
+        O.arena_recompute(ref)
+    assert_columns_equal(arena.read_columns(n), ref, n, "async then sync")
+    arena.close()

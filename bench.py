@@ -29,6 +29,7 @@ counters and times.
 from __future__ import annotations
 
 import argparse
+import gc
 import importlib
 import json
 import os
@@ -146,6 +147,18 @@ def gpu_local_cpus(torch, device: int):
         return set()
 
 
+def _siblings(cpu: int):
+    try:
+        txt = open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list").read().strip()
+        out = set()
+        for tok in txt.split(","):
+            lo, _, hi = tok.partition("-")
+            out.update(range(int(lo), int(hi or lo) + 1))
+        return out
+    except Exception:
+        return {cpu}
+
+
 def cpu_leg(n_groups, seed, rounds_wanted, threads, budget_s=20.0, joint=False):
     """The oracle (oracle/raft_oracle.c: apply + recompute, range-partitioned over `threads`
     pthreads) on a bounded sample of the same workload.  Only used as the CPU baseline."""
@@ -214,7 +227,9 @@ def main():
     ap.add_argument("--groups", type=int, default=0, help="override the groups per GPU of the workload")
     ap.add_argument("--e2e-threads", type=int, default=0, help="library staging threads (default: from the GPU-local cores)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
-    ap.add_argument("--e2e-chunk", type=int, default=8, help="pipelined e2e steps per timed chunk")
+    ap.add_argument("--e2e-chunk", type=int, default=0,
+                    help="pipelined e2e steps per timed chunk (default: all timed steps in one chunk, at most 32, for `e2e`; "
+                         "8 for the secondary legs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sublegs", action="store_true", help="skip recompute_only / scatter / secondary e2e legs")
     ap.add_argument("--profile", action="store_true",
@@ -387,20 +402,30 @@ def main():
     # staging threads per rank: one per physical GPU-local core, shared with the other ranks whose
     # GPU hangs off the same socket (two sockets per host)
     ranks_per_node = max(1, (world + 1) // 2)
-    e2e_threads = args.e2e_threads or max(4, min(32, (len(local_cpus) or 64) // (2 * ranks_per_node)))
+    # three quarters of the rank's share of the GPU-local logical CPUs: every physical core plus half of the SMT
+    # siblings (measured at N = 1: 32 threads 0.91e9/s, 48 threads 1.06e9/s, 56 threads stall -- the caller's and the
+    # submitter's threads need CPUs too)
+    e2e_threads = args.e2e_threads or max(4, min(48, (3 * (len(local_cpus) or 64)) // (4 * ranks_per_node)))
     os.environ.setdefault("RAFTGPU_HOST_THREADS", str(e2e_threads))
-    chunk = max(2, args.e2e_chunk)
     e2e_steps = 0 if args.profile else (args.e2e_steps or K)
+    chunk = max(2, args.e2e_chunk or min(32, e2e_steps))    # `e2e`: one pinned record buffer per step of a chunk
+    chunk2 = max(2, args.e2e_chunk or 8)                    # secondary legs
     es = B.Synth(n, seed0 + 0x10000 * rank, k_peers=K_PEERS, joint=joint)
     ea = B.Arena(n, device=local_rank, n_rings=e2e_threads)
-    assert ea.group_alloc_range(n) == 0
-    ea.load_columns(es.initial)
+    if local_cpus and world == 1:
+        # the caller's thread keeps off the cores the staging threads are pinned to (the first `e2e_threads` physical
+        # cores of the GPU's socket, staging_cpu_order in abi_staging.inc): it runs on their SMT siblings
+        prim = sorted(c for c in local_cpus if c == min(_siblings(c)))
+        order = prim + sorted(local_cpus - set(prim))            # physical cores first, then their SMT siblings
+        rest = local_cpus - set(order[:e2e_threads])
+        if rest:
+            os.sched_setaffinity(0, rest)
     flags = B.STEP_READ_COMMITTED
     # the caller's 24-byte records live in pinned, GPU-local host memory (raftgpu_host_alloc)
     rec_bytes = rec_slots * B.APPEND_RESP_DTYPE.itemsize
     bufs = [ea.host_alloc_bytes(rec_bytes).view(B.APPEND_RESP_DTYPE) for _ in range(chunk)] if e2e_steps else []
 
-    def pipelined_leg(prepare, begin):
+    def pipelined_leg(prepare, begin, chunk=chunk2):
         """`chunk` steps at a time: prepare(j) builds batch j (UNTIMED: the generation of the inputs);
         then, timed: begin(batch 0); for each j: begin(batch j+1) while step j is in flight; wait(j).
         Wall clock around the chunk, barrier + synchronize on both sides."""
@@ -418,6 +443,8 @@ def main():
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
+            gc.collect()
+            gc.disable()      # no collector pause inside the timed region
             t0 = time.perf_counter()
             begin(batches[0])
             phase[0] += time.perf_counter() - t0
@@ -432,7 +459,10 @@ def main():
                 phase[1] += tc - tb
                 dma[0] += sr.h2d_bytes
                 dma[1] += sr.d2h_bytes
+                if os.environ.get("RAFTGPU_TRACE"):
+                    print(f"[bench] step {j}: begin {1e6 * (tb - ta):.0f} us, wait {1e6 * (tc - tb):.0f} us", file=sys.stderr)
             secs += time.perf_counter() - t0
+            gc.enable()
             done += m
         d = max(1, done)
         return {"seconds": secs, "steps": done, "h2d": dma[0] / d, "d2h": dma[1] / d,
@@ -444,11 +474,11 @@ def main():
         # (RAFTGPU_STEP_ASYNC: the call returns once the staging threads have the batch; the records stay untouched
         # in their pinned buffer until the step's raftgpu_step_wait, which is what this loop does anyway)
         legs["e2e"] = pipelined_leg(lambda j: es.next_round(bufs[j]),
-                                    lambda recs: ea.step_begin_records(recs, flags | B.STEP_ASYNC))
+                                    lambda recs: ea.step_begin_records(recs, flags | B.STEP_ASYNC), chunk)
     if e2e_steps and sublegs:
         # e2e_prepacked: the caller already holds the compact stream (pack untimed)
         cap_b = B.compact_bound(rec_slots)
-        pk = [ea.host_alloc_bytes(cap_b) for _ in range(chunk)]
+        pk = [ea.host_alloc_bytes(cap_b) for _ in range(chunk2)]
         legs["e2e_prepacked"] = pipelined_leg(
             lambda j: (pk[j], B.pack_compact(es.next_round(bufs[j]), pk[j])[0]),
             lambda b: ea.step_begin_compact(b[0], b[1], flags))
@@ -457,7 +487,7 @@ def main():
         if hasattr(ea, "step_begin_wire"):
             # e2e_wire: serialized eraftpb.Message frames (pinned) -> device-side varint decode -> the same step
             W_ = importlib.import_module("raft-rs_b200").wire
-            wb = [W_.WireBuffers(ea, rec_slots) for _ in range(chunk)]
+            wb = [W_.WireBuffers(ea, rec_slots) for _ in range(chunk2)]
             legs["e2e_wire"] = pipelined_leg(
                 lambda j: wb[j].encode(es.next_round(bufs[j])),
                 lambda w_: ea.step_begin_wire(w_, flags))
@@ -545,7 +575,8 @@ def main():
             line[name] = {"value": world * n * lg["steps"] / maxes[name], "unit": UNIT,
                           "ms_per_step": 1e3 * maxes[name] / lg["steps"], "steps": lg["steps"],
                           "h2d_bytes_per_step": lg["h2d"], "d2h_bytes_per_step": lg["d2h"],
-                          "host_ms_per_step": lg["host_ms"], "pipelined_chunk": chunk, "api": apis[name]}
+                          "host_ms_per_step": lg["host_ms"], "pipelined_chunk": chunk if name == "e2e" else chunk2,
+                          "api": apis[name]}
         if "e2e" in line:
             line["e2e"].update({"caller_record_bytes_per_step": 24.0 * n_records / K, "host_threads": e2e_threads,
                                 "host_cpus_bound": len(local_cpus) or None})

@@ -369,7 +369,9 @@ def main():
             stream.synchronize()
         for i in range(W):
             step_fused(i)
-        ms_total, ms_kernel = timed(step_fused, W, K)
+        # the K timed steps are captured into ONE CUDA graph and replayed: the kernels run back to back, so their
+        # average duration is the timed region / K (no per-launch event pairs, no Python launch pacing in between)
+        ms_total, ms_kernel = timed(step_fused, W, K, per_launch=False)
         n_records = sum(round_len[a][r][1] for a, r in schedule[W:W + K])
         sc = ro = None
         if sublegs:
@@ -420,6 +422,8 @@ def main():
         rest = local_cpus - set(order[:e2e_threads])
         if rest:
             os.sched_setaffinity(0, rest)
+    assert ea.group_alloc_range(n) == 0
+    ea.load_columns(es.initial)
     flags = B.STEP_READ_COMMITTED
     # the caller's 24-byte records live in pinned, GPU-local host memory (raftgpu_host_alloc)
     rec_bytes = rec_slots * B.APPEND_RESP_DTYPE.itemsize
@@ -459,6 +463,8 @@ def main():
                 phase[1] += tc - tb
                 dma[0] += sr.h2d_bytes
                 dma[1] += sr.d2h_bytes
+                # the step really did the work it is credited with: every group recomputed, a full round applied
+                assert sr.n_groups == n and sr.n_records > n, (sr.n_groups, sr.n_records)
                 if os.environ.get("RAFTGPU_TRACE"):
                     print(f"[bench] step {j}: begin {1e6 * (tb - ta):.0f} us, wait {1e6 * (tc - tb):.0f} us", file=sys.stderr)
             secs += time.perf_counter() - t0

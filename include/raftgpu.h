@@ -53,6 +53,13 @@ extern "C" {
 #define RAFTGPU_ERR_PEER_NOT_FOUND (-7) /* Error::StepPeerNotFound, raw_node.rs:402-411 */
 #define RAFTGPU_ERR_COMMIT_RANGE (-8)   /* RaftLog::commit_to fatal!, raft_log.rs:291-298 */
 #define RAFTGPU_ERR_BUSY (-9)           /* a step is still in flight on this buffer */
+/* A group would need more than RAFTGPU_SLOTS peer slots (voters of both halves of a joint configuration +
+ * learners + learners_next, tracker.rs:37-92).  HARD LIMIT of this engine: the reference has none
+ * (majority.rs:86-93 sorts any number of voters on the heap); 8 covers 7 voters -- the largest configuration
+ * the reference keeps on its stack path (majority.rs:79) -- or a 5-voter group that swaps up to three members,
+ * or 5 voters + 2 learners + one joint change.  A caller that hits it keeps that group on the stock
+ * ProgressTracker (the arena is per group: other groups are unaffected). */
+#define RAFTGPU_ERR_TOO_MANY_PEERS (-10)
 
 const char *raftgpu_strerror(int32_t status);
 uint32_t raftgpu_abi_version(void);
@@ -209,7 +216,8 @@ typedef struct {
 
 /* ProgressTracker::with_capacity (tracker.rs:217-236) for `max_groups` trackers
  * at once: allocates every column in HBM plus the pinned staging buffers.
- * slots_per_group must be RAFTGPU_SLOTS.  ring_records = capacity of each of
+ * slots_per_group must be RAFTGPU_SLOTS (8): any other value is RAFTGPU_ERR_TOO_MANY_PEERS (16-slot arenas are
+ * not built; see that code).  ring_records = capacity of each of
  * the `n_rings` host staging rings (0 = default). */
 int32_t raftgpu_arena_create(int32_t device, uint32_t max_groups, uint32_t slots_per_group,
                              uint32_t n_rings, uint32_t ring_records, raftgpu_arena **out);

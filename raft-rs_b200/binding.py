@@ -25,7 +25,7 @@ U64_MAX = (1 << 64) - 1
 NO_TERM_START = U64_MAX
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NO_DEVICE, ERR_RANGE, ERR_FULL, ERR_PEER_NOT_FOUND, \
-    ERR_COMMIT_RANGE, ERR_BUSY = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
+    ERR_COMMIT_RANGE, ERR_BUSY, ERR_TOO_MANY_PEERS = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
 
 STATE_PROBE, STATE_REPLICATE, STATE_SNAPSHOT = 0, 1, 2
 VOTE_PENDING, VOTE_LOST, VOTE_WON = 0, 1, 2

@@ -513,7 +513,8 @@ void destroy(raftgpu_arena *a) {
 
 int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_rings,
                uint32_t ring_records, raftgpu_arena **out) {
-    if (!out || max_groups == 0 || slots != RAFTGPU_SLOTS) return RAFTGPU_ERR_INVALID;
+    if (!out || max_groups == 0) return RAFTGPU_ERR_INVALID;
+    if (slots != RAFTGPU_SLOTS) return RAFTGPU_ERR_TOO_MANY_PEERS;  // the documented hard limit (raftgpu.h)
     *out = nullptr;
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {

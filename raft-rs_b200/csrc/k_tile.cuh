@@ -231,16 +231,13 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                 if (j < cnt) return g_recs[j];
                 return make_ulonglong2(kPkExt, 0ull);
             };
-            // The main loop is STRAIGHT-LINE code for the records that make up ~98 % of the traffic -- an accept
-            // or a leader-local record for a staged cell of a peer in Replicate or Probe state: maybe_update
-            // (progress.rs:138-150), shared by the accept path (raft.rs:1674-1677, 1724-1730) and the leader-local
-            // path (raft.rs:974-991, 1010-1014); only an accept looks at is_paused() and may move a probing peer
-            // to Replicate.  Every load is issued unconditionally on a clamped address and every store is
-            // predicated, so two records per thread are in flight per iteration and nothing diverges.  Whatever
-            // else turns up (a rejection, a WIDE commit, a Snapshot-state peer, a learner outside the hint, a
-            // record that is not this tile's) is put on the WARP's deferred list and handled after the loop with
-            // all the warp's lanes working on such records at once, instead of one lane at a time in the loop:
-            // a wave has at most one record per cell, so the order between the two passes does not matter.
+            // The main loop handles the records that make up ~98 % of the traffic -- an accept or a leader-local
+            // record for a staged cell of a peer in Replicate or Probe state -- straight on the packed words and the
+            // shared-memory cell.  Whatever else turns up (a rejection, a WIDE commit, a Snapshot-state peer, a learner
+            // outside the hint, a record that is not this tile's) is put on the WARP's deferred list and handled after
+            // the loop with all the warp's lanes working on such records at once, instead of one lane at a time
+            // inside the loop (half of all warp-iterations contain a rejection): a wave has at most one record per
+            // cell, so the order between the two passes does not matter.
             uint32_t *my_defer = s_defer[warp];
             if (lane == 0) s_ndefer[warp] = 0;
             __syncwarp();
@@ -340,67 +337,66 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                 }
                 if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
             };
-            auto fast_record = [&](const ulonglong2 q, const uint32_t k) {
+            if (staged != 0) q_next = rec_at(tid);
+            for (uint32_t k = tid; k < cnt; k += kCT) {
+                const ulonglong2 q = q_next;
+                q_next = rec_at(k + kCT);
                 const uint64_t w0 = q.x;
-                const bool is_ext = (w0 & kPkExt) != 0;
+                if (w0 & kPkExt) {
+                    if (a.results) a.results[rbeg + k] = 0;
+                    continue;
+                }
                 const uint32_t slot = static_cast<uint32_t>(w0 >> 32) & 7u;
                 const uint32_t g = static_cast<uint32_t>(w0);
                 const uint32_t gl = g - g0;
-                const bool cell_ok = gl < ng && ((hint >> slot) & 1u);
-                const uint32_t gl_s = cell_ok ? gl : 0u;
-                const uint32_t r = cell_ok ? (kSimple5 ? slot : static_cast<uint32_t>(__popc(hint & ((1u << slot) - 1u)))) : 0u;
-                const uint32_t ci = r * R64 + gl_s, fi = r * kFRow8 + gl_s;
-                const uint32_t f0 = s_flags[fi];
-                const uint64_t m = s_matched[ci], nx = s_next[ci], pcv = s_pc[ci];
-                const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
-                bool present = true;
-                if constexpr (!kSimple5) {
-                    const uint32_t mt = s_meta[gl_s];
-                    present = ((RAFTGPU_META_IN(mt) | RAFTGPU_META_OUT(mt) | RAFTGPU_META_LEARN(mt)) >> slot) & 1u;
+                bool done = false;
+                if (!(w0 & (kPkWide | kPkReject)) && gl < ng && ((hint >> slot) & 1u)) {
+                    const uint32_t r = kSimple5 ? slot : static_cast<uint32_t>(__popc(hint & ((1u << slot) - 1u)));
+                    const uint32_t ci = r * R64 + gl;
+                    const uint32_t f0 = s_flags[r * kFRow8 + gl];
+                    const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
+                    const bool present = kSimple5 || (((RAFTGPU_META_IN(s_meta[gl]) | RAFTGPU_META_OUT(s_meta[gl]) |
+                                                        RAFTGPU_META_LEARN(s_meta[gl])) >> slot) & 1u);
+                    if (present && state != RAFTGPU_STATE_SNAPSHOT) {
+                        // accept / leader-local: maybe_update (progress.rs:138-150), shared by the accept path
+                        // (raft.rs:1674-1677, 1724-1730) and the leader-local path (raft.rs:974-991, 1010-1014);
+                        // only an accept looks at is_paused() and may move a probing peer to Replicate.
+                        const uint64_t index = q.y;
+                        const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
+                        const bool is_local = (w0 & kPkLocal) != 0;
+                        const uint64_t m = s_matched[ci], nx = s_next[ci], pcv = s_pc[ci];
+                        local[0]++;
+                        if (is_local && delta != kPkNoCommit) s_li[gl] = index + delta;   // raft.rs:974-991
+                        const uint64_t commit = index - delta;
+                        if (!is_local && commit > pcv) s_pc[ci] = commit;                 // raft.rs:1677
+                        const bool probe = state == RAFTGPU_STATE_PROBE;
+                        const bool need = m < index;
+                        const bool old_paused = !is_local && (f0 & (probe ? RAFTGPU_PF_PAUSED : RAFTGPU_PF_INS_FULL)) != 0;
+                        const bool trans = need && !is_local && probe;                    // raft.rs:1730 become_replicate
+                        uint32_t f = is_local ? f0 : (f0 | RAFTGPU_PF_RECENT_ACTIVE);     // raft.rs:1674
+                        if (need) f &= ~RAFTGPU_PF_PAUSED;
+                        if (trans)
+                            f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_REPLICATE;
+                        uint64_t nnx = nx < index + 1 ? index + 1 : nx;
+                        if (trans) {
+                            nnx = index + 1;                                              // next_idx = matched + 1
+                            c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
+                        }
+                        local[1] += need ? 1u : 0u;
+                        if (need) s_matched[ci] = index;
+                        if (nnx != nx) s_next[ci] = nnx;
+                        if (f != f0) s_flags[r * kFRow8 + gl] = static_cast<uint8_t>(f);
+                        if (a.results)
+                            a.results[rbeg + k] = static_cast<uint8_t>(need ? (RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u)) : 0u);
+                        done = true;
+                    }
                 }
-                const bool fast = !(w0 & (kPkExt | kPkWide | kPkReject)) && cell_ok && present && state != RAFTGPU_STATE_SNAPSHOT;
-                const uint64_t index = q.y;
-                const uint32_t delta = static_cast<uint32_t>(w0 >> 40);
-                const bool is_local = (w0 & kPkLocal) != 0;
-                const uint64_t commit = index - delta;
-                const bool probe = state == RAFTGPU_STATE_PROBE;
-                const bool need = m < index;
-                const bool old_paused = !is_local && (f0 & (probe ? RAFTGPU_PF_PAUSED : RAFTGPU_PF_INS_FULL)) != 0;
-                const bool trans = need && !is_local && probe;                    // raft.rs:1730 become_replicate
-                uint32_t f = is_local ? f0 : (f0 | RAFTGPU_PF_RECENT_ACTIVE);     // raft.rs:1674
-                if (need) f &= ~RAFTGPU_PF_PAUSED;
-                if (trans)
-                    f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | RAFTGPU_STATE_REPLICATE;
-                uint64_t nnx = nx < index + 1 ? index + 1 : nx;
-                if (trans) nnx = index + 1;                                       // next_idx = matched + 1
-                if (fast) {
-                    if (is_local && delta != kPkNoCommit) s_li[gl_s] = index + delta;   // raft.rs:974-991
-                    if (!is_local && commit > pcv) s_pc[ci] = commit;                   // raft.rs:1677
-                    if (need) s_matched[ci] = index;
-                    if (nnx != nx) s_next[ci] = nnx;
-                    if (f != f0) s_flags[fi] = static_cast<uint8_t>(f);
-                    if (trans) c.pending_snapshot[static_cast<size_t>(slot) * c.cap + g] = 0;
-                    local[0]++;
-                    local[1] += need ? 1u : 0u;
-                } else if (!is_ext) {
+                if (!done) {   // the rare kinds: onto the warp's list, handled after the loop by all its lanes together
                     const uint32_t at = atomicAdd(&s_ndefer[warp], 1u);
                     if (at < kFDefer)
                         my_defer[at] = k;
                     else
                         slow_record(k);  // the list is full: here and now (correct, only slower)
-                }
-                if (a.results && (fast || is_ext) && k < cnt)
-                    a.results[rbeg + k] = static_cast<uint8_t>((fast && need) ? (RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u)) : 0u);
-            };
-            {
-                ulonglong2 qa = staged != 0 ? rec_at(tid) : q_next;
-                ulonglong2 qb = rec_at(tid + kCT);
-                for (uint32_t k = tid; k < cnt; k += 2u * kCT) {
-                    const ulonglong2 q0 = qa, q1 = qb;
-                    qa = rec_at(k + 2u * kCT);
-                    qb = rec_at(k + 3u * kCT);
-                    fast_record(q0, k);
-                    fast_record(q1, k + kCT);   // past the end: a padding EXT, nothing happens
                 }
             }
             __syncwarp();

@@ -102,7 +102,7 @@ inline std::map<uint64_t, uint32_t> slot_map(const std::set<uint64_t> &a, const 
     for (const auto *s : {&a, &b})
         for (uint64_t id : *s)
             if (!m.count(id)) {
-                if (m.size() >= RAFTGPU_SLOTS) throw Error(RAFTGPU_ERR_INVALID, "more than RAFTGPU_SLOTS distinct voters");
+                if (m.size() >= RAFTGPU_SLOTS) throw Error(RAFTGPU_ERR_TOO_MANY_PEERS, "more than RAFTGPU_SLOTS distinct voters");
                 const uint32_t slot = static_cast<uint32_t>(m.size());
                 m[id] = slot;
             }
@@ -377,7 +377,7 @@ class ProgressTracker {
                 if (slots_.count(id)) continue;
                 uint32_t slot = 0;
                 while (slot < RAFTGPU_SLOTS && used_slots_ & (1u << slot)) slot++;
-                if (slot == RAFTGPU_SLOTS) throw Error(RAFTGPU_ERR_NOMEM, "more than RAFTGPU_SLOTS peers in one group");
+                if (slot == RAFTGPU_SLOTS) throw Error(RAFTGPU_ERR_TOO_MANY_PEERS, "more than RAFTGPU_SLOTS peers in one group");
                 used_slots_ |= 1u << slot;
                 slots_[id] = slot;
             } else if (const auto it = slots_.find(id); it != slots_.end()) {

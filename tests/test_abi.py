@@ -41,6 +41,10 @@ def test_null_arena_is_rejected_not_crashing():
     assert L.raftgpu_step(None, 0, None) == B.ERR_INVALID
     assert L.raftgpu_recompute(None, None, 0, 1, None, None, None, None) == B.ERR_INVALID
     assert L.raftgpu_arena_create(0, 0, 8, 0, 0, None) == B.ERR_INVALID
+    # the documented hard limit: 8 peer slots per group (a distinct code, not a generic failure)
+    out = C.c_void_p()
+    assert L.raftgpu_arena_create(0, 1024, 16, 0, 0, C.byref(out)) == B.ERR_TOO_MANY_PEERS
+    assert "peer slots" in B.strerror(B.ERR_TOO_MANY_PEERS)
 
 
 def test_no_device_means_error_not_fallback():
@@ -50,3 +54,32 @@ def test_no_device_means_error_not_fallback():
     with pytest.raises(B.RaftGpuError) as e:
         B.Arena(1024)
     assert e.value.status == B.ERR_NO_DEVICE
+
+
+def test_rust_stub_in_integration_md_is_generated_and_matches_the_header():
+    """INTEGRATION.md section 2 is scripts/gen_rust_stub.py's output (a stale hand-written stub declared a 24-byte
+    raftgpu_step_result against the header's 48 bytes in round 1), and every struct's C layout -- computed from the
+    header text -- agrees with the ctypes mirror in binding.py."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import gen_rust_stub as G
+    doc = open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8").read()
+    block = doc[doc.index(G.BEGIN) + len(G.BEGIN):doc.index(G.END)]
+    assert block.strip() == ("```rust\n" + G.generate() + "```").strip(), "run: python scripts/gen_rust_stub.py --update"
+    lay = G.struct_layouts()
+    mirror = {"raftgpu_progress": B.Progress, "raftgpu_group_state": B.GroupState, "raftgpu_info": B.Info,
+              "raftgpu_counters": B.Counters, "raftgpu_step_result": B.StepResult, "raftgpu_wire_batch": B.WireBatch}
+    for name, cls in mirror.items():
+        size, offs = lay[name]
+        assert C.sizeof(cls) == size, name
+        # same field order and offsets (ctypes names may differ where the header's is a Python keyword / differs)
+        assert [o for _, o, _ in offs] == [getattr(cls, f).offset for f, *_ in cls._fields_], name
+    assert lay["raftgpu_append_resp"][0] == B.APPEND_RESP_DTYPE.itemsize == 24
+    assert lay["raftgpu_send_entry"][0] == B.SEND_ENTRY_DTYPE.itemsize == 16
+    assert lay["raftgpu_compact_hdr"][0] == B.COMPACT_HDR_DTYPE.itemsize == 64
+    assert lay["raftgpu_step_result"][0] == 48
+    # the Rust text itself: every struct carries its size assertion
+    for name, (size, _) in lay.items():
+        assert f"size_of::<{name}>() == {size}" in block, name

@@ -403,7 +403,11 @@ def main():
     # ---- e2e: host buffers -> C-ABI -> results in host memory, on a fresh arena ------------------
     # staging threads per rank: one per physical GPU-local core, shared with the other ranks whose
     # GPU hangs off the same socket (two sockets per host)
-    ranks_per_node = max(1, (world + 1) // 2)
+    # ranks whose GPU hangs off the same socket share its cores: every rank takes its share (RAFTGPU_CPU_SHARE = k/R)
+    same_node = [r for r in range(world) if gpu_local_cpus(torch, r) == local_cpus] if local_cpus else list(range(world))
+    ranks_per_node = max(1, len(same_node))
+    if ranks_per_node > 1:
+        os.environ.setdefault("RAFTGPU_CPU_SHARE", f"{same_node.index(local_rank)}/{ranks_per_node}")
     # three quarters of the rank's share of the GPU-local logical CPUs: every physical core plus half of the SMT
     # siblings (measured at N = 1: 32 threads 0.91e9/s, 48 threads 1.06e9/s, 56 threads stall -- the caller's and the
     # submitter's threads need CPUs too)
@@ -414,12 +418,14 @@ def main():
     chunk2 = max(2, args.e2e_chunk or 8)                    # secondary legs
     es = B.Synth(n, seed0 + 0x10000 * rank, k_peers=K_PEERS, joint=joint)
     ea = B.Arena(n, device=local_rank, n_rings=e2e_threads)
-    if local_cpus and world == 1:
-        # the caller's thread keeps off the cores the staging threads are pinned to (the first `e2e_threads` physical
-        # cores of the GPU's socket, staging_cpu_order in abi_staging.inc): it runs on their SMT siblings
+    if local_cpus:
+        # the caller's thread keeps off the CPUs the staging threads are pinned to (staging_cpu_order in
+        # abi_staging.inc: the rank's share of the socket's physical cores, then of their SMT siblings)
         prim = sorted(c for c in local_cpus if c == min(_siblings(c)))
-        order = prim + sorted(local_cpus - set(prim))            # physical cores first, then their SMT siblings
-        rest = local_cpus - set(order[:e2e_threads])
+        sibs = sorted(local_cpus - set(prim))
+        k = same_node.index(local_rank) if ranks_per_node > 1 else 0
+        share = prim[k::ranks_per_node] + sibs[k::ranks_per_node]
+        rest = set(share[e2e_threads:])
         if rest:
             os.sched_setaffinity(0, rest)
     assert ea.group_alloc_range(n) == 0

@@ -86,15 +86,19 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, cpus=None):
         self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/raftgpu_clocks_{os.getpid()}.csv"
+        self.cpus = cpus    # where the poller may run: NOT on the staging threads' cores (it wakes every 50 ms and
+        #                     a pinned staging thread that loses its CPU for a time slice stalls the whole step)
 
     def start(self):
         try:
             self.f = open(self.path, "w")
+            cpus = self.cpus
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.gpu), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
+                 "-i", str(self.gpu), "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL,
+                preexec_fn=(lambda: os.sched_setaffinity(0, cpus)) if cpus else None)
         except Exception:
             self.proc = None
 
@@ -358,7 +362,7 @@ def main():
         total = e0.elapsed_time(e1)
         return total, (sum(a_.elapsed_time(b_) for a_, b_ in evs) if per_launch else total)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, (all_cpus - local_cpus) or None)   # the poller runs on the other socket
     sampler.start()
     with torch.cuda.stream(stream):
         # clocks up: the recompute pass is idempotent on unchanged progress

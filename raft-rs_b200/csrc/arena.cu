@@ -162,8 +162,12 @@ struct HostPool {
         start(fn);
         wait();
     }
+    cpu_set_t pool_cpus;      // RAFTGPU_PIN=set: every worker may run on any CPU of the pool's share
+    bool pin_set = false;
     void worker(int idx, int cpu) {
-        if (cpu >= 0) {  // one CPU per worker (ensure_pool picks them: GPU-local physical cores first)
+        if (pin_set) {
+            sched_setaffinity(0, sizeof(pool_cpus), &pool_cpus);
+        } else if (cpu >= 0) {  // one CPU per worker (ensure_pool picks them: GPU-local physical cores first)
             cpu_set_t one;
             CPU_ZERO(&one);
             CPU_SET(cpu, &one);

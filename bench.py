@@ -489,8 +489,12 @@ def main():
         # e2e: 24-byte records (pinned host memory) -> raftgpu_step_begin_records -> raftgpu_step_wait
         # (RAFTGPU_STEP_ASYNC: the call returns once the staging threads have the batch; the records stay untouched
         # in their pinned buffer until the step's raftgpu_step_wait, which is what this loop does anyway)
+        # With a small CPU share (several GPUs per socket) packing is the bottleneck: the records then cross PCIe as
+        # they are (RAFTGPU_STEP_RAW: 3.7x the bytes, no host work at all).  Crossover ~12 staging threads.
+        e2e_mode = os.environ.get("BENCH_E2E_MODE") or ("raw" if e2e_threads <= 12 else "packed")
+        e2e_flags = flags | (B.STEP_RAW if e2e_mode == "raw" else B.STEP_ASYNC)
         legs["e2e"] = pipelined_leg(lambda j: es.next_round(bufs[j]),
-                                    lambda recs: ea.step_begin_records(recs, flags | B.STEP_ASYNC), chunk)
+                                    lambda recs: ea.step_begin_records(recs, e2e_flags), chunk)
     if e2e_steps and sublegs:
         # e2e_prepacked: the caller already holds the compact stream (pack untimed)
         cap_b = B.compact_bound(rec_slots)
@@ -575,7 +579,8 @@ def main():
                 "frac": ro_gbs / world / peak_gbs, "traffic": traffic.get("recompute_kernel"),
                 "api": "raftgpu_recompute: Raft::maybe_commit for every group, nothing applied (BASELINE.md 3: rate x (8K+34) B)"}
         apis = {
-            "e2e": "raftgpu_step_begin_records(READ_COMMITTED | ASYNC) + raftgpu_step_wait: the step's 24-byte records "
+            "e2e": "raftgpu_step_begin_records(READ_COMMITTED | ASYNC, or | RAW when `mode` is raw: no packing, the records cross "
+                   "PCIe as they are) + raftgpu_step_wait: the step's 24-byte records "
                    "(raftgpu_append_resp, what handle_append_response consumes) sit in pinned host memory "
                    "(raftgpu_host_alloc); timed: the library's staging threads pack them into the compact stream, H2D "
                    "slice by slice, tile index + fused apply/recompute kernel, D2H of the advanced bitmap and the new "
@@ -594,7 +599,7 @@ def main():
                           "host_ms_per_step": lg["host_ms"], "pipelined_chunk": chunk if name == "e2e" else chunk2,
                           "api": apis[name]}
         if "e2e" in line:
-            line["e2e"].update({"caller_record_bytes_per_step": 24.0 * n_records / K, "host_threads": e2e_threads,
+            line["e2e"].update({"caller_record_bytes_per_step": 24.0 * n_records / K, "host_threads": e2e_threads, "mode": e2e_mode,
                                 "host_cpus_bound": len(local_cpus) or None})
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             os.sched_setaffinity(0, all_cpus)   # the CPU baseline gets every host core

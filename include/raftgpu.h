@@ -511,6 +511,14 @@ int32_t raftgpu_step_slot_results(raftgpu_arena *arena, const uint8_t **results,
  * then the only arena calls allowed are raftgpu_step_wait and the next raftgpu_step_begin_* (which first waits
  * for the pending submission).  This overlaps ALL host work of tick j+1 with the GPU work of tick j. */
 #define RAFTGPU_STEP_ASYNC 0x4u
+/* raftgpu_step_begin_records only: ship the 24-byte records AS THEY ARE (one H2D straight from the caller's buffer,
+ * which should be pinned: raftgpu_host_alloc) and apply them with the scatter kernel -- no host packing at all.
+ * 3.7x the PCIe bytes of the compact stream, zero CPU: the better choice when the caller's CPU share is small
+ * (several GPUs per socket: packing is CPU-bound, ~7 ns per record per staging thread).  Contract of
+ * the zero-copy paths: at most ONE record per (group, peer) cell, verified on the GPU (a duplicate is not applied,
+ * counted in n_duplicates, raftgpu_step_wait returns RAFTGPU_ERR_INVALID); `records` stays untouched until the
+ * step's raftgpu_step_wait returns. */
+#define RAFTGPU_STEP_RAW 0x8u
 int32_t raftgpu_step_begin(raftgpu_arena *arena, uint32_t flags);
 int32_t raftgpu_step_wait(raftgpu_arena *arena, raftgpu_step_result *out);
 int32_t raftgpu_step(raftgpu_arena *arena, uint32_t flags, raftgpu_step_result *out);

@@ -78,7 +78,7 @@ struct StagingSet {
     uint32_t *d_step_adv = nullptr;  // [0] advanced groups of the step, [1] duplicate records (zero-copy)
     uint32_t *d_touched = nullptr;   // [cap/4] zero-copy steps: one bit per (group, slot)
     // wire steps (grown on demand): the frames and their offsets on the device
-    uint8_t *d_wire = nullptr;
+    uint8_t *d_wire = nullptr;   // also the device copy of a RAFTGPU_STEP_RAW batch
     uint64_t d_wire_cap = 0;
     uint64_t wire_n = 0;             // frames of the wire step this set carried (0 = not a wire step)
     // sync

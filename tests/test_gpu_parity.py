@@ -1432,3 +1432,42 @@ def test_async_record_steps_keep_two_ticks_in_flight():
         O.arena_recompute(ref)
     assert_columns_equal(arena.read_columns(n), ref, n, "async then sync")
     arena.close()
+
+
+def test_raw_record_steps_match_the_packed_ones():
+    """RAFTGPU_STEP_RAW: the 24-byte records cross PCIe as they are (no host packing) and go through the scatter
+    kernel.  Same rounds as the packed form on a second arena: identical results, result bytes per record; a
+    second record for a cell is refused (one wave, verified on the GPU)."""
+    n = 200_000
+    synth = B.Synth(n, 0x0AB1, k_peers=5)
+    a1, a2 = B.Arena(n), B.Arena(n)
+    for a in (a1, a2):
+        assert a.group_alloc_range(n) == 0
+        a.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    buf = a2.host_alloc_bytes(24 * (5 * n + 64)).view(B.APPEND_RESP_DTYPE)
+    for rnd in range(3):
+        recs = synth.next_round().copy()
+        a1.step_begin_records(recs, B.STEP_READ_COMMITTED)
+        r1 = a1.step_wait()
+        buf[: len(recs)] = recs
+        a2.step_begin_records(buf[: len(recs)], B.STEP_READ_COMMITTED | B.STEP_READ_RESULTS | B.STEP_RAW)
+        r2 = a2.step_wait()
+        want_res = O.arena_apply(ref, recs, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        assert r1.n_advanced == r2.n_advanced == want_adv and r2.n_duplicates == 0
+        assert r2.h2d_bytes == 24 * len(recs)
+        assert np.array_equal(a2.slot_results()[: len(recs)], want_res)
+        b2, c2 = a2.step_results(n)
+        assert np.array_equal(b2, want_bm[: len(b2)])
+        adv = bitmap_to_bool(b2, n)
+        assert np.array_equal(c2[adv], ref.committed[:n][adv])
+    assert_columns_equal(a2.read_columns(n), ref, n, "raw steps")
+    assert_columns_equal(a1.read_columns(n), ref, n, "packed steps")
+    dup = np.concatenate([recs[:1000], recs[:1]])
+    dup = dup[(dup["flags"] & (B.REC_EXT | B.REC_REJECT)) == 0]
+    a2.step_begin_records(np.ascontiguousarray(np.concatenate([dup, dup[:1]])), B.STEP_RAW)
+    r = a2.step_wait(check=False)
+    assert r.status == B.ERR_INVALID and r.n_duplicates >= 1
+    a1.close()
+    a2.close()

@@ -66,7 +66,12 @@ class Progress(C.Structure):
                 ("pending_snapshot", C.c_uint64), ("pending_request_snapshot", C.c_uint64),
                 ("commit_group_id", C.c_uint64), ("committed_index", C.c_uint64),
                 ("state", C.c_uint8), ("paused", C.c_uint8), ("recent_active", C.c_uint8),
-                ("ins_full", C.c_uint8)]
+                ("ins_full", C.c_uint8), ("ins", C.c_void_p)]   # ins: optional ro_inflights*
+
+
+class Inflights(C.Structure):
+    """ro_inflights (inflights.rs:19-27): start, count, cap + the ring."""
+    _fields_ = [("start", C.c_uint32), ("count", C.c_uint32), ("cap", C.c_uint32), ("buffer", C.POINTER(C.c_uint64))]
 
 
 class RaftLog(C.Structure):
@@ -78,7 +83,8 @@ class ArenaView(C.Structure):
     _fields_ = [("cap", C.c_uint32), ("n_groups", C.c_uint32)] + \
         [(n, C.POINTER(C.c_uint64)) for n in PEER_COLUMNS] + \
         [("pflags", C.POINTER(C.c_uint8)), ("meta", C.POINTER(C.c_uint32))] + \
-        [(n, C.POINTER(C.c_uint64)) for n in GROUP_COLUMNS]
+        [(n, C.POINTER(C.c_uint64)) for n in GROUP_COLUMNS] + \
+        [("ins_cap", C.c_uint32), ("ins_meta", C.POINTER(C.c_uint32)), ("ins_buf", C.POINTER(C.c_uint64))]
 
 
 class WireMessage(C.Structure):
@@ -167,6 +173,12 @@ def lib() -> C.CDLL:
         L.ro_bench_step.restype = C.c_double
         L.ro_bench_step_fast.argtypes = [pv, C.c_void_p, sz, i32, p64]
         L.ro_bench_step_fast.restype = C.c_double
+        pi = C.POINTER(Inflights)
+        L.ro_inflights_full.argtypes, L.ro_inflights_full.restype = [pi], i32
+        L.ro_inflights_add.argtypes, L.ro_inflights_add.restype = [pi, u64], i32
+        L.ro_inflights_free_to.argtypes, L.ro_inflights_free_to.restype = [pi, u64], None
+        L.ro_inflights_free_first_one.argtypes, L.ro_inflights_free_first_one.restype = [pi], None
+        L.ro_inflights_reset.argtypes, L.ro_inflights_reset.restype = [pi], None
         L.wo_decode_message.argtypes = [C.c_void_p, sz, C.POINTER(WireMessage)]
         L.wo_decode_message.restype = i32
         L.wo_decode_batch.argtypes = [C.c_void_p, C.c_void_p, sz, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -248,6 +260,8 @@ def copy_columns(c):
     d = types.SimpleNamespace(cap=c.cap, n_groups=c.n_groups)
     for n in PEER_COLUMNS + ("pflags", "meta") + GROUP_COLUMNS:
         setattr(d, n, getattr(c, n).copy())
+    if getattr(c, "ins_cap", 0):
+        d.ins_cap, d.ins_meta, d.ins_buf = c.ins_cap, c.ins_meta.copy(), c.ins_buf.copy()
     return d
 
 
@@ -262,7 +276,22 @@ def view(c) -> ArenaView:
     assert c.meta.dtype == np.uint32 and c.meta.flags.c_contiguous
     v.pflags = c.pflags.ctypes.data_as(C.POINTER(C.c_uint8))
     v.meta = c.meta.ctypes.data_as(C.POINTER(C.c_uint32))
+    ins_cap = int(getattr(c, "ins_cap", 0))
+    v.ins_cap = ins_cap
+    if ins_cap:    # the Inflights windows are modelled (enable_inflights)
+        assert c.ins_meta.dtype == np.uint32 and c.ins_meta.shape == (SLOTS, c.cap) and c.ins_meta.flags.c_contiguous
+        assert c.ins_buf.dtype == np.uint64 and c.ins_buf.shape == (SLOTS, c.cap, ins_cap) and c.ins_buf.flags.c_contiguous
+        v.ins_meta = c.ins_meta.ctypes.data_as(C.POINTER(C.c_uint32))
+        v.ins_buf = c.ins_buf.ctypes.data_as(C.POINTER(C.c_uint64))
     return v
+
+
+def enable_inflights(c, ins_cap: int):
+    """Model the per-peer Inflights windows (inflights.rs) of these columns: empty rings of `ins_cap` entries."""
+    c.ins_cap = int(ins_cap)
+    c.ins_meta = np.zeros((SLOTS, c.cap), dtype=np.uint32)
+    c.ins_buf = np.zeros((SLOTS, c.cap, ins_cap), dtype=np.uint64)
+    return c
 
 
 def arena_mci(c, g: int):

@@ -159,6 +159,44 @@ int ro_joint_vote_result(const uint64_t *incoming, size_t n_in, const uint64_t *
 }
 
 /* ------------------------------------------------------------------------ */
+/* src/tracker/inflights.rs                                                  */
+
+int ro_inflights_full(const ro_inflights *in) { return in->count == in->cap; } /* :54-56 */
+
+/* :65-82 */
+int ro_inflights_add(ro_inflights *in, uint64_t inflight) {
+    if (ro_inflights_full(in)) return -1; /* panic!("cannot add into a full inflights") */
+    uint32_t next = in->start + in->count;
+    if (next >= in->cap) next -= in->cap;
+    in->buffer[next] = inflight; /* (the Vec grows by push until it holds cap entries: the same ring) */
+    in->count += 1;
+    return 0;
+}
+
+/* :85-110 */
+void ro_inflights_free_to(ro_inflights *in, uint64_t to) {
+    if (in->count == 0 || to < in->buffer[in->start]) return; /* out of the left side of the window */
+    uint32_t i = 0, idx = in->start;
+    while (i < in->count) {
+        if (to < in->buffer[idx]) break; /* found the first large inflight */
+        idx += 1;
+        if (idx >= in->cap) idx -= in->cap;
+        i += 1;
+    }
+    in->count -= i;
+    in->start = idx;
+}
+
+/* :113-116 */
+void ro_inflights_free_first_one(ro_inflights *in) { ro_inflights_free_to(in, in->buffer[in->start]); }
+
+/* :119-123 */
+void ro_inflights_reset(ro_inflights *in) {
+    in->count = 0;
+    in->start = 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* src/tracker/progress.rs                                                   */
 
 /* :60-73 */
@@ -182,6 +220,7 @@ static void reset_state(ro_progress *p, uint8_t state) {
     p->pending_snapshot = 0;
     p->state = state;
     p->ins_full = 0; /* ins.reset() */
+    if (p->ins) ro_inflights_reset(p->ins);
 }
 
 /* :82-92 */
@@ -194,6 +233,7 @@ void ro_progress_reset(ro_progress *p, uint64_t next_idx) {
     p->pending_request_snapshot = RO_INVALID_INDEX;
     p->recent_active = 0;
     p->ins_full = 0; /* ins.reset() */
+    if (p->ins) ro_inflights_reset(p->ins);
 }
 
 /* :95-107 */
@@ -286,7 +326,7 @@ int ro_progress_is_paused(const ro_progress *p) {
     case RO_STATE_PROBE:
         return p->paused;
     case RO_STATE_REPLICATE:
-        return p->ins_full; /* self.ins.full() */
+        return p->ins ? ro_inflights_full(p->ins) : p->ins_full; /* self.ins.full() */
     default:
         return 1; /* Snapshot */
     }
@@ -300,8 +340,9 @@ void ro_progress_pause(ro_progress *p) { p->paused = 1; }
 int ro_progress_update_state(ro_progress *p, uint64_t last) {
     switch (p->state) {
     case RO_STATE_REPLICATE:
+        if (p->ins && ro_inflights_full(p->ins)) return -1; /* ins.add on a full window panics (inflights.rs:66-68) */
         ro_progress_optimistic_update(p, last);
-        /* self.ins.add(last): Inflights is out of scope */
+        if (p->ins) ro_inflights_add(p->ins, last); /* else: the ring is the caller's */
         return 0;
     case RO_STATE_PROBE:
         ro_progress_pause(p);
@@ -348,8 +389,17 @@ static inline size_t cell(const ro_arena_view *a, uint32_t slot, uint32_t g) {
     return (size_t)slot * a->cap + g;
 }
 
-static void load_progress(const ro_arena_view *a, uint32_t slot, uint32_t g, ro_progress *p) {
+/* The Progress of one cell.  `ring` backs p->ins when the arena models the Inflights window. */
+static void load_progress_ins(const ro_arena_view *a, uint32_t slot, uint32_t g, ro_progress *p, ro_inflights *ring) {
     size_t c = cell(a, slot, g);
+    p->ins = NULL;
+    if (a->ins_cap && ring) {
+        ring->start = a->ins_meta[c] & 0xffffu;
+        ring->count = a->ins_meta[c] >> 16;
+        ring->cap = a->ins_cap;
+        ring->buffer = a->ins_buf + c * (size_t)a->ins_cap;
+        p->ins = ring;
+    }
     uint8_t f = a->pflags[c];
     p->matched = a->matched[c];
     p->next_idx = a->next_idx[c];
@@ -363,8 +413,12 @@ static void load_progress(const ro_arena_view *a, uint32_t slot, uint32_t g, ro_
     p->ins_full = (f & RO_PF_INS_FULL) != 0;
 }
 
-static void store_progress(ro_arena_view *a, uint32_t slot, uint32_t g, const ro_progress *p) {
+static void store_progress(ro_arena_view *a, uint32_t slot, uint32_t g, ro_progress *p) {
     size_t c = cell(a, slot, g);
+    if (p->ins) { /* the flag column mirrors ins.full() */
+        a->ins_meta[c] = p->ins->start | (p->ins->count << 16);
+        p->ins_full = (uint8_t)ro_inflights_full(p->ins);
+    }
     a->matched[c] = p->matched;
     a->next_idx[c] = p->next_idx;
     a->pending_snapshot[c] = p->pending_snapshot;
@@ -461,7 +515,8 @@ uint8_t ro_arena_handle_append_response(ro_arena_view *a, const ro_append_resp *
     if (slot >= RO_SLOTS || !(present & (1u << slot))) return RO_RES_NO_PROGRESS;
 
     ro_progress pr;
-    load_progress(a, slot, g, &pr);
+    ro_inflights ring;
+    load_progress_ins(a, slot, g, &pr, &ring);
     uint8_t res = 0;
 
     if (rec->flags & RO_REC_LOCAL) {
@@ -512,7 +567,7 @@ uint8_t ro_arena_handle_append_response(ro_arena_view *a, const ro_append_resp *
         if (ro_progress_maybe_snapshot_abort(&pr)) ro_progress_become_probe(&pr);
         break;
     default:
-        /* pr.ins.free_to(m.index): Inflights is out of scope */
+        if (pr.ins) ro_inflights_free_to(pr.ins, rec->index); /* :1742; else the ring is the caller's */
         break;
     }
     store_progress(a, slot, g, &pr);
@@ -546,11 +601,16 @@ uint8_t ro_arena_handle_heartbeat_response(ro_arena_view *a, const ro_append_res
     uint32_t present = RO_META_IN(meta) | RO_META_OUT(meta) | RO_META_LEARN(meta);
     if (slot >= RO_SLOTS || !(present & (1u << slot))) return RO_RES_NO_PROGRESS; /* :1779-1789 */
     ro_progress pr;
-    load_progress(a, slot, g, &pr);
+    ro_inflights ring;
+    load_progress_ins(a, slot, g, &pr, &ring);
     ro_progress_update_committed(&pr, rec->commit); /* :1791 */
     pr.recent_active = 1;                           /* :1792 */
     ro_progress_resume(&pr);                        /* :1793 */
-    if (pr.state == RO_STATE_REPLICATE && pr.ins_full) pr.ins_full = 0; /* :1796-1798 free_first_one */
+    if (pr.ins) {                                   /* :1796-1798 */
+        if (pr.state == RO_STATE_REPLICATE && ro_inflights_full(pr.ins)) ro_inflights_free_first_one(pr.ins);
+    } else if (pr.state == RO_STATE_REPLICATE && pr.ins_full) {
+        pr.ins_full = 0; /* a full window that loses its first entry is no longer full */
+    }
     uint8_t res = RO_RES_OK;
     if (pr.matched < a->last_index[g] || pr.pending_request_snapshot != RO_INVALID_INDEX) res |= RO_RES_SEND; /* :1800-1803 */
     store_progress(a, slot, g, &pr);
@@ -575,7 +635,8 @@ void ro_arena_update_state(ro_arena_view *a, const ro_send_entry *e, size_t n, u
             res = RO_RES_NO_PROGRESS;
         } else {
             ro_progress pr;
-            load_progress(a, slot, g, &pr);
+            ro_inflights ring;
+            load_progress_ins(a, slot, g, &pr, &ring);
             res = ro_progress_update_state(&pr, e[i].next_idx) == 0 ? 1 : 0xff;
             store_progress(a, slot, g, &pr);
         }

@@ -85,9 +85,24 @@ enum { RO_STATE_PROBE = 0, RO_STATE_REPLICATE = 1, RO_STATE_SNAPSHOT = 2 };
 /* raft.rs:81 */
 #define RO_INVALID_INDEX 0ull
 
-/* progress.rs:8-56.  `ins` (Inflights, a variable-length ring) is out of
- * scope; the single bit the path reads from it, `ins.full()` (progress.rs:213),
- * is carried as `ins_full`, cleared wherever the reference calls ins.reset(). */
+/* src/tracker/inflights.rs:19-110: the sliding window of in-flight MsgAppends of one peer (the last index of each),
+ * a ring of `cap` entries (Config::max_inflight_msgs, config.rs:112).  Pinned by the reference's own table tests
+ * (inflights.rs:131-256) in tests/test_oracle_tables.py. */
+typedef struct {
+    uint32_t start; /* inflights.rs:21 */
+    uint32_t count; /* :23 */
+    uint32_t cap;   /* buffer.capacity() */
+    uint64_t *buffer;
+} ro_inflights;
+int ro_inflights_full(const ro_inflights *in);            /* :54-56 */
+int ro_inflights_add(ro_inflights *in, uint64_t v);       /* :65-82; -1 where the reference panics (full) */
+void ro_inflights_free_to(ro_inflights *in, uint64_t to); /* :85-110 */
+void ro_inflights_free_first_one(ro_inflights *in);       /* :113-116 */
+void ro_inflights_reset(ro_inflights *in);                /* :119-123 */
+
+/* progress.rs:8-56.  `ins`: when the caller models the Inflights ring (`ins` != NULL) every place the
+ * reference touches it does; otherwise the single bit the path reads from it, `ins.full()`
+ * (progress.rs:213), is carried as `ins_full`, cleared wherever the reference calls ins.reset(). */
 typedef struct {
     uint64_t matched;
     uint64_t next_idx;
@@ -99,6 +114,7 @@ typedef struct {
     uint8_t paused;
     uint8_t recent_active;
     uint8_t ins_full;
+    ro_inflights *ins; /* optional */
 } ro_progress;
 
 void ro_progress_new(ro_progress *p, uint64_t next_idx);       /* progress.rs:60-73 */
@@ -174,6 +190,11 @@ typedef struct {
     uint64_t *term_start; /* first index of the leader's own term; UINT64_MAX = not leader */
     uint64_t *last_index;
     uint64_t *term;       /* only used by the literal synthetic-log check */
+    /* optional device-side Inflights: ins_cap = window size (0 = not modelled, the ins_full bit is
+     * then host-reported); ins_meta [RO_SLOTS][cap] = start | count << 16; ins_buf [RO_SLOTS][cap][ins_cap] */
+    uint32_t ins_cap;
+    uint32_t *ins_meta;
+    uint64_t *ins_buf;
 } ro_arena_view;
 
 /* AppendResponse record, 24 bytes; a REJECT record is followed

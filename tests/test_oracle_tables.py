@@ -445,3 +445,84 @@ def test_update_state_over_a_send_list():
     assert c.next_idx[1, 0] == 19             # optimistic_update of the second send to peer 1: last + 1
     assert c.pflags[2, 0] & O.PF_PAUSED and c.next_idx[2, 0] == 8     # Probe: paused, next_idx untouched
     assert c.next_idx[3, 0] == 10 and not (c.pflags[3, 0] & O.PF_PAUSED)
+
+
+# ---- src/tracker/inflights.rs:131-256: the reference's own table tests, restated for ro_inflights
+def _ins(cap, start=0, buffer=()):
+    buf = (C.c_uint64 * cap)(*buffer)
+    return O.Inflights(start, 0, cap, buf), buf
+
+
+def _state(ins, buf, n):
+    return ins.start, ins.count, list(buf)[:n]
+
+
+def test_inflight_add():
+    ins, buf = _ins(10)
+    for i in range(5):
+        assert L.ro_inflights_add(C.byref(ins), i) == 0
+    assert _state(ins, buf, 5) == (0, 5, [0, 1, 2, 3, 4])
+    for i in range(5, 10):
+        L.ro_inflights_add(C.byref(ins), i)
+    assert _state(ins, buf, 10) == (0, 10, list(range(10)))
+    assert L.ro_inflights_full(C.byref(ins)) and L.ro_inflights_add(C.byref(ins), 99) == -1    # :66-68 panic
+    ins2, buf2 = _ins(10, start=5, buffer=[0] * 5)
+    for i in range(5):
+        L.ro_inflights_add(C.byref(ins2), i)
+    assert _state(ins2, buf2, 10) == (5, 5, [0, 0, 0, 0, 0, 0, 1, 2, 3, 4])
+    for i in range(5, 10):
+        L.ro_inflights_add(C.byref(ins2), i)
+    assert _state(ins2, buf2, 10) == (5, 10, [5, 6, 7, 8, 9, 0, 1, 2, 3, 4])
+
+
+def test_inflight_free_to():
+    ins, buf = _ins(10)
+    for i in range(10):
+        L.ro_inflights_add(C.byref(ins), i)
+    L.ro_inflights_free_to(C.byref(ins), 4)
+    assert _state(ins, buf, 10) == (5, 5, list(range(10)))
+    L.ro_inflights_free_to(C.byref(ins), 8)
+    assert _state(ins, buf, 10) == (9, 1, list(range(10)))
+    for i in range(10, 15):
+        L.ro_inflights_add(C.byref(ins), i)
+    L.ro_inflights_free_to(C.byref(ins), 12)
+    assert _state(ins, buf, 10) == (3, 2, [10, 11, 12, 13, 14, 5, 6, 7, 8, 9])
+    L.ro_inflights_free_to(C.byref(ins), 14)
+    assert _state(ins, buf, 10) == (5, 0, [10, 11, 12, 13, 14, 5, 6, 7, 8, 9])
+
+
+def test_inflight_free_first_one():
+    ins, buf = _ins(10)
+    for i in range(10):
+        L.ro_inflights_add(C.byref(ins), i)
+    L.ro_inflights_free_first_one(C.byref(ins))
+    assert _state(ins, buf, 10) == (1, 9, list(range(10)))
+
+
+def test_arena_inflights_follow_the_messages():
+    """The window through the arena functions: update_state adds (progress.rs:231-236), an accepted append response
+    frees up to its index (raft.rs:1742), a heartbeat response frees the first entry of a full window (raft.rs:1796-1798),
+    a state change resets (progress.rs:75-80); INS_FULL mirrors ins.full() -- test_raft_flow_control.rs:26-98
+    (test_msg_app_flow_control_full / _move_forward) in miniature."""
+    c = O.enable_inflights(one_group([20, 4], last_index=20), 3)
+    c.pflags[1, 0] = REPL
+    e = np.zeros(1, dtype=[("group", "<u4"), ("peer_slot", "u1"), ("flags", "u1"), ("reserved", "<u2"), ("next_idx", "<u8")])
+    e["peer_slot"] = 1
+    for last in (5, 6, 7):
+        e["next_idx"] = last
+        assert O.arena_update_state(c, e).tolist() == [1]
+    assert c.ins_meta[1, 0] == (3 << 16) and c.ins_buf[1, 0].tolist() == [5, 6, 7] and c.pflags[1, 0] & O.PF_INS_FULL
+    e["next_idx"] = 8
+    assert O.arena_update_state(c, e).tolist() == [0xFF] and c.next_idx[1, 0] == 8      # add on a full window panics: nothing changes
+    r = rec(0, 1, 6, commit=0)
+    assert O.arena_apply(c, r, mode=0)[0] == O.RES_OK | O.RES_OLD_PAUSED                 # was paused: the window was full
+    assert c.ins_meta[1, 0] == (2 | (1 << 16)) and not (c.pflags[1, 0] & O.PF_INS_FULL)  # freed 5 and 6: start 2, count 1
+    for last in (8, 9):
+        e["next_idx"] = last
+        O.arena_update_state(c, e)
+    assert c.pflags[1, 0] & O.PF_INS_FULL and c.ins_buf[1, 0].tolist() == [8, 9, 7]
+    assert O.arena_apply_heartbeat(c, hb(0, 1))[0] & O.RES_OK
+    assert c.ins_meta[1, 0] == (0 | (2 << 16)) and not (c.pflags[1, 0] & O.PF_INS_FULL) # free_first_one: 7 is gone
+    rej = rec(0, 1, 9, reject=True, hint=5)
+    O.arena_apply(c, rej, mode=0)                                                         # Replicate -> Probe: ins.reset()
+    assert (c.pflags[1, 0] & 3) == PROBE and c.ins_meta[1, 0] == 0

@@ -82,7 +82,8 @@ uint32_t raftgpu_abi_version(void);
 #define RAFTGPU_PF_STATE_MASK 0x03u
 #define RAFTGPU_PF_PAUSED 0x04u        /* Progress::paused, progress.rs:24 */
 #define RAFTGPU_PF_RECENT_ACTIVE 0x08u /* Progress::recent_active, progress.rs:41 */
-#define RAFTGPU_PF_INS_FULL 0x10u      /* host-maintained copy of Inflights::full(), inflights.rs:54-56 */
+#define RAFTGPU_PF_INS_FULL 0x10u      /* Inflights::full(), inflights.rs:54-56: reported by the host, or (with
+                                          raftgpu_arena_enable_inflights) kept by the device */
 
 /* per-group meta word (column RAFTGPU_COL_META): the tracker::Configuration
  * (tracker.rs:37-92) as bit masks over peer slots. */
@@ -173,7 +174,8 @@ enum {
     RAFTGPU_COL_TERM_START = 10,          /* u64 [cap] */
     RAFTGPU_COL_LAST_INDEX = 11,          /* u64 [cap] */
     RAFTGPU_COL_TERM = 12,                /* u64 [cap]  Raft::term (raft.rs:227), 0 = unknown; only the wire path reads it */
-    RAFTGPU_COL__COUNT = 13
+    RAFTGPU_COL_INS_META = 13,            /* u32 [SLOTS][cap]  Inflights start | count << 16 (raftgpu_arena_enable_inflights) */
+    RAFTGPU_COL__COUNT = 14
 };
 
 typedef struct {
@@ -288,7 +290,14 @@ enum {
     RAFTGPU_POP_RESUME = 10,              /*                                              :219-222 */
     RAFTGPU_POP_PAUSE = 11,               /*                                              :225-228 */
     RAFTGPU_POP_UPDATE_STATE = 12,        /* (last)                                       :231-243 */
-    RAFTGPU_POP_RESET = 13                /* (next_idx)                                   :82-92   */
+    RAFTGPU_POP_RESET = 13,               /* (next_idx)                                   :82-92   */
+    /* Inflights (src/tracker/inflights.rs) of the peer's window, arenas with raftgpu_arena_enable_inflights only
+     * (*out_result = -3 otherwise) */
+    RAFTGPU_POP_INS_ADD = 14,             /* (inflight); -1 where the reference panics    inflights.rs:65-82 */
+    RAFTGPU_POP_INS_FREE_TO = 15,         /* (to)                                         :85-110  */
+    RAFTGPU_POP_INS_FREE_FIRST_ONE = 16,  /*                                              :113-116 */
+    RAFTGPU_POP_INS_RESET = 17,           /*                                              :119-123 */
+    RAFTGPU_POP_INS_FULL = 18             /*                                              :54-56   */
 };
 int32_t raftgpu_progress_op(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot, int32_t op,
                             uint64_t a0, uint64_t a1, uint64_t a2, int32_t *out_result);
@@ -646,6 +655,23 @@ int32_t raftgpu_heartbeat_resp(raftgpu_arena *arena, const raftgpu_append_resp *
 int32_t raftgpu_update_state_device(raftgpu_arena *arena, void *stream, const raftgpu_send_entry *d_entries, uint64_t n,
                                     uint8_t *d_results);
 int32_t raftgpu_update_state(raftgpu_arena *arena, const raftgpu_send_entry *entries, uint64_t n, uint8_t *results);
+
+/* ---- Inflights on the device --------------------------- */
+
+/* Keep every peer's Inflights window (src/tracker/inflights.rs:19-110: the last index of each in-flight MsgAppend, a
+ * ring of Config::max_inflight_msgs entries, config.rs:112) in HBM, so that nothing about flow control is left to
+ * per-message host work: raftgpu_update_state adds (progress.rs:231-236), an accepted append response frees up to
+ * its index (raft.rs:1742), a heartbeat response frees the first entry of a full window (raft.rs:1796-1798), every
+ * state change resets (progress.rs:75-80), and RAFTGPU_PF_INS_FULL -- what Progress::is_paused reads in Replicate
+ * state -- mirrors ins.full() (raftgpu_progress.ins_full is then an output only).  Call before groups are
+ * allocated.  Memory: 8 slots x max_groups x max_inflight x 8 bytes (256 entries: 16 KB per group), which is why
+ * it is opt-in.  With windows on, steps run through the scatter kernels (the fused tile kernels keep their rows in
+ * shared memory and do not carry the rings): raftgpu_step_sorted_device / raftgpu_step_compact_device return
+ * RAFTGPU_ERR_INVALID, every raftgpu_step_begin_* form works. */
+int32_t raftgpu_arena_enable_inflights(raftgpu_arena *arena, uint32_t max_inflight);
+/* One peer's window: *start, *count (inflights.rs:21-23) and, when buffer != NULL, its `capacity` ring entries. */
+int32_t raftgpu_inflights_get(raftgpu_arena *arena, uint32_t group, uint32_t peer_slot, uint32_t *start, uint32_t *count,
+                              uint64_t *buffer, uint32_t capacity);
 
 /* ---- votes ----------------------------------------- */
 

@@ -37,11 +37,12 @@ STEP_READ_COMMITTED, STEP_READ_RESULTS, STEP_ASYNC, STEP_RAW = 0x1, 0x2, 0x4, 0x
 BULK_SORTED = 0x1
 (POP_MAYBE_UPDATE, POP_MAYBE_DECR_TO, POP_UPDATE_COMMITTED, POP_OPTIMISTIC_UPDATE, POP_BECOME_PROBE,
  POP_BECOME_REPLICATE, POP_BECOME_SNAPSHOT, POP_SNAPSHOT_FAILURE, POP_MAYBE_SNAPSHOT_ABORT, POP_IS_PAUSED,
- POP_RESUME, POP_PAUSE, POP_UPDATE_STATE, POP_RESET) = range(14)
+ POP_RESUME, POP_PAUSE, POP_UPDATE_STATE, POP_RESET, POP_INS_ADD, POP_INS_FREE_TO, POP_INS_FREE_FIRST_ONE,
+ POP_INS_RESET, POP_INS_FULL) = range(19)
 
 (COL_MATCHED, COL_NEXT_IDX, COL_PEER_COMMITTED, COL_PENDING_SNAPSHOT, COL_PENDING_REQ_SNAPSHOT,
  COL_COMMIT_GROUP_ID, COL_PFLAGS, COL_VOTES, COL_META, COL_COMMITTED, COL_TERM_START,
- COL_LAST_INDEX, COL_TERM) = range(13)
+ COL_LAST_INDEX, COL_TERM, COL_INS_META) = range(14)
 WIRE_OK, WIRE_SKIP_TYPE, WIRE_TERM, WIRE_NEEDS_LOG, WIRE_MALFORMED, WIRE_DUP = range(6)
 
 APPEND_RESP_DTYPE = np.dtype(
@@ -266,6 +267,8 @@ def lib() -> C.CDLL:
             "raftgpu_step_send_list": ([vp, vp, u64, C.POINTER(u64)], i32),
             "raftgpu_vote_result": ([vp, u32, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)], i32),
             "raftgpu_group_set_term": ([vp, u32, u64], i32),
+            "raftgpu_arena_enable_inflights": ([vp, u32], i32),
+            "raftgpu_inflights_get": ([vp, u32, u32, C.POINTER(u32), C.POINTER(u32), vp, u32], i32),
             "raftgpu_heartbeat_resp_device": ([vp, vp, vp, u64, vp, vp], i32),
             "raftgpu_heartbeat_resp": ([vp, vp, u64, vp], i32),
             "raftgpu_update_state_device": ([vp, vp, vp, u64, vp], i32),
@@ -671,6 +674,19 @@ class Arena:
 
     def step_begin(self, flags=0):
         self._ck(self._L.raftgpu_step_begin(self._h, flags), "step_begin")
+
+    # -- Inflights on the device
+    def enable_inflights(self, max_inflight: int):
+        self._ck(self._L.raftgpu_arena_enable_inflights(self._h, max_inflight), "arena_enable_inflights")
+        self.ins_cap = max_inflight
+
+    def inflights_get(self, g, slot):
+        """(start, count, ring u64[cap]) of one peer's window."""
+        st, cnt = C.c_uint32(), C.c_uint32()
+        buf = np.zeros(self.ins_cap, dtype=np.uint64)
+        self._ck(self._L.raftgpu_inflights_get(self._h, g, slot, C.byref(st), C.byref(cnt), buf.ctypes.data, self.ins_cap),
+                 "inflights_get")
+        return st.value, cnt.value, buf
 
     # -- heartbeat responses / update_state (SURVEY 8(f) ranks 3 and 2)
     def heartbeat_resp(self, recs: np.ndarray) -> np.ndarray:

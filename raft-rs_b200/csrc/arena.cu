@@ -501,6 +501,8 @@ void destroy(raftgpu_arena *a) {
     cudaFree(c.term_start);
     cudaFree(c.last_index);
     cudaFree(c.term);
+    cudaFree(c.ins_meta);
+    cudaFree(c.ins_buf);
     cudaFree(a->d_wire_first);
     cudaFree(a->d_counters);
     cudaFree(a->d_scratch);
@@ -716,6 +718,10 @@ bool column_desc(raftgpu_arena *a, int32_t col, ColumnDesc *d) {
     case RAFTGPU_COL_TERM_START: *d = {c.term_start, 8, false}; return true;
     case RAFTGPU_COL_LAST_INDEX: *d = {c.last_index, 8, false}; return true;
     case RAFTGPU_COL_TERM: *d = {c.term, 8, false}; return true;
+    case RAFTGPU_COL_INS_META:
+        if (!c.ins_cap) return false;
+        *d = {c.ins_meta, 4, true};
+        return true;
     default: return false;
     }
 }

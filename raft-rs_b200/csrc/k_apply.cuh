@@ -9,9 +9,10 @@ struct Cell {
 };
 
 // progress.rs:75-80 reset_state: paused = false, pending_snapshot = 0, state, ins.reset()
-__device__ __forceinline__ void reset_state(Cell &p, uint32_t state, uint64_t *pending_snapshot) {
+__device__ __forceinline__ void reset_state(const Columns &c, size_t cell, Cell &p, uint32_t state, uint64_t *pending_snapshot) {
     p.flags &= ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK);
     p.flags |= state;
+    ins_reset(c, cell);  // ins.reset()
     // a plain store, not "if non-zero then clear": the cold column would otherwise cost a dependent
     // HBM read on every state transition (and, in the fused kernel, stall the tile's barrier)
     *pending_snapshot = 0;
@@ -238,7 +239,7 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs
                 res = RAFTGPU_RES_OK | RAFTGPU_RES_SEND;
                 if (state == RAFTGPU_STATE_REPLICATE) {
                     // raft.rs:1716-1718 become_probe (progress.rs:95-107, not Snapshot)
-                    reset_state(pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
+                    reset_state(c, cell, pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
                     pr.next_idx = pr.matched + 1;
                 }
             }
@@ -260,17 +261,18 @@ __device__ __forceinline__ uint32_t apply_one(const Columns &c, const void *recs
                 res = RAFTGPU_RES_OK | (old_paused ? RAFTGPU_RES_OLD_PAUSED : 0u);
                 if (state == RAFTGPU_STATE_PROBE) {
                     // raft.rs:1730 become_replicate, progress.rs:110-114
-                    reset_state(pr, RAFTGPU_STATE_REPLICATE, &c.pending_snapshot[cell]);
+                    reset_state(c, cell, pr, RAFTGPU_STATE_REPLICATE, &c.pending_snapshot[cell]);
                     pr.next_idx = pr.matched + 1;
                 } else if (state == RAFTGPU_STATE_SNAPSHOT) {
                     // raft.rs:1731-1741 maybe_snapshot_abort -> become_probe
                     const uint64_t pending = c.pending_snapshot[cell];
                     if (pr.matched >= pending) {  // progress.rs:131-134
-                        reset_state(pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
+                        reset_state(c, cell, pr, RAFTGPU_STATE_PROBE, &c.pending_snapshot[cell]);
                         pr.next_idx = umax64(pr.matched + 1, pending + 1);  // :99-102
                     }
-                }
-                // Replicate: pr.ins.free_to(m.index) -- Inflights stays host-side
+                } else if (c.ins_cap) {
+                    ins_free_to(c, cell, index, pr.flags);  // raft.rs:1742 Replicate: pr.ins.free_to(m.index)
+                }  // (without device-side windows the Inflights ring is the host's)
             }
         }
     }

@@ -19,6 +19,12 @@ struct Columns {
     uint64_t *term_start;
     uint64_t *last_index;
     uint64_t *term;  // Raft::term, 0 = unknown (wire path only)
+    // Inflights on the device (raftgpu_arena_enable_inflights): ins_cap = window size
+    // (Config::max_inflight_msgs), 0 = off (INS_FULL is then the host's to report); ins_meta [kSlots][cap] =
+    // start | count << 16 (inflights.rs:21-23); ins_buf [kSlots][cap][ins_cap] the rings
+    uint32_t ins_cap;
+    uint32_t *ins_meta;
+    uint64_t *ins_buf;
 };
 
 enum Counter : int {
@@ -41,6 +47,48 @@ __device__ __forceinline__ void prefetch_l2(const void *p) {
 
 __device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint64_t umax64(uint64_t a, uint64_t b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------
+// Inflights (src/tracker/inflights.rs) of one cell, when the arena keeps the windows on the device.  The flag bit
+// RAFTGPU_PF_INS_FULL mirrors ins.full() (what Progress::is_paused reads, progress.rs:213): every function
+// takes the caller's copy of the flag byte and keeps the bit right.
+__device__ __forceinline__ void ins_reset(const Columns &c, size_t cell) {  // :119-123
+    if (c.ins_cap) c.ins_meta[cell] = 0;
+}
+// :85-110 free_to
+__device__ __noinline__ void ins_free_to(const Columns &c, size_t cell, uint64_t to, uint32_t &flags) {
+    const uint32_t m = c.ins_meta[cell];
+    uint32_t start = m & 0xffffu, count = m >> 16;
+    const uint64_t *ring = c.ins_buf + cell * c.ins_cap;
+    if (count == 0 || to < ring[start]) return;  // out of the left side of the window
+    uint32_t i = 0, idx = start;
+    while (i < count) {
+        if (to < ring[idx]) break;  // found the first large inflight
+        idx += 1;
+        if (idx >= c.ins_cap) idx -= c.ins_cap;
+        i += 1;
+    }
+    c.ins_meta[cell] = idx | ((count - i) << 16);
+    if (i) flags &= ~RAFTGPU_PF_INS_FULL;
+}
+// :113-116 free_first_one
+__device__ __forceinline__ void ins_free_first_one(const Columns &c, size_t cell, uint32_t &flags) {
+    const uint32_t m = c.ins_meta[cell];
+    if ((m >> 16) == 0) return;
+    ins_free_to(c, cell, c.ins_buf[cell * c.ins_cap + (m & 0xffffu)], flags);
+}
+// :65-82 add; false where the reference panics (the window is full)
+__device__ __forceinline__ bool ins_add(const Columns &c, size_t cell, uint64_t inflight, uint32_t &flags) {
+    const uint32_t m = c.ins_meta[cell];
+    const uint32_t start = m & 0xffffu, count = m >> 16;
+    if (count == c.ins_cap) return false;
+    uint32_t next = start + count;
+    if (next >= c.ins_cap) next -= c.ins_cap;
+    c.ins_buf[cell * c.ins_cap + next] = inflight;
+    c.ins_meta[cell] = start | ((count + 1) << 16);
+    if (count + 1 == c.ins_cap) flags |= RAFTGPU_PF_INS_FULL;
+    return true;
+}
 
 // ---------------------------------------------------------------------------
 // MajorityConfig::committed_index without group commit (majority.rs:70-101):

@@ -128,7 +128,12 @@ heartbeat_resp_kernel(Columns c, const raftgpu_append_resp *__restrict__ recs, u
                     const size_t cell = static_cast<size_t>(slot) * c.cap + g;
                     const uint32_t f0 = c.pflags[cell];
                     uint32_t f = (f0 | RAFTGPU_PF_RECENT_ACTIVE) & ~RAFTGPU_PF_PAUSED;          // :1792-1793
-                    if ((f0 & RAFTGPU_PF_STATE_MASK) == RAFTGPU_STATE_REPLICATE) f &= ~RAFTGPU_PF_INS_FULL;  // :1796-1798
+                    if ((f0 & RAFTGPU_PF_STATE_MASK) == RAFTGPU_STATE_REPLICATE) {  // :1796-1798
+                        if (!c.ins_cap)
+                            f &= ~RAFTGPU_PF_INS_FULL;  // host-side windows: a full one that loses an entry is not full
+                        else if (f0 & RAFTGPU_PF_INS_FULL)
+                            ins_free_first_one(c, cell, f);
+                    }
                     if (commit > c.peer_committed[cell]) c.peer_committed[cell] = commit;      // :1791
                     if (f != f0) c.pflags[cell] = static_cast<uint8_t>(f);
                     res = RAFTGPU_RES_OK;
@@ -165,9 +170,15 @@ update_state_kernel(Columns c, const raftgpu_send_entry *__restrict__ e, uint64_
             const uint32_t f0 = c.pflags[cell];
             const uint32_t state = f0 & RAFTGPU_PF_STATE_MASK;
             res = 1;
-            if (state == RAFTGPU_STATE_REPLICATE)
-                c.next_idx[cell] = last + 1;                                      // :233-236 optimistic_update
-            else if (state == RAFTGPU_STATE_PROBE)
+            if (state == RAFTGPU_STATE_REPLICATE) {
+                uint32_t f = f0;
+                if (c.ins_cap && !ins_add(c, cell, last, f)) {
+                    res = 0xffu;                                                  // ins.add on a full window panics
+                } else {
+                    c.next_idx[cell] = last + 1;                                  // :233-236 optimistic_update
+                    if (f != f0) c.pflags[cell] = static_cast<uint8_t>(f);
+                }
+            } else if (state == RAFTGPU_STATE_PROBE)
                 c.pflags[cell] = static_cast<uint8_t>(f0 | RAFTGPU_PF_PAUSED);    // :237 pause()
             else
                 res = 0xffu;                                                      // :238-241 panic!
@@ -239,6 +250,7 @@ __global__ void conf_kernel(Columns c, uint32_t g, uint32_t new_meta, uint32_t a
             c.commit_group_id[cell] = 0;
             c.pflags[cell] = add ? RAFTGPU_PF_RECENT_ACTIVE : 0;  // tracker.rs:385-389
             c.votes[cell] = 0;
+            ins_reset(c, cell);  // Inflights::new(max_inflight), progress.rs:70
         }
     }
     c.meta[g] = new_meta;
@@ -258,6 +270,7 @@ __global__ void reset_kernel(Columns c, uint32_t g, uint64_t term_start, uint64_
         c.pending_snapshot[cell] = 0;
         c.pending_req_snapshot[cell] = RAFTGPU_INVALID_INDEX;
         c.pflags[cell] = RAFTGPU_STATE_PROBE;
+        ins_reset(c, cell);  // progress.rs:91 ins.reset()
         c.votes[cell] = 0;  // prs.reset_votes(), raft.rs:953
         if ((meta & RAFTGPU_META_HAS_SELF) && RAFTGPU_META_SELF(meta) == static_cast<uint32_t>(s)) {
             c.matched[cell] = persisted;         // raft.rs:967
@@ -279,6 +292,7 @@ __global__ void become_leader_kernel(Columns c, uint32_t g) {
             (c.pflags[cell] & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) |
             RAFTGPU_STATE_REPLICATE);
         c.pending_snapshot[cell] = 0;
+        ins_reset(c, cell);
         c.next_idx[cell] = c.matched[cell] + 1;  // progress.rs:110-114
     }
     const uint64_t li = c.last_index[g] + 1;  // raft.rs:1192 append_entry(&mut [Entry::default()])
@@ -313,10 +327,11 @@ __global__ void progress_set_kernel(Columns c, uint32_t g, uint32_t s, raftgpu_p
     c.pending_req_snapshot[cell] = p.pending_request_snapshot;
     c.commit_group_id[cell] = p.commit_group_id;
     c.peer_committed[cell] = p.committed_index;
+    const bool full = c.ins_cap ? (c.ins_meta[cell] >> 16) == c.ins_cap : p.ins_full != 0;  // device windows: derived
     c.pflags[cell] = static_cast<uint8_t>((p.state & RAFTGPU_PF_STATE_MASK) |
                                           (p.paused ? RAFTGPU_PF_PAUSED : 0) |
                                           (p.recent_active ? RAFTGPU_PF_RECENT_ACTIVE : 0) |
-                                          (p.ins_full ? RAFTGPU_PF_INS_FULL : 0));
+                                          (full ? RAFTGPU_PF_INS_FULL : 0));
 }
 
 __device__ __forceinline__ uint32_t majority_vote(uint32_t mask, uint32_t yes, uint32_t no);
@@ -333,6 +348,7 @@ __global__ void progress_op_kernel(Columns c, uint32_t g, uint32_t s, int op, ui
     auto reset_st = [&](uint32_t st) {  // progress.rs:75-80
         f = (f & ~(RAFTGPU_PF_PAUSED | RAFTGPU_PF_INS_FULL | RAFTGPU_PF_STATE_MASK)) | st;
         c.pending_snapshot[cell] = 0;
+        ins_reset(c, cell);
     };
     switch (op) {
     case RAFTGPU_POP_MAYBE_UPDATE:  // progress.rs:138-150
@@ -405,9 +421,12 @@ __global__ void progress_op_kernel(Columns c, uint32_t g, uint32_t s, int op, ui
         f |= RAFTGPU_PF_PAUSED;
         break;
     case RAFTGPU_POP_UPDATE_STATE:  // progress.rs:231-243 (a0 = last); -1 where the reference panics
-        if (state == RAFTGPU_STATE_REPLICATE)
-            next = a0 + 1;  // optimistic_update; ins.add(last) is the host's
-        else if (state == RAFTGPU_STATE_PROBE)
+        if (state == RAFTGPU_STATE_REPLICATE) {
+            if (c.ins_cap && !ins_add(c, cell, a0, f))
+                ret = -1;       // ins.add on a full window panics (inflights.rs:66-68)
+            else
+                next = a0 + 1;  // optimistic_update (without device windows ins.add(last) is the host's)
+        } else if (state == RAFTGPU_STATE_PROBE)
             f |= RAFTGPU_PF_PAUSED;
         else
             ret = -1;
@@ -418,6 +437,23 @@ __global__ void progress_op_kernel(Columns c, uint32_t g, uint32_t s, int op, ui
         f = RAFTGPU_STATE_PROBE;
         c.pending_snapshot[cell] = 0;
         c.pending_req_snapshot[cell] = RAFTGPU_INVALID_INDEX;
+        ins_reset(c, cell);
+        break;
+    // Inflights (src/tracker/inflights.rs) on the cell's window; -3 when the arena keeps no windows
+    case RAFTGPU_POP_INS_ADD:  // :65-82 (a0 = inflight); -1 where the reference panics
+        ret = !c.ins_cap ? -3 : (ins_add(c, cell, a0, f) ? 0 : -1);
+        break;
+    case RAFTGPU_POP_INS_FREE_TO:  // :85-110
+        if (c.ins_cap) ins_free_to(c, cell, a0, f); else ret = -3;
+        break;
+    case RAFTGPU_POP_INS_FREE_FIRST_ONE:  // :113-116
+        if (c.ins_cap) ins_free_first_one(c, cell, f); else ret = -3;
+        break;
+    case RAFTGPU_POP_INS_RESET:  // :119-123
+        if (c.ins_cap) { ins_reset(c, cell); f &= ~RAFTGPU_PF_INS_FULL; } else ret = -3;
+        break;
+    case RAFTGPU_POP_INS_FULL:  // :54-56
+        ret = !c.ins_cap ? -3 : ((c.ins_meta[cell] >> 16) == c.ins_cap);
         break;
     default:
         ret = -2;

@@ -53,12 +53,11 @@ extern "C" {
 #define RAFTGPU_ERR_PEER_NOT_FOUND (-7) /* Error::StepPeerNotFound, raw_node.rs:402-411 */
 #define RAFTGPU_ERR_COMMIT_RANGE (-8)   /* RaftLog::commit_to fatal!, raft_log.rs:291-298 */
 #define RAFTGPU_ERR_BUSY (-9)           /* a step is still in flight on this buffer */
-/* A group would need more than RAFTGPU_SLOTS peer slots (voters of both halves of a joint configuration +
- * learners + learners_next, tracker.rs:37-92).  HARD LIMIT of this engine: the reference has none
- * (majority.rs:86-93 sorts any number of voters on the heap); 8 covers 7 voters -- the largest configuration
- * the reference keeps on its stack path (majority.rs:79) -- or a 5-voter group that swaps up to three members,
- * or 5 voters + 2 learners + one joint change.  A caller that hits it keeps that group on the stock
- * ProgressTracker (the arena is per group: other groups are unaffected). */
+/* A group would need more peer slots than it has: 8 (RAFTGPU_SLOTS) for an ordinary group, 16 for a wide one
+ * (raftgpu_group_alloc_wide).  Peers = voters of both halves of a joint configuration + learners + learners_next
+ * (tracker.rs:37-92).  The reference has no limit (majority.rs:86-93 sorts any number of voters on the heap); 16
+ * covers two disjoint 7-voter sets in a joint change plus learners.  Beyond that the caller keeps the group on the
+ * stock ProgressTracker (arena groups are independent). */
 #define RAFTGPU_ERR_TOO_MANY_PEERS (-10)
 
 const char *raftgpu_strerror(int32_t status);
@@ -93,6 +92,11 @@ uint32_t raftgpu_abi_version(void);
 #define RAFTGPU_META_SELF(m) (((m) >> 24) & 0x7u)   /* slot of Raft::id */
 #define RAFTGPU_META_HAS_SELF 0x08000000u
 #define RAFTGPU_META_GROUP_COMMIT 0x10000000u       /* ProgressTracker::group_commit, tracker.rs:207 */
+/* A WIDE group (raftgpu_group_alloc_wide: up to 16 peers) occupies two consecutive group slots: `g` (even) holds
+ * peers 0..7 and carries WIDE_LO, `g + 1` holds peers 8..15 and carries WIDE_HI.  Each half's masks describe its own
+ * eight peers; quorum / votes / commit are evaluated once, on the low half, over both. */
+#define RAFTGPU_META_WIDE_LO 0x20000000u
+#define RAFTGPU_META_WIDE_HI 0x40000000u
 
 /* ---- plain data types --------------------------------------------------- */
 typedef struct raftgpu_arena raftgpu_arena; /* opaque; owns all device + pinned memory */
@@ -218,8 +222,8 @@ typedef struct {
 
 /* ProgressTracker::with_capacity (tracker.rs:217-236) for `max_groups` trackers
  * at once: allocates every column in HBM plus the pinned staging buffers.
- * slots_per_group must be RAFTGPU_SLOTS (8): any other value is RAFTGPU_ERR_TOO_MANY_PEERS (16-slot arenas are
- * not built; see that code).  ring_records = capacity of each of
+ * slots_per_group must be RAFTGPU_SLOTS (8): the unit of the arena is the 8-slot group, and a group that needs up
+ * to 16 peers takes two of them (raftgpu_group_alloc_wide); any other value is RAFTGPU_ERR_TOO_MANY_PEERS.  ring_records = capacity of each of
  * the `n_rings` host staging rings (0 = default). */
 int32_t raftgpu_arena_create(int32_t device, uint32_t max_groups, uint32_t slots_per_group,
                              uint32_t n_rings, uint32_t ring_records, raftgpu_arena **out);
@@ -233,6 +237,15 @@ const char *raftgpu_last_error(const raftgpu_arena *arena);
 /* Raft::new (raft.rs:318-400) / drop: one slot per ProgressTracker. */
 int32_t raftgpu_group_alloc(raftgpu_arena *arena, uint32_t *out_group);
 int32_t raftgpu_group_alloc_range(raftgpu_arena *arena, uint32_t n, uint32_t *out_first);
+/* A WIDE group: up to 16 peer slots (a joint configuration of large voter sets with learners; the reference has no
+ * limit, majority.rs:86-93).  It occupies two consecutive group slots: *out_group (even) and *out_group + 1.  Every
+ * single-group call takes the group id with peer slots 0..15 and 16-bit masks; in RECORDS (and send-list entries,
+ * wire frames, column IO) peer 8 + s of wide group g is addressed as (group g + 1, slot s) -- the per-cell paths do
+ * not know about wide groups at all.  Quorum, votes and Raft::maybe_commit are evaluated once, on the low half, over
+ * both halves' peers; the advanced bit and the commit index are the low half's.  While an arena holds wide groups its
+ * steps run through the scatter + recompute kernels (the fused tile kernel evaluates 8-slot groups); a 17th peer is
+ * RAFTGPU_ERR_TOO_MANY_PEERS. */
+int32_t raftgpu_group_alloc_wide(raftgpu_arena *arena, uint32_t *out_group);
 int32_t raftgpu_group_free(raftgpu_arena *arena, uint32_t group);
 
 /* ProgressTracker::apply_conf (tracker.rs:380-397) / confchange::restore
@@ -394,6 +407,9 @@ int32_t raftgpu_enqueue_append_resp(raftgpu_arena *arena, uint32_t ring,
 /* Bulk form of the above for a caller that already holds a whole batch in host memory:
  * the library splits it over its own staging threads (pinned to the GPU-local CPUs; count
  * from RAFTGPU_HOST_THREADS, default 16, at most the arena's ring count), one ring each.
+ * The records of one (group, peer) cell keep their arrival order when the group's records are contiguous in
+ * the batch (what a ready loop produces); a cell whose records are scattered through an unordered batch
+ * belongs on one ring through raftgpu_enqueue_append_resp.
  * RAFTGPU_BULK_SORTED: the caller promises records are in non-decreasing group order, which
  * lets the threads skip atomics on the per-cell bookkeeping; the order is verified and
  * RAFTGPU_ERR_INVALID returned (nothing is applied; call raftgpu_step to discard) if not. */
@@ -481,7 +497,9 @@ int32_t raftgpu_step_begin_compact(raftgpu_arena *arena, const void *pinned_blob
  * works through the scatter kernel, one record per cell), then the step is submitted like
  * raftgpu_step_begin_compact.  Nothing may have been enqueued for this step.  `records` can be
  * reused as soon as the call returns.  A batch too hostile for the compact form (every record
- * escaping to the side table) goes through raftgpu_enqueue_bulk + raftgpu_step_begin instead.
+ * escaping to the side table) goes through raftgpu_enqueue_bulk + raftgpu_step_begin instead, and so does
+ * a batch with several records per cell on an arena that cannot run the fused kernel (device-side
+ * Inflights, wide groups; RAFTGPU_STEP_ASYNC is ignored on such arenas).
  * raft.rs:1663-1743 + 893-904 for a whole tick, as one call. */
 int32_t raftgpu_step_begin_records(raftgpu_arena *arena, const raftgpu_append_resp *records, uint64_t n,
                                    uint32_t flags);

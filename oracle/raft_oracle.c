@@ -435,20 +435,25 @@ static void store_progress(ro_arena_view *a, uint32_t slot, uint32_t g, ro_progr
  * numbers + 1 (any injective id assignment gives the same result). */
 void ro_arena_mci(const ro_arena_view *a, uint32_t g, uint64_t *out_index, int *out_use_gc) {
     uint32_t meta = a->meta[g];
-    uint32_t in = RO_META_IN(meta), out = RO_META_OUT(meta), learn = RO_META_LEARN(meta);
-    uint32_t present = in | out | learn; /* every voter / learner has a Progress */
-    uint64_t in_ids[RO_SLOTS], out_ids[RO_SLOTS], map_ids[RO_SLOTS];
-    ro_index map_idx[RO_SLOTS];
+    uint32_t halves = (meta & RO_META_WIDE_LO) ? 2 : 1; /* a wide group: peers 8..15 are the cells of g + 1 */
+    uint64_t in_ids[2 * RO_SLOTS], out_ids[2 * RO_SLOTS], map_ids[2 * RO_SLOTS];
+    ro_index map_idx[2 * RO_SLOTS];
     size_t n_in = 0, n_out = 0, n_map = 0;
-    for (uint32_t s = 0; s < RO_SLOTS; s++) {
-        if (in & (1u << s)) in_ids[n_in++] = s + 1;
-        if (out & (1u << s)) out_ids[n_out++] = s + 1;
-        if (present & (1u << s)) {
-            size_t c = cell(a, s, g);
-            map_ids[n_map] = s + 1;
-            map_idx[n_map].index = a->matched[c];           /* tracker.rs:186 */
-            map_idx[n_map].group_id = a->commit_group_id[c]; /* tracker.rs:187 */
-            n_map++;
+    for (uint32_t h = 0; h < halves; h++) {
+        uint32_t m = a->meta[g + h];
+        uint32_t in = RO_META_IN(m), out = RO_META_OUT(m), learn = RO_META_LEARN(m);
+        uint32_t present = in | out | learn; /* every voter / learner has a Progress */
+        for (uint32_t s = 0; s < RO_SLOTS; s++) {
+            uint64_t id = 8 * h + s + 1;
+            if (in & (1u << s)) in_ids[n_in++] = id;
+            if (out & (1u << s)) out_ids[n_out++] = id;
+            if (present & (1u << s)) {
+                size_t c = cell(a, s, g + h);
+                map_ids[n_map] = id;
+                map_idx[n_map].index = a->matched[c];           /* tracker.rs:186 */
+                map_idx[n_map].group_id = a->commit_group_id[c]; /* tracker.rs:187 */
+                n_map++;
+            }
         }
     }
     ro_ack_indexer l = {map_ids, map_idx, n_map};
@@ -456,19 +461,41 @@ void ro_arena_mci(const ro_arena_view *a, uint32_t g, uint64_t *out_index, int *
                              out_index, out_use_gc);
 }
 
+/* the leader's own Progress cell: (slot, group slot) -- in whichever half of a wide group it lives */
+static int self_cell(const ro_arena_view *a, uint32_t g, size_t *c) {
+    uint32_t halves = (a->meta[g] & RO_META_WIDE_LO) ? 2 : 1;
+    for (uint32_t h = 0; h < halves; h++) {
+        uint32_t m = a->meta[g + h];
+        if (m & RO_META_HAS_SELF) {
+            *c = cell(a, RO_META_SELF(m), g + h);
+            return 1;
+        }
+    }
+    return 0;
+}
+
+/* both halves of a wide group carry the group's log bounds and commit index */
+static void wide_merge(ro_arena_view *a, uint32_t g) {
+    if (!(a->meta[g] & RO_META_WIDE_LO)) return;
+    uint64_t li = a->last_index[g] > a->last_index[g + 1] ? a->last_index[g] : a->last_index[g + 1];
+    a->last_index[g] = a->last_index[g + 1] = li;
+}
+
 /* raft.rs:893-904 with raft_log.rs:487-499 in range form. */
 int ro_arena_maybe_commit(ro_arena_view *a, uint32_t g) {
     uint64_t mci;
     int gc;
+    if (a->meta[g] & RO_META_WIDE_HI) return 0; /* not a group of its own */
     ro_arena_mci(a, g, &mci, &gc);
+    wide_merge(a, g);
     /* raft_log.rs:488: max_index > committed && term(max_index) == term.
      * On a leader the entries of its own term are exactly
      * [term_start, last_index] and term() is 0 above last_index. */
     if (mci > a->committed[g] && mci >= a->term_start[g] && mci <= a->last_index[g]) {
         a->committed[g] = mci; /* commit_to: mci <= last_index so no panic */
-        uint32_t meta = a->meta[g];
-        if (meta & RO_META_HAS_SELF) { /* raft.rs:896-900 */
-            size_t c = cell(a, RO_META_SELF(meta), g);
+        if (a->meta[g] & RO_META_WIDE_LO) a->committed[g + 1] = mci;
+        size_t c;
+        if (self_cell(a, g, &c)) { /* raft.rs:896-900 */
             if (mci > a->peer_committed[c]) a->peer_committed[c] = mci;
         }
         return 1;
@@ -528,7 +555,7 @@ uint8_t ro_arena_handle_append_response(ro_arena_view *a, const ro_append_resp *
             res |= RO_RES_OK;
             store_progress(a, slot, g, &pr);
             if (per_message_commit) {
-                int adv = ro_arena_maybe_commit(a, g);
+                int adv = ro_arena_maybe_commit(a, (meta & RO_META_WIDE_HI) ? g - 1 : g);
                 if (advanced) *advanced = adv;
             }
         } else {
@@ -572,7 +599,7 @@ uint8_t ro_arena_handle_append_response(ro_arena_view *a, const ro_append_resp *
     }
     store_progress(a, slot, g, &pr);
     if (per_message_commit) { /* :1745 */
-        int adv = ro_arena_maybe_commit(a, g);
+        int adv = ro_arena_maybe_commit(a, (meta & RO_META_WIDE_HI) ? g - 1 : g);
         if (advanced) *advanced = adv;
     }
     return res;
@@ -648,7 +675,7 @@ uint64_t ro_arena_recompute(ro_arena_view *a, uint32_t first, uint32_t n, uint32
                             uint64_t *mci_out, uint8_t *gc_out) {
     uint64_t advanced = 0;
     for (uint32_t g = first; g < first + n; g++) {
-        if (mci_out || gc_out) {
+        if ((mci_out || gc_out) && !(a->meta[g] & RO_META_WIDE_HI)) {
             uint64_t mci;
             int gc;
             ro_arena_mci(a, g, &mci, &gc);
@@ -670,25 +697,30 @@ uint64_t ro_arena_recompute(ro_arena_view *a, uint32_t first, uint32_t n, uint32
 /* tracker.rs:313-340 (tally_votes) with the joint vote_result. */
 int ro_arena_vote_result(const ro_arena_view *a, const uint8_t *votes, uint32_t g,
                          uint32_t *granted, uint32_t *rejected) {
-    uint32_t meta = a->meta[g];
-    uint32_t in = RO_META_IN(meta), out = RO_META_OUT(meta);
-    uint64_t in_ids[RO_SLOTS], out_ids[RO_SLOTS], v_ids[RO_SLOTS];
-    uint8_t v_vote[RO_SLOTS];
+    if (a->meta[g] & RO_META_WIDE_HI) g--; /* both halves of a wide group report the group's result */
+    uint32_t halves = (a->meta[g] & RO_META_WIDE_LO) ? 2 : 1;
+    uint64_t in_ids[2 * RO_SLOTS], out_ids[2 * RO_SLOTS], v_ids[2 * RO_SLOTS];
+    uint8_t v_vote[2 * RO_SLOTS];
     size_t n_in = 0, n_out = 0, n_v = 0;
     uint32_t gr = 0, rj = 0;
-    for (uint32_t s = 0; s < RO_SLOTS; s++) {
-        if (in & (1u << s)) in_ids[n_in++] = s + 1;
-        if (out & (1u << s)) out_ids[n_out++] = s + 1;
-        uint8_t v = votes[cell(a, s, g)];
-        if (v) {
-            v_ids[n_v] = s + 1;
-            v_vote[n_v] = (v == 2);
-            n_v++;
-            if ((in | out) & (1u << s)) { /* tracker.rs:320-322: only voters count */
-                if (v == 2)
-                    gr++;
-                else
-                    rj++;
+    for (uint32_t h = 0; h < halves; h++) {
+        uint32_t meta = a->meta[g + h];
+        uint32_t in = RO_META_IN(meta), out = RO_META_OUT(meta);
+        for (uint32_t s = 0; s < RO_SLOTS; s++) {
+            uint64_t id = 8 * h + s + 1;
+            if (in & (1u << s)) in_ids[n_in++] = id;
+            if (out & (1u << s)) out_ids[n_out++] = id;
+            uint8_t v = votes[cell(a, s, g + h)];
+            if (v) {
+                v_ids[n_v] = id;
+                v_vote[n_v] = (v == 2);
+                n_v++;
+                if ((in | out) & (1u << s)) { /* tracker.rs:320-322: only voters count */
+                    if (v == 2)
+                        gr++;
+                    else
+                        rj++;
+                }
             }
         }
     }
@@ -729,8 +761,9 @@ uint64_t ro_arena_send_list(const ro_arena_view *a, uint32_t first, uint32_t n, 
                             ro_send_entry *out, uint64_t cap) {
     uint64_t k = 0;
     for (uint32_t g = first; g < first + n; g++) {
-        if (adv_bitmap && !(adv_bitmap[g >> 5] & (1u << (g & 31)))) continue;
         uint32_t meta = a->meta[g];
+        uint32_t bit = (meta & RO_META_WIDE_HI) ? g - 1 : g; /* peers 8..15 of a wide group follow the group's bit */
+        if (adv_bitmap && !(adv_bitmap[bit >> 5] & (1u << (bit & 31)))) continue;
         uint32_t peers = RO_META_IN(meta) | RO_META_OUT(meta) | RO_META_LEARN(meta);
         for (uint32_t s = 0; s < RO_SLOTS; s++) {
             if (!(peers & (1u << s))) continue;

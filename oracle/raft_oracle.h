@@ -171,6 +171,11 @@ int ro_log_maybe_commit(ro_raft_log *l, uint64_t max_index, uint64_t term); /* r
 #define RO_META_SELF(m) (((m) >> 24) & 0x7u)
 #define RO_META_HAS_SELF 0x08000000u
 #define RO_META_GROUP_COMMIT 0x10000000u
+/* A wide group (up to 16 peers) = two consecutive group slots: g (even, WIDE_LO, peers 0..7) and g + 1 (WIDE_HI,
+ * peers 8..15).  Cells are addressed per half; quorum, votes and maybe_commit are evaluated on the low half over
+ * both halves' peers (ids 1..16), and the group's log / commit columns are kept equal on both. */
+#define RO_META_WIDE_LO 0x20000000u
+#define RO_META_WIDE_HI 0x40000000u
 
 #define RO_SLOTS 8
 

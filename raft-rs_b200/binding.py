@@ -15,7 +15,7 @@ import types
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libraftgpu.so")
+LIB_PATH = os.environ.get("RAFTGPU_LIB") or os.path.join(_HERE, "libraftgpu.so")   # (RAFTGPU_LIB: experimental builds)
 SYNTH_LIB_PATH = os.path.join(_HERE, "libraftgpu_synth.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "raftgpu.h")
 SYNTH_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "raftgpu_synth.h")
@@ -216,6 +216,7 @@ def lib() -> C.CDLL:
             "raftgpu_last_error": ([vp], C.c_char_p),
             "raftgpu_group_alloc": ([vp, C.POINTER(u32)], i32),
             "raftgpu_group_alloc_range": ([vp, u32, C.POINTER(u32)], i32),
+            "raftgpu_group_alloc_wide": ([vp, C.POINTER(u32)], i32),
             "raftgpu_group_free": ([vp, u32], i32),
             "raftgpu_group_set_conf": ([vp, u32, u32, u32, u32, i32, u64], i32),
             "raftgpu_group_reset": ([vp, u32, u64, u64, u64, u64], i32),
@@ -486,6 +487,12 @@ class Arena:
     def group_alloc(self) -> int:
         g = C.c_uint32()
         self._ck(self._L.raftgpu_group_alloc(self._h, C.byref(g)), "group_alloc")
+        return g.value
+
+    def group_alloc_wide(self) -> int:
+        """A group of up to 16 peers = group slots g (even) and g + 1 (include/raftgpu.h)."""
+        g = C.c_uint32()
+        self._ck(self._L.raftgpu_group_alloc_wide(self._h, C.byref(g)), "group_alloc_wide")
         return g.value
 
     def group_alloc_range(self, n: int) -> int:

@@ -216,6 +216,8 @@ struct raftgpu_arena {
     uint64_t overflow_records = 0;
     uint32_t voter_hint = 0;                 // superset of every group's voter slots (recompute_kernel)
     int grid_recompute = 0, grid_recompute5 = 0, grid_apply = 0;  // persistent grid sizes (blocks)
+    bool rec_fallback_sorted = false;        // raftgpu_step_begin_records: the batch going to the general staging path is in group order
+    uint32_t n_wide = 0;                     // wide groups (two slots each): the fused tile kernels are not used while any exist
     uint32_t n_simple5 = 0;                  // groups whose meta is the plain 5-voter configuration
     bool force_general = false;              // RAFTGPU_FORCE_GENERAL=1: never take the simple5 kernels
     bool prefetch = false;                   // RAFTGPU_PREFETCH=1: kernels with the L2 prefetch stage
@@ -382,12 +384,55 @@ inline uint32_t div_up(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a
 // True when every group of [first, first+n) is the plain 5-voter configuration in slots 0..4
 // (no joint half, no group commit): the host's meta mirror is authoritative, so the kernels
 // specialised for that case need no per-group check.
-inline bool is_simple5(uint32_t meta) { return (meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT)) == 0x1fu; }
+inline bool is_simple5(uint32_t meta) {
+    return (meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT | RAFTGPU_META_WIDE_LO | RAFTGPU_META_WIDE_HI)) == 0x1fu;
+}
+inline bool wide_lo(const raftgpu_arena *a, uint32_t g) { return (a->h_meta[g] & RAFTGPU_META_WIDE_LO) != 0; }
+inline bool wide_hi(const raftgpu_arena *a, uint32_t g) { return (a->h_meta[g] & RAFTGPU_META_WIDE_HI) != 0; }
+// peer slot 0..15 of a wide group -> (half, slot in the half); false = no such slot in this group
+inline bool resolve_slot(const raftgpu_arena *a, uint32_t g, uint32_t slot, uint32_t *g2, uint32_t *s2) {
+    if (slot < RAFTGPU_SLOTS) {
+        *g2 = g;
+        *s2 = slot;
+        return true;
+    }
+    if (slot < 2 * RAFTGPU_SLOTS && wide_lo(a, g)) {
+        *g2 = g + 1;
+        *s2 = slot - RAFTGPU_SLOTS;
+        return true;
+    }
+    return false;
+}
 inline bool range_simple5(const raftgpu_arena *a, uint32_t first, uint32_t n) {
     return a->n_simple5 == a->hi && static_cast<uint64_t>(first) + n <= a->hi;
 }
+// Tuning / diagnostic knobs of the fused tile kernel, read once per process -- or on every launch when
+// RAFTGPU_TILE_TUNE is set (scripts/micro_tile.py sweeps them inside one process).
+//   RAFTGPU_TILE_VARIANT = <threads per consumer group><groups> (2563 = 256 x 3), _RECCAP = records staged per tile
+//   (0: read directly), _STAGES, _DEBUG (phase cycle counters), _SKIP (diagnostics, wrong results)
+struct TileKnobs {
+    int variant, cap, stages;
+    bool debug;
+    uint32_t skip;
+};
+inline TileKnobs read_tile_knobs() {
+    auto num = [](const char *name, int dflt) {
+        const char *v = getenv(name);
+        return v ? atoi(v) : dflt;
+    };
+    return TileKnobs{num("RAFTGPU_TILE_VARIANT", 2563), num("RAFTGPU_TILE_RECCAP", 0), num("RAFTGPU_TILE_STAGES", kFMaxStages),
+                     getenv("RAFTGPU_TILE_DEBUG") != nullptr, static_cast<uint32_t>(num("RAFTGPU_TILE_SKIP", 0))};
+}
+inline const TileKnobs &tile_knobs() {
+    static const bool tune = getenv("RAFTGPU_TILE_TUNE") != nullptr;
+    static TileKnobs k = read_tile_knobs();
+    if (tune) k = read_tile_knobs();
+    return k;
+}
+
 inline void set_meta(raftgpu_arena *a, uint32_t g, uint32_t meta) {
     a->n_simple5 += static_cast<uint32_t>(is_simple5(meta)) - static_cast<uint32_t>(is_simple5(a->h_meta[g]));
+    a->n_wide += ((meta & RAFTGPU_META_WIDE_LO) ? 1u : 0u) - ((a->h_meta[g] & RAFTGPU_META_WIDE_LO) ? 1u : 0u);
     a->h_meta[g] = meta;
     a->voter_hint |= voter_mask(meta);
 }
@@ -398,7 +443,7 @@ int32_t launch_recompute(raftgpu_arena *a, cudaStream_t st, uint32_t first, uint
     if (n == 0) return RAFTGPU_OK;
     const bool simple5 = range_simple5(a, first, n) && !a->force_general;
     if (simple5) hint = 0x1fu;
-    if (a->use_tma && n >= 16u * kTile && hint != 0) {
+    if (a->use_tma && a->n_wide == 0 && n >= 16u * kTile && hint != 0) {
         // TMA-fed pipeline: one persistent CTA per SM, as many stages as fit in shared memory
         const uint32_t stage_bytes =
             (static_cast<uint32_t>(__builtin_popcount(hint & 0xffu)) + 3u) * kTile * 8u + kTile * 4u;

@@ -224,12 +224,97 @@ __device__ __forceinline__ void group_mci(const Columns &c, uint32_t g, uint32_t
     }
 }
 
+// ---------------------------------------------------------------------------
+// WIDE groups (RAFTGPU_META_WIDE_LO / _HI): up to 16 peers over two consecutive group slots.  Rare (a joint change of
+// a large configuration with learners), so the code is the literal algorithm on 16 values, out of line.
+
+// MajorityConfig::committed_index over up to 16 voters: gather, stable descending insertion sort (majority.rs:95), the
+// quorum element, then -- with group commit -- the scan of majority.rs:102-123.
+__device__ __noinline__ void majority_committed_index16(const uint64_t *v, const uint64_t *gid, uint32_t mask, bool group_commit,
+                                                        uint64_t *out_index, bool *out_use_gc) {
+    if (mask == 0) {  // majority.rs:71-75
+        *out_index = UINT64_MAX;
+        *out_use_gc = true;
+        return;
+    }
+    uint64_t idx[16], grp[16];
+    int n = 0;
+    for (int s = 0; s < 16; s++)
+        if ((mask >> s) & 1u) {
+            idx[n] = v[s];
+            grp[n] = gid ? gid[s] : 0;
+            n++;
+        }
+    for (int i = 1; i < n; i++) {
+        const uint64_t xi = idx[i], xg = grp[i];
+        int j = i;
+        while (j > 0 && idx[j - 1] < xi) {
+            idx[j] = idx[j - 1];
+            grp[j] = grp[j - 1];
+            j--;
+        }
+        idx[j] = xi;
+        grp[j] = xg;
+    }
+    const int quorum = n / 2 + 1;  // util.rs:118-120
+    const uint64_t quorum_commit_index = idx[quorum - 1];
+    if (!group_commit) {  // majority.rs:99-101
+        *out_index = quorum_commit_index;
+        *out_use_gc = false;
+        return;
+    }
+    uint64_t checked_group_id = grp[quorum - 1];
+    bool single_group = true;
+    for (int i = 0; i < n; i++) {  // :105-118
+        if (grp[i] == 0) {
+            single_group = false;
+            continue;
+        }
+        if (checked_group_id == 0) {
+            checked_group_id = grp[i];
+            continue;
+        }
+        if (checked_group_id == grp[i]) continue;
+        *out_index = umin64(idx[i], quorum_commit_index);
+        *out_use_gc = true;
+        return;
+    }
+    *out_index = single_group ? quorum_commit_index : idx[n - 1];  // :119-123
+    *out_use_gc = false;
+}
+
+// maximal_committed_index of the wide group whose low half is g (tracker.rs:294-298, joint.rs:47-51)
+__device__ __noinline__ void wide_mci(const Columns &c, uint32_t g, uint32_t meta_lo, uint64_t &mci, bool &use_gc) {
+    const uint32_t meta_hi = c.meta[g + 1];
+    const uint32_t in = RAFTGPU_META_IN(meta_lo) | (RAFTGPU_META_IN(meta_hi) << 8);
+    const uint32_t out = RAFTGPU_META_OUT(meta_lo) | (RAFTGPU_META_OUT(meta_hi) << 8);
+    const uint32_t voters = in | out;
+    const bool gc = (meta_lo & RAFTGPU_META_GROUP_COMMIT) != 0;
+    uint64_t v[16], gid[16];
+    for (int s = 0; s < 16; s++) {
+        const size_t cell = static_cast<size_t>(s & 7) * c.cap + g + (s >> 3);
+        const bool member = (voters >> s) & 1u;
+        v[s] = member ? c.matched[cell] : 0ull;
+        gid[s] = (member && gc) ? c.commit_group_id[cell] : 0ull;
+    }
+    uint64_t i_idx, o_idx;
+    bool i_gc, o_gc;
+    majority_committed_index16(v, gid, in, gc, &i_idx, &i_gc);
+    majority_committed_index16(v, gid, out, gc, &o_idx, &o_gc);
+    mci = umin64(i_idx, o_idx);  // joint.rs:50
+    use_gc = i_gc && o_gc;
+}
+
 // Side-effect-free single-group query (thread 0 of one warp).
 __global__ void mci_kernel(Columns c, uint32_t g, uint64_t *out_mci, uint8_t *out_gc) {
     if (threadIdx.x != 0) return;
     uint64_t mci;
     bool use_gc;
-    group_mci(c, g, c.meta[g], mci, use_gc);
+    const uint32_t meta = c.meta[g];
+    if (meta & RAFTGPU_META_WIDE_LO)
+        wide_mci(c, g, meta, mci, use_gc);
+    else
+        group_mci(c, g, meta, mci, use_gc);
     *out_mci = mci;
     *out_gc = use_gc ? 1 : 0;
 }

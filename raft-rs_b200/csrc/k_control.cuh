@@ -11,7 +11,8 @@
 // next_idx, pending_request_snapshot of its peers) read, 16 written per entry.
 __global__ void __launch_bounds__(256)
 send_list_kernel(Columns c, uint32_t first, uint32_t n, const uint32_t *__restrict__ adv_bitmap,
-                 raftgpu_send_entry *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ count) {
+                 raftgpu_send_entry *__restrict__ out, unsigned long long capacity, unsigned long long *__restrict__ count,
+                 bool has_wide) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t base = first & ~31u;
     const uint32_t n_tiles = static_cast<uint32_t>((static_cast<uint64_t>(first - base) + n + 31) >> 5);
@@ -20,7 +21,11 @@ send_list_kernel(Columns c, uint32_t first, uint32_t n, const uint32_t *__restri
     for (uint32_t tile = warp; tile < n_tiles; tile += n_warps) {
         const uint32_t g = base + tile * 32u + lane;
         const uint32_t word = adv_bitmap ? adv_bitmap[g >> 5] : 0xffffffffu;
-        const bool sel = g >= first && g < first + n && ((word >> lane) & 1u);
+        const bool in_range = g >= first && g < first + n;
+        // the high half of a wide group (odd slot, RAFTGPU_META_WIDE_HI) follows the low half's bit: its entries name
+        // (g, slot) = the wide group's peer 8 + slot
+        const uint32_t bit = (has_wide && in_range && (lane & 1u) && (c.meta[g] & RAFTGPU_META_WIDE_HI)) ? lane - 1 : lane;
+        const bool sel = in_range && ((word >> bit) & 1u);
         uint32_t send = 0;
         uint64_t nx[kSlots], prs[kSlots];  // loaded together with the flag bytes: one round trip, not one per entry
         if (sel) {
@@ -207,14 +212,28 @@ tally_kernel(Columns c, uint32_t first, uint32_t n, uint32_t *__restrict__ out,
     const bool active = t < n;
     if (active) {
         const uint32_t g = first + static_cast<uint32_t>(t);
-        const uint32_t meta = c.meta[g];
-        const uint32_t in = RAFTGPU_META_IN(meta), outm = RAFTGPU_META_OUT(meta);
+        uint32_t meta = c.meta[g];
+        uint32_t in = RAFTGPU_META_IN(meta), outm = RAFTGPU_META_OUT(meta);
         uint32_t yes = 0, no = 0;
 #pragma unroll
         for (int s = 0; s < kSlots; s++) {
             const uint32_t v = c.votes[static_cast<size_t>(s) * c.cap + g];
             yes |= (v == 2u) << s;
             no |= (v == 1u) << s;
+        }
+        if (meta & (RAFTGPU_META_WIDE_LO | RAFTGPU_META_WIDE_HI)) {  // a wide group: both halves get the result over 16 peers
+            const uint32_t other = (meta & RAFTGPU_META_WIDE_LO) ? g + 1 : g - 1, sh_me = (meta & RAFTGPU_META_WIDE_LO) ? 0u : 8u;
+            const uint32_t mo = c.meta[other];
+            uint32_t yo = 0, no2 = 0;
+            for (int s = 0; s < kSlots; s++) {
+                const uint32_t v = c.votes[static_cast<size_t>(s) * c.cap + other];
+                yo |= (v == 2u) << s;
+                no2 |= (v == 1u) << s;
+            }
+            in = (in << sh_me) | (RAFTGPU_META_IN(mo) << (8u - sh_me));
+            outm = (outm << sh_me) | (RAFTGPU_META_OUT(mo) << (8u - sh_me));
+            yes = (yes << sh_me) | (yo << (8u - sh_me));
+            no = (no << sh_me) | (no2 << (8u - sh_me));
         }
         const uint32_t i = majority_vote(in, yes, no), o = majority_vote(outm, yes, no);
         uint32_t r;
@@ -468,14 +487,17 @@ __global__ void progress_op_kernel(Columns c, uint32_t g, uint32_t s, int op, ui
 // and quorum_recently_active (tracker.rs:346-361), which also clears recent_active.
 __global__ void quorum_kernel(Columns c, uint32_t g, int op, uint32_t arg, int32_t *out) {
     const uint32_t meta = c.meta[g];
-    const uint32_t in = RAFTGPU_META_IN(meta), outm = RAFTGPU_META_OUT(meta);
+    const bool wide = (meta & RAFTGPU_META_WIDE_LO) != 0;  // peers 8..15 live in group g + 1
+    const uint32_t meta_hi = wide ? c.meta[g + 1] : 0u;
+    const uint32_t in = RAFTGPU_META_IN(meta) | (RAFTGPU_META_IN(meta_hi) << 8);
+    const uint32_t outm = RAFTGPU_META_OUT(meta) | (RAFTGPU_META_OUT(meta_hi) << 8);
     uint32_t active = arg;
     if (op == 1) {  // quorum_recently_active(perspective_of = slot arg)
-        const uint32_t present = in | outm | RAFTGPU_META_LEARN(meta);
+        const uint32_t present = in | outm | RAFTGPU_META_LEARN(meta) | (RAFTGPU_META_LEARN(meta_hi) << 8);
         active = 0;
-        for (int s = 0; s < kSlots; s++) {
+        for (int s = 0; s < (wide ? 2 * kSlots : kSlots); s++) {
             if (!((present >> s) & 1u)) continue;
-            uint8_t *f = &c.pflags[static_cast<size_t>(s) * c.cap + g];
+            uint8_t *f = &c.pflags[static_cast<size_t>(s & 7) * c.cap + g + (s >> 3)];
             if (static_cast<uint32_t>(s) == arg) {
                 *f |= RAFTGPU_PF_RECENT_ACTIVE;  // tracker.rs:350-352
                 active |= 1u << s;
@@ -488,6 +510,17 @@ __global__ void quorum_kernel(Columns c, uint32_t g, int op, uint32_t arg, int32
     // members of the set vote yes, everyone else is missing (None)
     const uint32_t i = majority_vote(in, active, 0), o = majority_vote(outm, active, 0);
     *out = (i == RAFTGPU_VOTE_WON && o == RAFTGPU_VOTE_WON) ? 1 : 0;
+}
+
+// The two halves of a wide group share the group's log / commit columns: make them agree (a LOCAL record or a
+// single-half control-plane call may have touched one half only).
+__global__ void wide_sync_kernel(Columns c, uint32_t g) {
+    const uint64_t li = umax64(c.last_index[g], c.last_index[g + 1]);
+    const uint64_t cm = umax64(c.committed[g], c.committed[g + 1]);
+    c.last_index[g] = c.last_index[g + 1] = li;
+    c.committed[g] = c.committed[g + 1] = cm;
+    c.term_start[g + 1] = c.term_start[g];
+    c.term[g + 1] = c.term[g];
 }
 
 __global__ void group_get_kernel(Columns c, uint32_t g, raftgpu_group_state *out) {

@@ -38,7 +38,7 @@ __device__ __forceinline__ void eval_mci(const Columns &c, uint32_t g, uint32_t 
             for (int s = 0; s < kSlots; s++)
                 if ((missing >> s) & 1u) v[s] = c.matched[static_cast<size_t>(s) * c.cap + g];
         }
-        if ((meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT)) == 0x1fu) {
+        if ((meta & (0xffffu | RAFTGPU_META_GROUP_COMMIT | RAFTGPU_META_WIDE_LO | RAFTGPU_META_WIDE_HI)) == 0x1fu) {
             mci = median5(v[0], v[1], v[2], v[3], v[4]);
             use_gc = false;
         } else if (!(meta & RAFTGPU_META_GROUP_COMMIT)) {
@@ -73,6 +73,38 @@ __device__ __forceinline__ bool commit_group(const Columns &c, uint32_t g, uint3
         if (commit_out) commit_out[g] = mci;
         if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
             const size_t cell = static_cast<size_t>(RAFTGPU_META_SELF(meta)) * c.cap + g;
+            if (mci > c.peer_committed[cell]) c.peer_committed[cell] = mci;
+        }
+    }
+    return advanced;
+}
+
+// Raft::maybe_commit for the wide group whose low half is g: maximal_committed_index over both halves' peers, the
+// term / range test against the group's log bounds (a LOCAL record writes last_index on the half that holds the
+// leader's own slot: the halves are merged here -- last_index only grows between control-plane resets), and the new
+// commit index on BOTH halves (heartbeat commits and heartbeat responses read their own half's columns).
+__device__ __noinline__ bool commit_wide_group(const Columns &c, uint32_t g, uint32_t meta_lo, uint64_t *commit_out,
+                                               uint64_t *mci_out, uint8_t *gc_out) {
+    uint64_t mci;
+    bool use_gc;
+    wide_mci(c, g, meta_lo, mci, use_gc);
+    if (mci_out) mci_out[g] = mci;
+    if (gc_out) gc_out[g] = use_gc ? 1 : 0;
+    const uint64_t li = umax64(c.last_index[g], c.last_index[g + 1]);
+    if (c.last_index[g] != li) c.last_index[g] = li;
+    if (c.last_index[g + 1] != li) c.last_index[g + 1] = li;
+    const uint64_t committed = c.committed[g];
+    const bool advanced = mci > committed && mci >= c.term_start[g] && mci <= li;  // raft_log.rs:487-499
+    if (advanced) {
+        c.committed[g] = mci;
+        c.committed[g + 1] = mci;
+        if (commit_out) commit_out[g] = mci;
+        const uint32_t meta_hi = c.meta[g + 1];  // raft.rs:896-900: the leader's own Progress, in whichever half it lives
+        if (meta_lo & RAFTGPU_META_HAS_SELF) {
+            const size_t cell = static_cast<size_t>(RAFTGPU_META_SELF(meta_lo)) * c.cap + g;
+            if (mci > c.peer_committed[cell]) c.peer_committed[cell] = mci;
+        } else if (meta_hi & RAFTGPU_META_HAS_SELF) {
+            const size_t cell = static_cast<size_t>(RAFTGPU_META_SELF(meta_hi)) * c.cap + g + 1;
             if (mci > c.peer_committed[cell]) c.peer_committed[cell] = mci;
         }
     }
@@ -134,7 +166,7 @@ recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint_arg,
                 prefetch_l2(c.meta + gn);
             }
         }
-        bool advanced = false;
+        bool advanced = false, wide_hi = false;
         if (active) {
             // one batch of independent loads
             const uint32_t meta = c.meta[g];
@@ -147,11 +179,19 @@ recompute_kernel(Columns c, uint32_t first, uint32_t n, uint32_t hint_arg,
             const uint64_t last_index = c.last_index[g];
             uint64_t mci;
             bool use_gc;
-            eval_mci<kSimple5>(c, g, meta, v, hint, mci, use_gc);
-            advanced = commit_group(c, g, meta, mci, use_gc, committed, term_start, last_index, commit_out,
-                                    mci_out, gc_out);
+            if (!kSimple5 && (meta & (RAFTGPU_META_WIDE_LO | RAFTGPU_META_WIDE_HI))) {
+                // a wide group is evaluated once, on its low half, over both halves' peers; the high half is not a
+                // group of its own (its bit of the bitmap stays 0, it is not counted)
+                if (meta & RAFTGPU_META_WIDE_LO) advanced = commit_wide_group(c, g, meta, commit_out, mci_out, gc_out);
+                wide_hi = (meta & RAFTGPU_META_WIDE_HI) != 0;
+            } else {
+                eval_mci<kSimple5>(c, g, meta, v, hint, mci, use_gc);
+                advanced = commit_group(c, g, meta, mci, use_gc, committed, term_start, last_index, commit_out,
+                                        mci_out, gc_out);
+            }
         }
         publish_tile(adv_bitmap, g64, lane, active, advanced, local);
+        if (wide_hi) local[0]--;  // publish_tile counted the lane as a recompute
     }
     const int which[2] = {kCntRecomputes, kCntAdvanced};
     block_flush_counts<2>(local, which, counters, step_advanced);

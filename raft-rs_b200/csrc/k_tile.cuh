@@ -53,6 +53,7 @@ struct TileArgs {
     uint32_t *step_advanced;   // nullable
     unsigned long long *counters;
     unsigned long long *dbg;   // nullable: [8] cycle totals per phase (diagnostics, RAFTGPU_TILE_DEBUG=1)
+    uint32_t skip;             // diagnostics only (RAFTGPU_TILE_SKIP, results are WRONG): 1 no records, 2 no recompute, 4 no stores
 };
 
 // bytes of one stage for H hinted slots (shared by host and device)
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             const uint32_t ng16 = (ng + 15u) & ~15u;
             uint8_t *sb = smem + static_cast<size_t>(st) * stage_bytes;
             mbar_wait(&done_bar[st], ph);  // every lane waits: the barrier's completion orders the consumers' writes
-            for (uint32_t j = lane; j < n_out; j += 32) {
+            for (uint32_t j = lane; j < ((a.skip & 4u) ? 0u : n_out); j += 32) {
                 if (j < 4u * H) {
                     const uint32_t col = j / H, r = j % H;
                     uint32_t slot = 0, seen = 0;
@@ -214,8 +215,12 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             uint8_t *s_flags = sb + o_flags;
             const PackedRec *s_recs = reinterpret_cast<const PackedRec *>(sb + o_recs);
             const ulonglong2 *g_recs = reinterpret_cast<const ulonglong2 *>(a.recs + rbeg);
+            // direct records: this thread's first record is requested BEFORE the wait for the stage (its address does
+            // not depend on it); the loop then fetches one record ahead.  (Two ahead measured 11 % SLOWER -- 83.5 vs
+            // 75.0 us, scripts/micro_tile.py: the kernel sits at its 72-register ceiling and the consumers are bound by
+            // issue latency, not by the record reads.)
             ulonglong2 q_next = make_ulonglong2(kPkExt, 0ull);
-            if (staged == 0 && tid < cnt) q_next = g_recs[tid];  // direct records: in flight during the wait
+            if (staged == 0 && tid < cnt) q_next = g_recs[tid];
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
             if (a.dbg && tid == 0) t0 = clock64();
             mbar_wait(&full_bar[st], ph);
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                 if (a.results) a.results[rbeg + k] = static_cast<uint8_t>(res);
             };
             if (staged != 0) q_next = rec_at(tid);
-            for (uint32_t k = tid; k < cnt; k += kCT) {
+            for (uint32_t k = tid; k < ((a.skip & 1u) ? 0u : cnt); k += kCT) {
                 const ulonglong2 q = q_next;
                 q_next = rec_at(k + kCT);
                 const uint64_t w0 = q.x;
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             if (a.dbg && tid == 0) t2 = clock64();
 
             // ---- B: Raft::maybe_commit for the tile's groups (raft.rs:893-904)
-            if (tid < kFTile) {  // warp-uniform: kFTile is a multiple of 32
+            if (tid < kFTile && !(a.skip & 2u)) {  // warp-uniform: kFTile is a multiple of 32
                 const uint32_t gl = tid;
                 const bool active = gl < ng;
                 const uint32_t g = g0 + gl;

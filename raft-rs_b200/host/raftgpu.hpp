@@ -74,8 +74,13 @@ class Arena {
         if (rc == RAFTGPU_ERR_COMMIT_RANGE) throw Fatal(rc, msg);
         throw Error(rc, msg);
     }
-    // a spare group used to evaluate free-standing quorum functions on the device
-    uint32_t scratch_group() {
+    // a spare group used to evaluate free-standing quorum functions on the device; more than 8 distinct ids take a
+    // wide one (allocated only then: while an arena holds a wide group its steps skip the fused tile kernel)
+    uint32_t scratch_group(size_t n_ids = 0) {
+        if (n_ids > RAFTGPU_SLOTS) {
+            if (scratch_wide_ == UINT32_MAX) check(raftgpu_group_alloc_wide(a_, &scratch_wide_), "group_alloc_wide");
+            return scratch_wide_;
+        }
         if (scratch_ == UINT32_MAX) check(raftgpu_group_alloc(a_, &scratch_), "group_alloc");
         return scratch_;
     }
@@ -83,7 +88,7 @@ class Arena {
   private:
     explicit Arena(raftgpu_arena *a) : a_(a) {}
     raftgpu_arena *a_;
-    uint32_t scratch_ = UINT32_MAX;
+    uint32_t scratch_ = UINT32_MAX, scratch_wide_ = UINT32_MAX;
 };
 
 // quorum.rs:35-38
@@ -96,13 +101,13 @@ using AckIndexer = std::unordered_map<uint64_t, Index>;
 
 namespace detail {
 // ids -> peer slots of the scratch group (the reference's voter sets hold at most 7 ids on the
-// stack path, majority.rs:79; a joint config unions two of them; RAFTGPU_SLOTS = 8)
+// stack path, majority.rs:79; a joint config unions two of them; more than 8 distinct ids use a wide scratch group: 16 slots)
 inline std::map<uint64_t, uint32_t> slot_map(const std::set<uint64_t> &a, const std::set<uint64_t> &b) {
     std::map<uint64_t, uint32_t> m;
     for (const auto *s : {&a, &b})
         for (uint64_t id : *s)
             if (!m.count(id)) {
-                if (m.size() >= RAFTGPU_SLOTS) throw Error(RAFTGPU_ERR_TOO_MANY_PEERS, "more than RAFTGPU_SLOTS distinct voters");
+                if (m.size() >= 2 * RAFTGPU_SLOTS) throw Error(RAFTGPU_ERR_TOO_MANY_PEERS, "more than 16 distinct voters");
                 const uint32_t slot = static_cast<uint32_t>(m.size());
                 m[id] = slot;
             }
@@ -150,7 +155,7 @@ class JointConfig {
     // joint.rs:47-51
     std::pair<uint64_t, bool> committed_index(Arena &arena, bool use_group_commit, const AckIndexer &l) const {
         const auto slots = detail::slot_map(incoming.ids(), outgoing.ids());
-        const uint32_t g = arena.scratch_group();
+        const uint32_t g = arena.scratch_group(slots.size());
         raftgpu_arena *a = arena.raw();
         arena.check(raftgpu_group_set_conf(a, g, 0, 0, 0, -1, 1), "group_set_conf");
         arena.check(raftgpu_group_set_conf(a, g, detail::mask_of(incoming.ids(), slots),
@@ -172,7 +177,7 @@ class JointConfig {
     // joint.rs:56-67
     VoteResult vote_result(Arena &arena, const std::function<std::optional<bool>(uint64_t)> &check) const {
         const auto slots = detail::slot_map(incoming.ids(), outgoing.ids());
-        const uint32_t g = arena.scratch_group();
+        const uint32_t g = arena.scratch_group(slots.size());
         raftgpu_arena *a = arena.raw();
         arena.check(raftgpu_group_set_conf(a, g, 0, 0, 0, -1, 1), "group_set_conf");
         arena.check(raftgpu_group_set_conf(a, g, detail::mask_of(incoming.ids(), slots),
@@ -275,8 +280,13 @@ class ProgressRef {
 class ProgressTracker {
   public:
     // tracker.rs:211-236 new / with_capacity
-    ProgressTracker(std::shared_ptr<Arena> arena, size_t max_inflight) : arena_(std::move(arena)), max_inflight_(max_inflight) {
-        arena_->check(raftgpu_group_alloc(arena_->raw(), &group_), "group_alloc");
+    // wide = a group of up to 16 peers (raftgpu_group_alloc_wide: two consecutive group slots); the default holds 8
+    ProgressTracker(std::shared_ptr<Arena> arena, size_t max_inflight, bool wide = false)
+        : arena_(std::move(arena)), max_inflight_(max_inflight), n_slots_(wide ? 2 * RAFTGPU_SLOTS : RAFTGPU_SLOTS) {
+        if (wide)
+            arena_->check(raftgpu_group_alloc_wide(arena_->raw(), &group_), "group_alloc_wide");
+        else
+            arena_->check(raftgpu_group_alloc(arena_->raw(), &group_), "group_alloc");
     }
     ~ProgressTracker() { raftgpu_group_free(arena_->raw(), group_); }
     ProgressTracker(const ProgressTracker &) = delete;
@@ -291,6 +301,9 @@ class ProgressTracker {
     const Configuration &conf() const { return conf_; }
     size_t max_inflight() const { return max_inflight_; }
     uint32_t group() const { return group_; }
+    // how a RECORD names peer slot `slot` of this group: peers 8..15 of a wide group are the cells of group + 1
+    uint32_t record_group(uint32_t slot) const { return group_ + (slot >> 3); }
+    static uint8_t record_slot(uint32_t slot) { return static_cast<uint8_t>(slot & 7u); }
     std::optional<uint32_t> slot_of(uint64_t id) const {
         const auto it = slots_.find(id);
         return it == slots_.end() ? std::nullopt : std::optional<uint32_t>(it->second);
@@ -376,8 +389,8 @@ class ProgressTracker {
             if (ty == MapChangeType::Add) {
                 if (slots_.count(id)) continue;
                 uint32_t slot = 0;
-                while (slot < RAFTGPU_SLOTS && used_slots_ & (1u << slot)) slot++;
-                if (slot == RAFTGPU_SLOTS) throw Error(RAFTGPU_ERR_TOO_MANY_PEERS, "more than RAFTGPU_SLOTS peers in one group");
+                while (slot < n_slots_ && used_slots_ & (1u << slot)) slot++;
+                if (slot == n_slots_) throw Error(RAFTGPU_ERR_TOO_MANY_PEERS, "more peers than the group has slots (8, or 16 for a wide group)");
                 used_slots_ |= 1u << slot;
                 slots_[id] = slot;
             } else if (const auto it = slots_.find(id); it != slots_.end()) {
@@ -403,6 +416,7 @@ class ProgressTracker {
     std::shared_ptr<Arena> arena_;
     uint32_t group_ = 0;
     size_t max_inflight_;
+    uint32_t n_slots_ = RAFTGPU_SLOTS;
     bool group_commit_ = false;
     uint64_t self_id_ = INVALID_ID;
     Configuration conf_;
@@ -493,15 +507,15 @@ class MultiRaftDriver {
         const auto slot = prs.slot_of(from);
         if (!slot) throw StepPeerNotFound();  // raw_node.rs:402-411
         raftgpu_append_resp r[2] = {};
-        r[0] = {prs.group(), static_cast<uint8_t>(*slot), static_cast<uint8_t>(reject ? RAFTGPU_REC_REJECT : 0), 0, index, commit};
-        r[1] = {prs.group(), static_cast<uint8_t>(*slot), RAFTGPU_REC_EXT, 0, next_probe_index, request_snapshot};
+        r[0] = {prs.record_group(*slot), prs.record_slot(*slot), static_cast<uint8_t>(reject ? RAFTGPU_REC_REJECT : 0), 0, index, commit};
+        r[1] = {prs.record_group(*slot), prs.record_slot(*slot), RAFTGPU_REC_EXT, 0, next_probe_index, request_snapshot};
         arena_->check(raftgpu_enqueue_append_resp(arena_->raw(), ring, r, reject ? 2 : 1), "enqueue_append_resp");
     }
     // append_entry + on_persist_entries of the leader (raft.rs:974-1016)
     void local_progress(const ProgressTracker &prs, uint64_t self_id, uint64_t persisted, uint64_t last_index, uint32_t ring = 0) {
         const auto slot = prs.slot_of(self_id);
         if (!slot) throw StepPeerNotFound();
-        const raftgpu_append_resp r{prs.group(), static_cast<uint8_t>(*slot), RAFTGPU_REC_LOCAL, 0, persisted, last_index};
+        const raftgpu_append_resp r{prs.record_group(*slot), prs.record_slot(*slot), RAFTGPU_REC_LOCAL, 0, persisted, last_index};
         arena_->check(raftgpu_enqueue_append_resp(arena_->raw(), ring, &r, 1), "enqueue_append_resp");
     }
     // one batched pass; returns how many groups advanced their commit index
@@ -525,13 +539,13 @@ class MultiRaftDriver {
                               uint64_t next_probe_index = 0, uint64_t request_snapshot = INVALID_INDEX) {
         const auto slot = prs.slot_of(from);
         if (!slot) throw StepPeerNotFound();  // raw_node.rs:402-411
-        tick_.push_back({prs.group(), static_cast<uint8_t>(*slot), static_cast<uint8_t>(reject ? RAFTGPU_REC_REJECT : 0), 0, index, commit});
-        if (reject) tick_.push_back({prs.group(), static_cast<uint8_t>(*slot), RAFTGPU_REC_EXT, 0, next_probe_index, request_snapshot});
+        tick_.push_back({prs.record_group(*slot), prs.record_slot(*slot), static_cast<uint8_t>(reject ? RAFTGPU_REC_REJECT : 0), 0, index, commit});
+        if (reject) tick_.push_back({prs.record_group(*slot), prs.record_slot(*slot), RAFTGPU_REC_EXT, 0, next_probe_index, request_snapshot});
     }
     void push_local_progress(const ProgressTracker &prs, uint64_t self_id, uint64_t persisted, uint64_t last_index) {
         const auto slot = prs.slot_of(self_id);
         if (!slot) throw StepPeerNotFound();
-        tick_.push_back({prs.group(), static_cast<uint8_t>(*slot), RAFTGPU_REC_LOCAL, 0, persisted, last_index});
+        tick_.push_back({prs.record_group(*slot), prs.record_slot(*slot), RAFTGPU_REC_LOCAL, 0, persisted, last_index});
     }
     raftgpu_step_result step_tick(uint32_t flags = RAFTGPU_STEP_READ_COMMITTED) {
         raftgpu_step_result res{};

@@ -390,6 +390,63 @@ static void test_errors() {
     CHECK(!f.prs.get(42).has_value(), "get(unknown) is None");
 }
 
+// More than 8 peers: the reference sorts any number of voters (majority.rs:86-93); here the group is a WIDE one.
+// A joint change between two disjoint 5-voter sets (ids 1..5 -> 6..10) plus a learner (11), leader = 1: an index is
+// committed only when a majority of BOTH sets holds it (joint.rs:47-51).
+static void test_wide_group() {
+    Arena &a = *g_arena;
+    {   // free-standing quorum functions over 11 and 13 ids (a wide scratch group)
+        AckIndexer l;
+        for (uint64_t id = 1; id <= 11; id++) l[id] = Index{id * 10, 0};
+        const auto r = MajorityConfig({1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11}).committed_index(a, false, l);
+        CHECK(r.first == 60, "11 voters [10..110] -> %llu, want 60", (unsigned long long)r.first);   // the 6th largest
+        const auto j = JointConfig(MajorityConfig({1, 2, 3, 4, 5, 6, 7}), MajorityConfig({8, 9, 10, 11, 12, 13})).committed_index(a, false, l);
+        // incoming: 4th largest of [70..10] = 40; outgoing (12 and 13 never acked): 4th largest of [110,100,90,80,0,0] = 80
+        CHECK(j.first == 40, "joint (1..7)x(8..13) -> %llu, want 40", (unsigned long long)j.first);
+    }
+    ProgressTracker prs(g_arena, 256, /*wide=*/true);
+    LeaderLog log(g_arena, prs);
+    prs.set_self(1);
+    Configuration conf;
+    MapChange changes;
+    std::set<uint64_t> in, out;
+    for (uint64_t id = 1; id <= 11; id++) {
+        changes.emplace_back(id, MapChangeType::Add);
+        if (id <= 5) in.insert(id);
+        else if (id <= 10) out.insert(id);
+    }
+    conf.voters = JointConfig(MajorityConfig(in), MajorityConfig(out));
+    conf.learners.insert(11);
+    prs.apply_conf(conf, changes, 1);
+    log.reset(2, 0, 2);
+    log.become_leader();
+    log.set_log_bounds(2, 3);
+    for (uint64_t id = 2; id <= 11; id++) prs.get_mut(id)->become_replicate();
+    MultiRaftDriver drv(g_arena);
+    drv.push_local_progress(prs, 1, 3, 3);
+    for (uint64_t id : {2, 3, 6, 7}) drv.push_append_response(prs, id, 3, 0);
+    drv.push_append_response(prs, 11, 3, 0);  // the learner's ack does not count
+    raftgpu_step_result r = drv.step_tick();
+    CHECK(r.n_advanced == 0 && log.committed() == 0, "3 of the incoming set but 2 of the outgoing: nothing commits (committed = %llu)", (unsigned long long)log.committed());
+    CHECK(prs.get(7)->matched == 3 && prs.get(11)->matched == 3, "acks of peers in the high half land");
+    drv.push_append_response(prs, 9, 3, 0);   // peer slot 8: the first cell of the high half
+    r = drv.step_tick();
+    CHECK(r.n_advanced == 1 && log.committed() == 3 && drv.advanced(prs.group()), "third ack of the outgoing set commits 3 (committed = %llu)", (unsigned long long)log.committed());
+    CHECK(prs.maximal_committed_index().first == 3, "maximal_committed_index over 10 voters");
+    CHECK(prs.has_quorum({1, 2, 3, 6, 7, 9}) && !prs.has_quorum({1, 2, 3, 4, 5, 6, 7}), "has_quorum needs both majorities");
+    bool threw = false;
+    try {
+        MapChange more;
+        Configuration c2 = conf;
+        for (uint64_t id = 12; id <= 17; id++) {
+            more.emplace_back(id, MapChangeType::Add);
+            c2.learners.insert(id);
+        }
+        prs.apply_conf(c2, more, 1);
+    } catch (const Error &e) { threw = e.status == RAFTGPU_ERR_TOO_MANY_PEERS; }
+    CHECK(threw, "a 17th peer -> RAFTGPU_ERR_TOO_MANY_PEERS");
+}
+
 int main() {
     try {
         g_arena = Arena::create(0, 4096);
@@ -410,6 +467,7 @@ int main() {
     test_tick_batch_and_send_list();
     test_quorum_activity();
     test_errors();
+    test_wide_group();
     std::printf("%s: %d checks, %d failed\n", g_failed ? "FAILED" : "ok", g_checks, g_failed);
     g_arena.reset();
     return g_failed ? 1 : 0;

@@ -6,6 +6,8 @@ test_oracle_golden.py this is what "parity pinned" means for oracle/.
 """
 import ctypes as C
 
+import random
+
 import numpy as np
 import pytest
 
@@ -526,3 +528,52 @@ def test_arena_inflights_follow_the_messages():
     rej = rec(0, 1, 9, reject=True, hint=5)
     O.arena_apply(c, rej, mode=0)                                                         # Replicate -> Probe: ins.reset()
     assert (c.pflags[1, 0] & 3) == PROBE and c.ins_meta[1, 0] == 0
+
+
+def test_wide_groups_in_the_arena_view_equal_the_id_list_functions():
+    """A wide group (two consecutive slots, RO_META_WIDE_LO / _HI) in the arena view against the oracle's own
+    id-list functions (majority.rs / joint.rs restated for any number of voters): committed index, group commit,
+    vote result, and Raft::maybe_commit writing both halves."""
+    rng = random.Random(77)
+    WIDE_LO, WIDE_HI = 0x20000000, 0x40000000
+    for it in range(200):
+        c = O.new_columns(4, 4)
+        inc, out = rng.randrange(1, 1 << 16), rng.choice([0, rng.randrange(0, 1 << 16)])
+        learn = rng.randrange(0, 1 << 16) & ~(inc | out) if rng.random() < 0.3 else 0
+        gc = rng.random() < 0.4
+        voters = [s for s in range(16) if (inc | out) >> s & 1]
+        self_slot = rng.choice(voters)
+        for h in (0, 1):
+            c.meta[2 + h] = O.make_meta((inc >> 8 * h) & 0xff, (out >> 8 * h) & 0xff, (learn >> 8 * h) & 0xff,
+                                        self_slot - 8 * h if self_slot // 8 == h else None, group_commit=gc) | (WIDE_HI if h else WIDE_LO)
+        lookup, votes_by_id = {}, {}
+        votes = np.zeros((8, 4), dtype=np.uint8)
+        for s in range(16):
+            m, gid = rng.randrange(0, 60), rng.randrange(0, 3)
+            c.matched[s & 7, 2 + (s >> 3)], c.commit_group_id[s & 7, 2 + (s >> 3)] = m, gid
+            if (inc | out | learn) >> s & 1:
+                lookup[s + 1] = (m, gid)
+            v = rng.randrange(0, 3)
+            votes[s & 7, 2 + (s >> 3)] = v
+            if v:
+                votes_by_id[s + 1] = v == 2
+        a = [s + 1 for s in range(16) if inc >> s & 1]
+        b = [s + 1 for s in range(16) if out >> s & 1]
+        full = {i: lookup.get(i, (0, 0)) for i in set(a) | set(b)}
+        want = O.joint_committed_index(a, b, full, gc)
+        assert tuple(O.arena_mci(c, 2)) == tuple(want), (it, a, b)
+        gr, rj, res = O.arena_vote_result(c, votes, 2)
+        assert res == O.joint_vote_result(a, b, votes_by_id)
+        assert O.arena_vote_result(c, votes, 3) == (gr, rj, res)          # the high half reports the group's result
+        assert gr == sum(1 for i, v in votes_by_id.items() if v and i in full)
+        # maybe_commit: log bounds on one half only (a LOCAL record wrote there), commit index lands on both
+        c.term_start[2] = c.term_start[3] = 1
+        c.last_index[2 + (self_slot >> 3)] = 100
+        adv, bm, _, _ = O.arena_recompute(c)
+        mci = want[0]
+        if 0 < mci <= 100:
+            assert adv == 1 and bm[0] == 0b100
+            assert c.committed[2] == c.committed[3] == mci and c.last_index[2] == c.last_index[3] == 100
+            assert c.peer_committed[self_slot & 7, 2 + (self_slot >> 3)] == mci
+        else:
+            assert adv == 0 and bm[0] == 0

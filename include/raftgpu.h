@@ -356,7 +356,8 @@ int32_t raftgpu_maybe_commit(raftgpu_arena *arena, uint32_t group, int32_t *out_
  * Asynchronous on `stream`.  d_adv_bitmap (device, u32 words indexed by
  * group >> 5 from group 0; may be NULL) gets bit g set iff group g advanced;
  * d_commit_out (device u64 [cap], may be NULL) gets the new committed index of
- * advanced groups; d_mci_out / d_gc_out (may be NULL) get maximal_committed_index
+ * advanced groups (entries of other groups are unspecified: the fused step kernels
+ * copy every group's commit index there, this pass only the advanced ones); d_mci_out / d_gc_out (may be NULL) get maximal_committed_index
  * for every group. */
 int32_t raftgpu_recompute(raftgpu_arena *arena, void *stream, uint32_t first, uint32_t n,
                           uint32_t *d_adv_bitmap, uint64_t *d_commit_out, uint64_t *d_mci_out,
@@ -546,6 +547,16 @@ int32_t raftgpu_step_slot_results(raftgpu_arena *arena, const uint8_t **results,
  * counted in n_duplicates, raftgpu_step_wait returns RAFTGPU_ERR_INVALID); `records` stays untouched until the
  * step's raftgpu_step_wait returns. */
 #define RAFTGPU_STEP_RAW 0x8u
+/* raftgpu_step_begin_records only, `records` in PINNED host memory (ignored otherwise, and with RAFTGPU_STEP_RAW or
+ * RAFTGPU_STEP_READ_RESULTS): HYBRID staging.  Packing costs host CPU time, the raw form costs PCIe time; with few
+ * staging threads per GPU (eight GPUs share the host's cores) neither alone keeps up.  The library packs the first
+ * part of the batch (cut at a group boundary) into the compact stream while the DMA engine ships the rest as 24-byte
+ * records straight from the caller's buffer, sized so that both finish together (model: RAFTGPU_HYBRID_PACK_NS per
+ * record and thread, default 7.6; RAFTGPU_HYBRID_PCIE_GBS, default 50; or RAFTGPU_HYBRID_PACK_PCT to fix the
+ * split).  On the device the raw part goes through the scatter kernel (one record per cell, verified), then the
+ * fused kernel applies the packed part and recomputes every group.  `records` must stay untouched until
+ * raftgpu_step_wait returns. */
+#define RAFTGPU_STEP_HYBRID 0x10u
 int32_t raftgpu_step_begin(raftgpu_arena *arena, uint32_t flags);
 int32_t raftgpu_step_wait(raftgpu_arena *arena, raftgpu_step_result *out);
 int32_t raftgpu_step(raftgpu_arena *arena, uint32_t flags, raftgpu_step_result *out);

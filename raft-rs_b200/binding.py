@@ -33,7 +33,7 @@ PF_STATE_MASK, PF_PAUSED, PF_RECENT_ACTIVE, PF_INS_FULL = 0x03, 0x04, 0x08, 0x10
 META_HAS_SELF, META_GROUP_COMMIT = 0x08000000, 0x10000000
 REC_REJECT, REC_LOCAL, REC_HEARTBEAT, REC_EXT = 0x01, 0x02, 0x04, 0x80
 RES_OK, RES_OLD_PAUSED, RES_NO_PROGRESS, RES_SEND = 0x01, 0x02, 0x04, 0x08
-STEP_READ_COMMITTED, STEP_READ_RESULTS, STEP_ASYNC, STEP_RAW = 0x1, 0x2, 0x4, 0x8
+STEP_READ_COMMITTED, STEP_READ_RESULTS, STEP_ASYNC, STEP_RAW, STEP_HYBRID = 0x1, 0x2, 0x4, 0x8, 0x10
 BULK_SORTED = 0x1
 (POP_MAYBE_UPDATE, POP_MAYBE_DECR_TO, POP_UPDATE_COMMITTED, POP_OPTIMISTIC_UPDATE, POP_BECOME_PROBE,
  POP_BECOME_REPLICATE, POP_BECOME_SNAPSHOT, POP_SNAPSHOT_FAILURE, POP_MAYBE_SNAPSHOT_ABORT, POP_IS_PAUSED,

@@ -81,6 +81,8 @@ struct StagingSet {
     uint8_t *d_wire = nullptr;   // also the device copy of a RAFTGPU_STEP_RAW batch
     uint64_t d_wire_cap = 0;
     uint64_t wire_n = 0;             // frames of the wire step this set carried (0 = not a wire step)
+    uint64_t raw_n = 0;              // RAFTGPU_STEP_HYBRID: 24-byte records of this step that sit in d_wire as they are
+    uint32_t raw_min_group = 0;      // ... all of groups >= this one (the packed part ends below it)
     // sync
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
     bool in_flight = false;
@@ -216,6 +218,7 @@ struct raftgpu_arena {
     uint64_t overflow_records = 0;
     uint32_t voter_hint = 0;                 // superset of every group's voter slots (recompute_kernel)
     int grid_recompute = 0, grid_recompute5 = 0, grid_apply = 0;  // persistent grid sizes (blocks)
+    double hyb_pack_ns = 0.0;                // RAFTGPU_STEP_HYBRID: measured packing cost (ns per record and staging thread), 0 = not measured yet
     bool rec_fallback_sorted = false;        // raftgpu_step_begin_records: the batch going to the general staging path is in group order
     uint32_t n_wide = 0;                     // wide groups (two slots each): the fused tile kernels are not used while any exist
     uint32_t n_simple5 = 0;                  // groups whose meta is the plain 5-voter configuration

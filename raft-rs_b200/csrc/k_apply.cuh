@@ -290,7 +290,9 @@ template <bool kPacked, bool kCheckDup = false, bool kPrefetch = false>
 __global__ void __launch_bounds__(256, 4)
 apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__restrict__ results,
              unsigned long long *__restrict__ counters, uint32_t *__restrict__ touched = nullptr,
-             uint32_t *__restrict__ dup_count = nullptr) {
+             uint32_t *__restrict__ dup_count = nullptr, uint32_t min_group = 0) {
+    // (kCheckDup: a record of a group below min_group is refused like a duplicate -- the hybrid step promises that
+    //  its raw part only holds groups above its packed part)
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
     uint32_t local[5] = {0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress
     uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -306,7 +308,7 @@ apply_kernel(Columns c, const void *__restrict__ recs, uint64_t n, uint8_t *__re
             const uint32_t g = static_cast<uint32_t>(rec_a.w0), slot = static_cast<uint32_t>(rec_a.w0 >> 32) & 0xffu;
             if (!((rec_a.w0 >> 40) & RAFTGPU_REC_EXT) && g < c.cap && slot < kSlots) {
                 const uint32_t bit = 1u << (8 * (g & 3u) + slot);
-                if (atomicOr(&touched[g >> 2], bit) & bit) {  // second record for this cell in one wave
+                if (g < min_group || (atomicOr(&touched[g >> 2], bit) & bit)) {  // second record for this cell in one wave
                     atomicAdd(dup_count, 1u);
                     if (results) results[i] = 0;
                     rec_a = rec_b;

@@ -33,6 +33,16 @@ constexpr uint32_t kFDefer = 32;                 // deferred (rare-path) records
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
+// A consumer's wait for "stage armed for MY tile, and its loads have landed" (see s_stage_tile in the kernels): a
+// parity wait can pass while the stage still belongs to the tile before mine, so wait until the stage names my tile
+// -- from then on its barrier is in my phase (or past it) and the final parity wait is exact.
+__device__ __forceinline__ void wait_stage(uint64_t *full_bar, uint32_t parity, const uint32_t *stage_tile, uint32_t tile) {
+    for (;;) {
+        mbar_wait(full_bar, parity);
+        if (*reinterpret_cast<const volatile uint32_t *>(stage_tile) == tile) break;
+    }
+    mbar_wait(full_bar, parity);
+}
 // 1-D TMA store: shared -> global, tracked by the per-thread bulk async-group
 __device__ __forceinline__ void tma_store_1d(void *dst, const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
@@ -71,6 +81,12 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
     __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];  // rows read by the stores (store warp -> load warp)
     __shared__ uint32_t s_defer[32][kFDefer];                 // per warp: tile-relative indexes of its rare-path records
     __shared__ uint32_t s_ndefer[32];
+    // Which tile a stage is armed for.  A consumer group sees only every kNG-th tile, so on one stage's barrier it
+    // skips phases -- and a parity wait is only meaningful when the waiter is at most ONE phase ahead: a group that
+    // is done with a light tile early could pass `full_bar` of a stage whose PREVIOUS tile has not even landed
+    // (loads complete out of order when tiles differ in weight, e.g. a batch that covers only some of the groups).
+    // The load warp therefore names the tile before it arms the stage, and a consumer waits until it reads its own.
+    __shared__ uint32_t s_stage_tile[kFMaxStages];
 
     const uint32_t hint = kSimple5 ? 0x1fu : (a.hint & 0xffu);
     const uint32_t H = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint));
@@ -86,6 +102,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             mbar_init(&full_bar[s], 1);
             mbar_init(&done_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            s_stage_tile[s] = 0xffffffffu;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -94,7 +111,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
     uint32_t local[7] = {0, 0, 0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress | recomputes, advanced
     if (warp == kNG * kCT / 32 + 1) {
         // ===================== store warp: rows back to HBM, then the stage is free =====================
-        const uint32_t n_out = 4u * H + 2u;
+        const uint32_t n_out = 4u * H + 2u + (a.commit_out ? 1u : 0u);
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
             const int st = it % a.n_stages;
@@ -120,8 +137,10 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                     if (col == 3) tma_store_1d(c.pflags + cell, sb + o_flags + r * kFRow8, ng16);
                 } else if (j == 4u * H) {
                     tma_store_1d(c.committed + g0, sb + o_committed, ng16 * 8u);
-                } else {
+                } else if (j == 4u * H + 1u) {
                     tma_store_1d(c.last_index + g0, sb + o_li, ng16 * 8u);
+                } else {  // the step's commit-index output: the tile's `committed` row, one dense copy (not 8-byte scatters)
+                    tma_store_1d(a.commit_out + g0, sb + o_committed, ng16 * 8u);
                 }
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -151,6 +170,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             const uint32_t staged = rend - rbeg < kFRecCap ? rend - rbeg : kFRecCap;
             if (lane == 0) {
                 mbar_wait(&empty_bar[st], ph ^ 1u);
+                *reinterpret_cast<volatile uint32_t *>(&s_stage_tile[st]) = tile;  // (released by the arrive below)
                 mbar_expect_tx(&full_bar[st], 3u * H * ng16 * 8u + H * ng16 + 3u * ng16 * 8u + ng16 * 4u + staged * 16u);
             }
             __syncwarp();
@@ -223,7 +243,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             if (staged == 0 && tid < cnt) q_next = g_recs[tid];
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
             if (a.dbg && tid == 0) t0 = clock64();
-            mbar_wait(&full_bar[st], ph);
+            wait_stage(&full_bar[st], ph, &s_stage_tile[st], tile);
             if (a.dbg && tid == 0) t1 = clock64();
 
             // ---- A: the tile's records against the shared-memory rows (raft.rs:1663-1743)
@@ -435,8 +455,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
                     eval_mci<kSimple5>(c, g, meta, v, hint, mci, use_gc);
                     advanced = mci > s_committed[gl] && mci >= s_ts[gl] && mci <= s_li[gl];  // raft_log.rs:488
                     if (advanced) {
-                        s_committed[gl] = mci;
-                        if (a.commit_out) a.commit_out[g] = mci;
+                        s_committed[gl] = mci;  // (the store warp copies the row to commit_out too)
                         if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
                             const uint32_t self = RAFTGPU_META_SELF(meta);
                             uint64_t *pc = ((hint >> self) & 1u)

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
     __shared__ __align__(8) uint64_t full_bar[kFMaxStages];
     __shared__ __align__(8) uint64_t done_bar[kFMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];
+    __shared__ uint32_t s_stage_tile[kFMaxStages];  // which tile a stage is armed for (see step_tile_kernel)
 
     const uint32_t hint = kSimple5 ? 0x1fu : (a.hint & 0xffu);
     const uint32_t H = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint));
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
             mbar_init(&full_bar[s], 1);
             mbar_init(&done_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            s_stage_tile[s] = 0xffffffffu;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
     uint32_t local[7] = {0, 0, 0, 0, 0, 0, 0};  // records, updates, rejects, decrements, no_progress | recomputes, advanced
     if (warp == kNG * kCT / 32 + 1) {
         // ===================== store warp =====================
-        const uint32_t n_out = 4u * H + 2u;
+        const uint32_t n_out = 4u * H + 2u + (a.commit_out ? 1u : 0u);
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
             const int st = it % a.n_stages;
@@ -205,8 +207,10 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
                     if (col == 3) tma_store_1d(c.pflags + cell, sb + o_flags + r * kFRow8, ng16);
                 } else if (j == 4u * H) {
                     tma_store_1d(c.committed + g0, sb + o_committed, ng16 * 8u);
-                } else {
+                } else if (j == 4u * H + 1u) {
                     tma_store_1d(c.last_index + g0, sb + o_li, ng16 * 8u);
+                } else {  // the step's commit-index output: the tile's `committed` row, one dense copy (not 8-byte scatters)
+                    tma_store_1d(a.commit_out + g0, sb + o_committed, ng16 * 8u);
                 }
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
             const uint32_t staged = u1 > u0 ? (cnt4 < a.unit_cap ? cnt4 : a.unit_cap) : 0u;
             if (lane == 0) {
                 mbar_wait(&empty_bar[st], ph ^ 1u);
+                *reinterpret_cast<volatile uint32_t *>(&s_stage_tile[st]) = tile;  // (released by the arrive below)
                 mbar_expect_tx(&full_bar[st], 3u * H * ng16 * 8u + H * ng16 + 3u * ng16 * 8u + ng16 * 4u + staged * 4u);
             }
             __syncwarp();
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
             const uint32_t blk0 = ua / RAFTGPU_COMPACT_BLOCK;
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
             if (a.dbg && tid == 0) t0 = clock64();
-            mbar_wait(&full_bar[st], ph);
+            wait_stage(&full_bar[st], ph, &s_stage_tile[st], tile);
             if (a.dbg && tid == 0) t1 = clock64();
 
             // ---- 0: first run header of every group of the tile.  The g_base words of the (at most
@@ -522,8 +527,7 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
                     eval_mci<kSimple5>(c, g, meta, v, hint, mci, use_gc);
                     advanced = mci > t.committed[gl] && mci >= t.ts[gl] && mci <= t.li[gl];  // raft_log.rs:488
                     if (advanced) {
-                        t.committed[gl] = mci;
-                        if (a.commit_out) a.commit_out[g] = mci;
+                        t.committed[gl] = mci;  // (the store warp copies the row to commit_out too)
                         if (meta & RAFTGPU_META_HAS_SELF) {  // raft.rs:896-900
                             const uint32_t self = RAFTGPU_META_SELF(meta);
                             uint64_t *pc = ((hint >> self) & 1u)

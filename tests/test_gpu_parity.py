@@ -1471,3 +1471,124 @@ def test_raw_record_steps_match_the_packed_ones():
     assert r.status == B.ERR_INVALID and r.n_duplicates >= 1
     a1.close()
     a2.close()
+
+
+def test_hybrid_record_steps_split_between_packer_and_dma(monkeypatch):
+    """RAFTGPU_STEP_HYBRID: the head of the batch through the host packer + fused kernel, the tail over PCIe as it is
+    + scatter kernel, for several splits (0 % = everything raw, 100 % = nothing), synchronous and asynchronous: results
+    identical to the oracle's; the bytes that crossed PCIe add up; a batch that is not in group order is refused on the
+    device (the two parts must not share a group); pageable records ignore the flag."""
+    n = 200_000
+    synth = B.Synth(n, 0x0AB2, k_peers=5)
+    a = B.Arena(n)
+    assert a.group_alloc_range(n) == 0
+    a.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    buf = a.host_alloc_bytes(24 * (5 * n + 64)).view(B.APPEND_RESP_DTYPE)       # pinned
+    seen_split = 0
+    for rnd, (pct, extra) in enumerate([("40", 0), ("0", 0), ("100", 0), ("75", B.STEP_ASYNC), (None, B.STEP_ASYNC), ("55", 0)]):
+        if pct is None:
+            monkeypatch.delenv("RAFTGPU_HYBRID_PACK_PCT", raising=False)      # the library's own model
+        else:
+            monkeypatch.setenv("RAFTGPU_HYBRID_PACK_PCT", pct)
+        recs = synth.next_round()
+        k = len(recs)
+        buf[:k] = recs
+        a.step_begin_records(buf[:k], B.STEP_READ_COMMITTED | B.STEP_HYBRID | extra)
+        r = a.step_wait()
+        O.arena_apply(ref, recs, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        assert r.n_advanced == want_adv and r.n_duplicates == 0, (rnd, pct)
+        assert np.count_nonzero((recs["flags"] & B.REC_EXT) == 0) <= r.n_records <= k, (rnd, r.n_records, k)
+        if pct == "0":
+            assert r.h2d_bytes >= 24 * k
+        elif pct == "100":
+            assert r.h2d_bytes < 8 * k
+        elif pct is not None:
+            raw = (1 - int(pct) / 100) * 24 * k
+            assert 0.9 * raw < r.h2d_bytes < raw + 8 * k, (pct, r.h2d_bytes, k)
+            seen_split += 1
+        bm, com = a.step_results(n)
+        assert np.array_equal(bm, want_bm[: len(bm)]), (rnd, pct)
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+        assert_columns_equal(a.read_columns(n), ref, n, f"hybrid round {rnd} ({pct} % packed)")
+    assert seen_split == 3
+    # pageable records: the flag is ignored, the step is the ordinary one
+    monkeypatch.setenv("RAFTGPU_HYBRID_PACK_PCT", "50")
+    recs = synth.next_round().copy()
+    a.step_begin_records(recs, B.STEP_HYBRID)
+    r = a.step_wait()
+    O.arena_apply(ref, recs, mode=0)
+    O.arena_recompute(ref)
+    assert r.h2d_bytes < 8 * len(recs)
+    assert_columns_equal(a.read_columns(n), ref, n, "pageable + hybrid")
+    # the two halves of the batch swapped: the raw part now holds groups below the packed part's -> refused
+    recs = synth.next_round()
+    k = len(recs)
+    h = k // 2
+    while recs["group"][h] == recs["group"][h - 1] or recs["flags"][h] & B.REC_EXT:
+        h += 1
+    buf[: k - h] = recs[h:]
+    buf[k - h: k] = recs[:h]
+    a.step_begin_records(buf[:k], B.STEP_HYBRID)
+    r = a.step_wait(check=False)
+    assert r.status == B.ERR_INVALID and r.n_duplicates >= 1
+    a.close()
+
+
+def test_batches_that_cover_only_some_groups_at_full_size():
+    """A tick in which only part of the store's groups have traffic -- the first 5 % of the groups, every seventh tile,
+    a random 2 % -- at 1M groups, through both fused kernels (records API -> compact stream, and packed records + tile
+    index, device resident).  Light (record-less) tiles finish early and their loads land out of order with the heavy
+    ones: the consumers of the TMA ring must still pair every stage with its own tile (this hung / corrupted results
+    before the ring named the tile a stage is armed for).  Several rounds each: the failure was intermittent."""
+    n = 1_000_000
+    synth = B.Synth(n, 0x5A7E, k_peers=5)
+    arenas = [B.Arena(n), B.Arena(n)]
+    for a in arenas:
+        assert a.group_alloc_range(n) == 0
+        a.load_columns(synth.initial)
+    ref = O.copy_columns(synth.initial)
+    rng = np.random.default_rng(5)
+    pk = np.zeros((6 * n, 2), dtype=np.uint64)
+    d_pk, d_off = arenas[1].device_alloc(pk.nbytes), arenas[1].device_alloc(4 * (n // B.tile_groups() + 2))
+    d_bm = arenas[1].device_alloc(4 * (n // 32 + 1))
+    words = (n + 31) // 32
+    for rnd in range(8):
+        recs = synth.next_round()
+        g = recs["group"]
+        if rnd % 4 == 0:
+            keep = g < n // 20
+        elif rnd % 4 == 1:
+            keep = (g // 256) % 7 == 0
+        elif rnd % 4 == 2:
+            chosen = rng.random(n) < 0.02
+            keep = chosen[g]
+        else:
+            keep = g >= n - n // 50
+        part = np.ascontiguousarray(recs[keep])
+        O.arena_apply(ref, part, mode=0)
+        want_adv, want_bm, _, _ = O.arena_recompute(ref)
+        a = arenas[0]
+        a.step_begin_records(part, B.STEP_READ_COMMITTED)
+        r = a.step_wait()
+        assert r.n_advanced == want_adv and r.n_duplicates == 0, rnd
+        bm, com = a.step_results(n)
+        assert np.array_equal(bm[:words], want_bm[:words]), rnd
+        adv = bitmap_to_bool(bm, n)
+        assert np.array_equal(com[adv], ref.committed[:n][adv])
+        a = arenas[1]
+        k = a.pack_records(part, pk)
+        a.h2d(d_pk, pk[: max(k, 1)])
+        a.h2d(d_off, B.tile_index(pk, k, n))
+        a.step_sorted_device(d_pk, k, d_off, d_adv=d_bm)
+        got_bm = np.zeros(words, dtype=np.uint32)
+        a.d2h(got_bm, d_bm)
+        assert np.array_equal(got_bm, want_bm[:words]), rnd
+        for a, name in zip(arenas, ("records api", "packed device")):
+            got = a.read_columns(n)
+            for col in ("matched", "next_idx", "peer_committed", "pflags", "committed", "last_index"):
+                assert checksum(getattr(got, col)) == checksum(getattr(ref, col)[..., :n]), (name, rnd, col)
+    for a in arenas:
+        a.close()

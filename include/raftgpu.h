@@ -552,7 +552,7 @@ int32_t raftgpu_step_slot_results(raftgpu_arena *arena, const uint8_t **results,
  * staging threads per GPU (eight GPUs share the host's cores) neither alone keeps up.  The library packs the first
  * part of the batch (cut at a group boundary) into the compact stream while the DMA engine ships the rest as 24-byte
  * records straight from the caller's buffer, sized so that both finish together (model: RAFTGPU_HYBRID_PACK_NS per
- * record and thread, default 7.6; RAFTGPU_HYBRID_PCIE_GBS, default 50; or RAFTGPU_HYBRID_PACK_PCT to fix the
+ * record and thread, default: measured on every step; RAFTGPU_HYBRID_PCIE_GBS, default 54; or RAFTGPU_HYBRID_PACK_PCT to fix the
  * split).  On the device the raw part goes through the scatter kernel (one record per cell, verified), then the
  * fused kernel applies the packed part and recomputes every group.  `records` must stay untouched until
  * raftgpu_step_wait returns. */

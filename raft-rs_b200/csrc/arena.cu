@@ -109,6 +109,7 @@ struct RecJob {
     uint64_t stream_cap_units = 0;
     std::chrono::steady_clock::time_point t_begin;
     std::vector<double> tr_a, tr_b;
+    std::atomic<uint64_t> busy_ns{0};  // time the staging threads spent packing this job's slices (for the hybrid split)
     double us_since() const { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); }
 };
 

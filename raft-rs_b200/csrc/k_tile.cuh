@@ -33,14 +33,17 @@ constexpr uint32_t kFDefer = 32;                 // deferred (rare-path) records
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
-// A consumer's wait for "stage armed for MY tile, and its loads have landed" (see s_stage_tile in the kernels): a
-// parity wait can pass while the stage still belongs to the tile before mine, so wait until the stage names my tile
-// -- from then on its barrier is in my phase (or past it) and the final parity wait is exact.
-__device__ __forceinline__ void wait_stage(uint64_t *full_bar, uint32_t parity, const uint32_t *stage_tile, uint32_t tile) {
-    for (;;) {
-        mbar_wait(full_bar, parity);
-        if (*reinterpret_cast<const volatile uint32_t *>(stage_tile) == tile) break;
-    }
+// A consumer's wait for "the loads of MY tile have landed in this stage".  A consumer group sees only every kNG-th
+// tile, so on one stage's `full` barrier it skips phases -- and a parity wait is only exact while the waiter is at
+// most ONE phase ahead.  With uniform tiles that always holds; with a batch that covers only part of the groups it
+// does not (record-less tiles are done in a microsecond, loads of light and heavy tiles land out of order): a group
+// could pass the barrier of a stage still armed for the PREVIOUS tile and work on half-landed rows.  So it first
+// waits for the previous use of the stage to be DONE (`done` barrier, previous phase).  That wait is exact: the
+// group's own previous tile was loaded, hence the tile n_stages before IT was stored, stores happen in tile order,
+// and with n_stages >= kNG that covers the previous user of this stage; and once the previous user is done, the
+// `full` barrier is in this tile's phase, so the second wait is exact too.
+__device__ __forceinline__ void wait_stage(uint64_t *full_bar, uint64_t *done_bar, uint32_t parity) {
+    mbar_wait(done_bar, parity ^ 1u);  // (first use of a stage: the parity-1 wait on a fresh barrier passes at once)
     mbar_wait(full_bar, parity);
 }
 // 1-D TMA store: shared -> global, tracked by the per-thread bulk async-group
@@ -81,12 +84,6 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
     __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];  // rows read by the stores (store warp -> load warp)
     __shared__ uint32_t s_defer[32][kFDefer];                 // per warp: tile-relative indexes of its rare-path records
     __shared__ uint32_t s_ndefer[32];
-    // Which tile a stage is armed for.  A consumer group sees only every kNG-th tile, so on one stage's barrier it
-    // skips phases -- and a parity wait is only meaningful when the waiter is at most ONE phase ahead: a group that
-    // is done with a light tile early could pass `full_bar` of a stage whose PREVIOUS tile has not even landed
-    // (loads complete out of order when tiles differ in weight, e.g. a batch that covers only some of the groups).
-    // The load warp therefore names the tile before it arms the stage, and a consumer waits until it reads its own.
-    __shared__ uint32_t s_stage_tile[kFMaxStages];
 
     const uint32_t hint = kSimple5 ? 0x1fu : (a.hint & 0xffu);
     const uint32_t H = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint));
@@ -102,7 +99,6 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             mbar_init(&full_bar[s], 1);
             mbar_init(&done_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
-            s_stage_tile[s] = 0xffffffffu;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -170,7 +166,6 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             const uint32_t staged = rend - rbeg < kFRecCap ? rend - rbeg : kFRecCap;
             if (lane == 0) {
                 mbar_wait(&empty_bar[st], ph ^ 1u);
-                *reinterpret_cast<volatile uint32_t *>(&s_stage_tile[st]) = tile;  // (released by the arrive below)
                 mbar_expect_tx(&full_bar[st], 3u * H * ng16 * 8u + H * ng16 + 3u * ng16 * 8u + ng16 * 4u + staged * 16u);
             }
             __syncwarp();
@@ -243,7 +238,7 @@ __global__ void __launch_bounds__(kCT *kNG + 64, 1) step_tile_kernel(Columns c, 
             if (staged == 0 && tid < cnt) q_next = g_recs[tid];
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
             if (a.dbg && tid == 0) t0 = clock64();
-            wait_stage(&full_bar[st], ph, &s_stage_tile[st], tile);
+            wait_stage(&full_bar[st], &done_bar[st], ph);
             if (a.dbg && tid == 0) t1 = clock64();
 
             // ---- A: the tile's records against the shared-memory rows (raft.rs:1663-1743)

@@ -154,7 +154,6 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
     __shared__ __align__(8) uint64_t full_bar[kFMaxStages];
     __shared__ __align__(8) uint64_t done_bar[kFMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kFMaxStages];
-    __shared__ uint32_t s_stage_tile[kFMaxStages];  // which tile a stage is armed for (see step_tile_kernel)
 
     const uint32_t hint = kSimple5 ? 0x1fu : (a.hint & 0xffu);
     const uint32_t H = kSimple5 ? 5u : static_cast<uint32_t>(__popc(hint));
@@ -171,7 +170,6 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
             mbar_init(&full_bar[s], 1);
             mbar_init(&done_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
-            s_stage_tile[s] = 0xffffffffu;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -241,7 +239,6 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
             const uint32_t staged = u1 > u0 ? (cnt4 < a.unit_cap ? cnt4 : a.unit_cap) : 0u;
             if (lane == 0) {
                 mbar_wait(&empty_bar[st], ph ^ 1u);
-                *reinterpret_cast<volatile uint32_t *>(&s_stage_tile[st]) = tile;  // (released by the arrive below)
                 mbar_expect_tx(&full_bar[st], 3u * H * ng16 * 8u + H * ng16 + 3u * ng16 * 8u + ng16 * 4u + staged * 4u);
             }
             __syncwarp();
@@ -324,7 +321,7 @@ __global__ void __launch_bounds__(kFTile *kNG + 64, 1) step_tile_compact_kernel(
             const uint32_t blk0 = ua / RAFTGPU_COMPACT_BLOCK;
             long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
             if (a.dbg && tid == 0) t0 = clock64();
-            wait_stage(&full_bar[st], ph, &s_stage_tile[st], tile);
+            wait_stage(&full_bar[st], &done_bar[st], ph);  // (k_tile.cuh: exact although this group skips phases)
             if (a.dbg && tid == 0) t1 = clock64();
 
             // ---- 0: first run header of every group of the tile.  The g_base words of the (at most

@@ -1542,7 +1542,7 @@ def test_batches_that_cover_only_some_groups_at_full_size():
     a random 2 % -- at 1M groups, through both fused kernels (records API -> compact stream, and packed records + tile
     index, device resident).  Light (record-less) tiles finish early and their loads land out of order with the heavy
     ones: the consumers of the TMA ring must still pair every stage with its own tile (this hung / corrupted results
-    before the ring named the tile a stage is armed for).  Several rounds each: the failure was intermittent."""
+    before the consumers checked the previous use of a stage, wait_stage in k_tile.cuh).  Several rounds each: the failure was intermittent."""
     n = 1_000_000
     synth = B.Synth(n, 0x5A7E, k_peers=5)
     arenas = [B.Arena(n), B.Arena(n)]

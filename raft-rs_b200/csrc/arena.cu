@@ -219,6 +219,7 @@ struct raftgpu_arena {
     uint64_t overflow_records = 0;
     uint32_t voter_hint = 0;                 // superset of every group's voter slots (recompute_kernel)
     int grid_recompute = 0, grid_recompute5 = 0, grid_apply = 0;  // persistent grid sizes (blocks)
+    uint32_t hyb_samples = 0;
     double hyb_pack_ns = 0.0;                // RAFTGPU_STEP_HYBRID: measured packing cost (ns per record and staging thread), 0 = not measured yet
     bool rec_fallback_sorted = false;        // raftgpu_step_begin_records: the batch going to the general staging path is in group order
     uint32_t n_wide = 0;                     // wide groups (two slots each): the fused tile kernels are not used while any exist

@@ -392,7 +392,8 @@ int32_t raftgpu_step_sorted_device(raftgpu_arena *arena, void *stream, const voi
                                    uint64_t n_packed, const uint32_t *d_tile_off, uint8_t *d_results,
                                    uint32_t *d_adv_bitmap, uint64_t *d_commit_out);
 /* Host helper: out[t] for t = 0..n_tiles where n_tiles = ceil(n_groups / RAFTGPU_TILE_GROUPS)
- * (out has n_tiles + 1 entries).  RAFTGPU_ERR_INVALID if the records are not in group order. */
+ * (out has n_tiles + 1 entries).  RAFTGPU_ERR_INVALID if the records are not in group order,
+ * RAFTGPU_ERR_RANGE if one names a group >= n_groups (no tile would visit it). */
 int32_t raftgpu_tile_index(const raftgpu_packed_rec *packed, uint64_t n_packed, uint32_t n_groups,
                            uint32_t *out, uint64_t out_capacity);
 

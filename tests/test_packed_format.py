@@ -117,3 +117,9 @@ def test_tile_index():
     with pytest.raises(B.RaftGpuError):
         B.tile_index(np.ascontiguousarray(pk[::-1]), len(pk), n_groups)
     assert np.array_equal(B.tile_index(pk[:0], 0, n_groups), np.zeros(n_tiles + 1, dtype=np.uint32))
+    # a record of a group the arena does not have (no tile would visit it): refused, not dropped
+    recs2 = recs[-3:].copy()
+    recs2["group"] = [n_groups - 1, n_groups, n_groups + 7]
+    with pytest.raises(B.RaftGpuError) as e:
+        B.tile_index(pack(recs2), 3, n_groups)
+    assert e.value.status == B.ERR_RANGE

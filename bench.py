@@ -547,6 +547,8 @@ def main():
         gbs = alg_bytes / (ms_kernel * 1e-3) / 1e9
         tkey = "step_tile_kernel" + ("" if args.workload in ("cfg3", "cfg5", "cfg2") else "_" + args.workload)
         tr = traffic.get(tkey)
+        if tr and n != 1_000_000:
+            tr = int(tr * n / 1_000_000)   # the captures are of 1M-group launches; the kernel's traffic is linear in the groups
         dom = {"kernel": "step_tile_kernel", "avg_us": 1e3 * ms_kernel / K, "share": ms_kernel / ms_total,
                "alg_bytes_per_launch": alg_bytes / K, "achieved": gbs, "frac": gbs / peak_gbs, "traffic": tr}
         if tr:   # the honest bandwidth fraction: DRAM bytes the kernel really moves (ncu) / its duration
@@ -582,10 +584,11 @@ def main():
                 "api": "raftgpu_apply_device_packed + raftgpu_recompute: the general path, any arrival order (one record per "
                        "cell per call), no tile index"}
             ro_gbs = world * n * K * b_alg_recompute / (maxes["ro_ms"] * 1e-3) / 1e9
+            rkey = "recompute_kernel" + ("" if args.workload in ("cfg3", "cfg5", "cfg2") else "_" + args.workload)
             line["recompute_only"] = {
                 "value": world * n * K / (maxes["ro_ms"] * 1e-3), "unit": UNIT, "us_per_pass": 1e3 * maxes["ro_ms"] / K,
                 "bytes_per_recompute": b_alg_recompute, "achieved_gbs_per_gpu": ro_gbs / world,
-                "frac": ro_gbs / world / peak_gbs, "traffic": traffic.get("recompute_kernel"),
+                "frac": ro_gbs / world / peak_gbs, "traffic": (int(traffic[rkey] * n / 1_000_000) if traffic.get(rkey) else None),
                 "api": "raftgpu_recompute: Raft::maybe_commit for every group, nothing applied (BASELINE.md 3: rate x (8K+34) B)"}
         apis = {
             "e2e": "raftgpu_step_begin_records(READ_COMMITTED | ASYNC, or | RAW when `mode` is raw: no packing, the records cross "

@@ -206,8 +206,8 @@ __device__ __forceinline__ void group_mci(const Columns &c, uint32_t g, uint32_t
     for (int s = 0; s < kSlots; s++)
         v[s] = ((voters >> s) & 1u) ? c.matched[static_cast<size_t>(s) * c.cap + g] : 0ull;
     if (!(meta & RAFTGPU_META_GROUP_COMMIT)) {
-        const uint64_t i_idx = quorum_index(v, in);
-        const uint64_t o_idx = quorum_index(v, out);  // empty outgoing => u64::MAX
+        uint64_t i_idx, o_idx;
+        quorum_index_joint(v, in, out, i_idx, o_idx);  // quorum_select.h; empty outgoing => u64::MAX
         mci = umin64(i_idx, o_idx);                    // joint.rs:50
         // a non-empty half reports false (majority.rs:99-101), an empty one true (:71-75)
         use_gc = (in == 0) && (out == 0);

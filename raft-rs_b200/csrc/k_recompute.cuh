@@ -42,18 +42,22 @@ __device__ __forceinline__ void eval_mci(const Columns &c, uint32_t g, uint32_t 
             mci = median5(v[0], v[1], v[2], v[3], v[4]);
             use_gc = false;
         } else if (!(meta & RAFTGPU_META_GROUP_COMMIT)) {
-            const uint64_t i_idx = quorum_index(v, in);
-            const uint64_t o_idx = quorum_index(v, out);  // empty outgoing => u64::MAX
+            uint64_t i_idx, o_idx;
+            quorum_index_joint(v, in, out, i_idx, o_idx);  // both halves from one comparison pass; empty => u64::MAX
             mci = umin64(i_idx, o_idx);                    // joint.rs:50
             use_gc = (in == 0) && (out == 0);              // majority.rs:71-75 vs :99-101
         } else {
-            uint64_t gid[kSlots];
-            for (int s = 0; s < kSlots; s++)
+            // (a COPY of v goes to the out-of-line group-commit routine: taking v's own address would put it in local
+            //  memory for the common path too)
+            uint64_t vv[kSlots], gid[kSlots];
+            for (int s = 0; s < kSlots; s++) {
+                vv[s] = v[s];
                 gid[s] = ((voters >> s) & 1u) ? c.commit_group_id[static_cast<size_t>(s) * c.cap + g] : 0ull;
+            }
             uint64_t i_idx, o_idx;
             bool i_gc, o_gc;
-            majority_group_commit(v, gid, in, &i_idx, &i_gc);
-            majority_group_commit(v, gid, out, &o_idx, &o_gc);
+            majority_group_commit(vv, gid, in, &i_idx, &i_gc);
+            majority_group_commit(vv, gid, out, &o_idx, &o_gc);
             mci = umin64(i_idx, o_idx);
             use_gc = i_gc && o_gc;
         }

@@ -11,6 +11,7 @@
 
 #include "raftgpu.h"
 #include "wire_format.h"
+#include "quorum_select.h"
 
 namespace raftgpu {
 

@@ -121,3 +121,16 @@ def test_joint_properties_random():
         assert j == O.joint_committed_index(b, a, l)            # symmetry
         assert O.joint_committed_index(a, [], l)[0] == ia[0]    # zero-joint
         assert O.joint_committed_index(a, a, l)[0] == ia[0]     # self-joint
+
+
+def test_quorum_select_header_against_a_sort(tmp_path):
+    """raft-rs_b200/csrc/quorum_select.h (the joint quorum index the general kernels use: one comparison pass, two
+    masks) built for the HOST and compared with a plain sort over random values with many ties and every kind of mask
+    pair (scripts/micro/quorum_select_test.cpp).  The same code runs on the device."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "qs_test")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "raft-rs_b200", "csrc"),
+                    os.path.join(root, "scripts", "micro", "quorum_select_test.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe, "600"], capture_output=True, text=True)
+    assert out.returncode == 0 and "quorum select ok" in out.stdout, out.stdout + out.stderr

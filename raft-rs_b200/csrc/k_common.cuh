@@ -95,41 +95,9 @@ __device__ __forceinline__ bool ins_add(const Columns &c, size_t cell, uint64_t 
 // the q-th largest acked index of the voters in `mask`, q = n/2 + 1
 // (util.rs:118-120); the empty config yields u64::MAX (majority.rs:71-75).
 
-// compare-exchange, larger value first
-__device__ __forceinline__ void cex(uint64_t &a, uint64_t &b) {
-    const bool lt = a < b;
-    const uint64_t hi = lt ? b : a, lo = lt ? a : b;
-    a = hi;
-    b = lo;
-}
-
-// General form.  Non-members are zeroed, which leaves the top-q ranks of the
-// members intact (q <= n); a 19-comparator network sorts the 8 slots in
-// descending order (the reference's stable sort_by, majority.rs:95 -- ties are
-// equal values, so any order of them selects the same index) and the q-th
-// element is picked.
-__device__ __forceinline__ uint64_t quorum_index(const uint64_t (&v)[kSlots], uint32_t mask) {
-    if (mask == 0) return UINT64_MAX;
-    const uint32_t q = (static_cast<uint32_t>(__popc(mask)) >> 1) + 1;
-    uint64_t w0 = (mask & 1u) ? v[0] : 0, w1 = (mask & 2u) ? v[1] : 0, w2 = (mask & 4u) ? v[2] : 0,
-             w3 = (mask & 8u) ? v[3] : 0, w4 = (mask & 16u) ? v[4] : 0, w5 = (mask & 32u) ? v[5] : 0,
-             w6 = (mask & 64u) ? v[6] : 0, w7 = (mask & 128u) ? v[7] : 0;
-    // Batcher / optimal 19-comparator network for 8 inputs
-    cex(w0, w1); cex(w2, w3); cex(w4, w5); cex(w6, w7);
-    cex(w0, w2); cex(w1, w3); cex(w4, w6); cex(w5, w7);
-    cex(w1, w2); cex(w5, w6); cex(w0, w4); cex(w3, w7);
-    cex(w1, w5); cex(w2, w6);
-    cex(w1, w4); cex(w3, w6);
-    cex(w2, w4); cex(w3, w5);
-    cex(w3, w4);
-    // q in 1..5 for up to 8 voters
-    uint64_t r = w0;
-    r = q == 2 ? w1 : r;
-    r = q == 3 ? w2 : r;
-    r = q == 4 ? w3 : r;
-    r = q == 5 ? w4 : r;
-    return r;
-}
+// General form (any masks, joint configurations): quorum_index_joint in quorum_select.h -- the 8 slots are ordered
+// once as predecessor bit masks (28 compares) and the q-th largest member of each half is the member with q - 1
+// predecessors inside its mask.  (Until round 2 each half sorted the zero-padded slots with a 19-comparator network.)
 
 // The common 5-voter case (q = 3): the median, by the classic 10 min/max form
 // med5(a..e) = med3(e, max(min(a,b),min(c,d)), min(max(a,b),max(c,d))).

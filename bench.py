@@ -591,12 +591,12 @@ def main():
                 "frac": ro_gbs / world / peak_gbs, "traffic": (int(traffic[rkey] * n / 1_000_000) if traffic.get(rkey) else None),
                 "api": "raftgpu_recompute: Raft::maybe_commit for every group, nothing applied (BASELINE.md 3: rate x (8K+34) B)"}
         apis = {
-            "e2e": "raftgpu_step_begin_records(READ_COMMITTED | ASYNC, or | RAW when `mode` is raw: no packing, the records cross "
-                   "PCIe as they are) + raftgpu_step_wait: the step's 24-byte records "
-                   "(raftgpu_append_resp, what handle_append_response consumes) sit in pinned host memory "
-                   "(raftgpu_host_alloc); timed: the library's staging threads pack them into the compact stream, H2D "
-                   "slice by slice, tile index + fused apply/recompute kernel, D2H of the advanced bitmap and the new "
-                   "commit indexes; two steps in flight",
+            "e2e": "raftgpu_step_begin_records(READ_COMMITTED | ASYNC | HYBRID) + raftgpu_step_wait (`mode`: hybrid; packed = "
+                   "without HYBRID, raw = RAFTGPU_STEP_RAW): the step's 24-byte records (raftgpu_append_resp, what "
+                   "handle_append_response consumes) sit in pinned host memory (raftgpu_host_alloc); timed: the library's "
+                   "staging threads pack the head of the batch into the compact stream while the DMA engine ships the tail "
+                   "as it is (split so that both finish together), H2D, scatter apply of the raw part, tile index + fused "
+                   "apply/recompute kernel, D2H of the advanced bitmap and the commit indexes; two steps in flight",
             "e2e_prepacked": "raftgpu_step_begin_compact + raftgpu_step_wait: the caller already holds the batch as the "
                              "compact stream (raftgpu_pack_compact NOT timed): the PCIe-bound floor of the step",
             "e2e_wire": "raftgpu_step_begin_wire + raftgpu_step_wait: serialized eraftpb.Message frames in pinned host "

@@ -553,7 +553,7 @@ int32_t raftgpu_step_slot_results(raftgpu_arena *arena, const uint8_t **results,
  * staging threads per GPU (eight GPUs share the host's cores) neither alone keeps up.  The library packs the first
  * part of the batch (cut at a group boundary) into the compact stream while the DMA engine ships the rest as 24-byte
  * records straight from the caller's buffer, sized so that both finish together (model: RAFTGPU_HYBRID_PACK_NS per
- * record and thread, default: measured on every step; RAFTGPU_HYBRID_PCIE_GBS, default 54; or RAFTGPU_HYBRID_PACK_PCT to fix the
+ * record and thread, and RAFTGPU_HYBRID_PCIE_GBS: both measured on every step unless set; or RAFTGPU_HYBRID_PACK_PCT to fix the
  * split).  The batch must be in group order with at most ONE record per (group, peer) cell in its tail (a tick with
  * several acknowledgements per peer belongs to the plain form, whose fused kernel walks them in order); both are
  * verified on the device and a violation fails the step's raftgpu_step_wait.  The raw part goes through the scatter kernel, then the

@@ -85,6 +85,8 @@ struct StagingSet {
     uint32_t raw_min_group = 0;      // ... all of groups >= this one (the packed part ends below it)
     // sync
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_raw0 = nullptr, ev_raw1 = nullptr;  // around the hybrid step's raw H2D copy (timing: the effective PCIe rate)
+    uint64_t raw_timed_bytes = 0;                      // bytes of that copy, 0 = nothing to read back
     bool in_flight = false;
     std::atomic<bool> dirty{false};  // touched[] has bits set (set by any enqueueing thread)
     uint32_t flags = 0;
@@ -220,6 +222,7 @@ struct raftgpu_arena {
     uint32_t voter_hint = 0;                 // superset of every group's voter slots (recompute_kernel)
     int grid_recompute = 0, grid_recompute5 = 0, grid_apply = 0;  // persistent grid sizes (blocks)
     uint32_t hyb_samples = 0;
+    double hyb_pcie_gbs = 0.0;               // RAFTGPU_STEP_HYBRID: measured rate of the raw H2D copies (GB/s), 0 = not measured yet
     double hyb_pack_ns = 0.0;                // RAFTGPU_STEP_HYBRID: measured packing cost (ns per record and staging thread), 0 = not measured yet
     bool rec_fallback_sorted = false;        // raftgpu_step_begin_records: the batch going to the general staging path is in group order
     uint32_t n_wide = 0;                     // wide groups (two slots each): the fused tile kernels are not used while any exist
@@ -521,6 +524,8 @@ void free_set(StagingSet &s) {
     cudaFree(s.d_touched);
     cudaFree(s.d_wire);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_raw0) cudaEventDestroy(s.ev_raw0);
+    if (s.ev_raw1) cudaEventDestroy(s.ev_raw1);
     if (s.ev_compute) cudaEventDestroy(s.ev_compute);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
 }
@@ -724,6 +729,8 @@ int32_t create(int32_t device, uint32_t max_groups, uint32_t slots, uint32_t n_r
         TRY(dev_alloc(a, &s.d_step_adv, 4));
         TRY(dev_alloc(a, &s.d_touched, a->cap / 4));
         TRYC(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        TRYC(cudaEventCreate(&s.ev_raw0));
+        TRYC(cudaEventCreate(&s.ev_raw1));
         TRYC(cudaEventCreateWithFlags(&s.ev_compute, cudaEventDisableTiming));
         TRYC(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     }

@@ -9,16 +9,23 @@ from __future__ import annotations
 import numpy as np
 
 
-def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
-    """Contiguous block of groups owned by `rank`: stable group -> rank = g // ceil(n / world)."""
+def block_size(n_total: int, world: int) -> int:
+    """Groups per rank: ceil(n / world), rounded up to an EVEN count -- a wide group (include/raftgpu.h
+    raftgpu_group_alloc_wide) is two consecutive slots starting at an even one, so a block boundary must
+    neither split the pair nor change the parity of the rank-local slot numbers."""
     per = (n_total + world - 1) // world
+    return (per + 1) & ~1
+
+
+def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block of groups owned by `rank`: stable group -> rank = g // block_size."""
+    per = block_size(n_total, world)
     lo = min(n_total, rank * per)
     return lo, min(n_total, lo + per)
 
 
 def owner_of(groups: np.ndarray, n_total: int, world: int) -> np.ndarray:
-    per = (n_total + world - 1) // world
-    return (groups // per).astype(np.int64)
+    return (groups // block_size(n_total, world)).astype(np.int64)
 
 
 def route_records(recs: np.ndarray, n_total: int, world: int, rank: int) -> np.ndarray:

@@ -82,5 +82,10 @@ def test_shard_bounds_cover_exactly():
             spans = [S.shard_bounds(n, w, r) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            # every block starts on an even group: a wide group (two consecutive slots from an even one) is never
+            # split between ranks and keeps its parity after the rebase to rank-local slots
+            assert all(lo % 2 == 0 for lo, hi in spans if hi > lo)
     g = np.array([0, 1_249_999, 1_250_000, 9_999_999], dtype=np.uint32)
     assert S.owner_of(g, 10_000_000, 8).tolist() == [0, 0, 1, 7]
+    pair = np.array([7 * 142_858 - 2, 7 * 142_858 - 1], dtype=np.uint32)      # an even/odd pair near a block seam
+    assert len(set(S.owner_of(pair, 1_000_003, 7).tolist())) == 1

@@ -18,6 +18,24 @@ def test_library_exports_every_declared_symbol():
     assert sorted(L._signatures) == declared
 
 
+def test_synth_library_exports_every_symbol_of_its_header():
+    """include/raftgpu_synth.h (the bench's workload generator, its own library -- not part of the product .so)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "raftgpu_synth.h"), encoding="utf-8").read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(raftgpu_synth_[a-z0-9_]+)\s*\(", text)))
+    assert len(declared) >= 3
+    S = B.synth_lib()
+    missing = [s for s in declared if not hasattr(S, s)]
+    assert not missing, missing
+    # ... and none of them leaks into the product library
+    L = B.lib()
+    for s in declared:
+        with pytest.raises(AttributeError):
+            getattr(L, s)
+
+
 def test_abi_version_and_strerror():
     L = B.lib()
     assert L.raftgpu_abi_version() == 1

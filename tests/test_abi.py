@@ -101,3 +101,17 @@ def test_rust_stub_in_integration_md_is_generated_and_matches_the_header():
     # the Rust text itself: every struct carries its size assertion
     for name, (size, _) in lay.items():
         assert f"size_of::<{name}>() == {size}" in block, name
+
+
+@pytest.mark.parametrize("header", ["raftgpu.h", "raftgpu_synth.h"])
+def test_headers_are_plain_c(header, tmp_path):
+    """The boundary is a C-ABI: include/*.h must compile as C99 (what a cgo / bindgen / ctypes user feeds it to) and
+    as C++17, warnings as errors, with nothing but the standard headers."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text(f'#include "{header}"\nint main(void) {{ return 0; }}\n')
+    inc = "-I" + os.path.join(root, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", inc, "-fsyntax-only", "-x", "c++", str(src)], check=True)
